@@ -1,0 +1,103 @@
+"""The oracle (oracle/mudg_oracle.py) replayed against the golden vectors that
+oracle/make_golden.py produced from the UNCHANGED reference modules (CPU, fp32)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import torch
+
+from oracle import mudg_oracle as O
+
+
+def _digest(shapes):
+    h = hashlib.sha256()
+    for k in sorted(shapes):
+        h.update(f"{k}:{tuple(shapes[k])};".encode())
+    return h.hexdigest()
+
+
+def _meta(golden_dir):
+    with open(os.path.join(golden_dir, "meta.json")) as f:
+        return json.load(f)
+
+
+def test_full_size_state_dict_layout(golden_dir):
+    """Key names + shapes of the full-size UNet / VAE equal the reference's (pinned via strict load)."""
+    meta = _meta(golden_dir)
+    u = O.unet_param_shapes(O.UNetCfg())
+    assert len(u) == meta["unet_full"]["n_keys"] == 1520
+    assert int(sum(np.prod(s) for s in u.values())) == meta["unet_full"]["n_params"] == 1440917060
+    assert _digest(u) == meta["unet_full"]["digest"]
+    v = O.vae_param_shapes(O.VaeCfg())
+    assert _digest(v) == meta["vae_full"]["digest"]
+    # the typo'd attribute is part of the checkpoint layout (openaimodel3d.py:190)
+    assert "input_blocks.1.0.temopral_conv.conv1.2.weight" in u
+
+
+def test_unet_forward_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "unet_small.npz"))
+    cfg = O.UNetCfg(model_channels=64, temporal_length=4)
+    sd = O.seeded_state_dict(O.unet_param_shapes(cfg), seed=1)
+    t = lambda k: torch.from_numpy(g[k])
+    y = O.unet_forward(sd, cfg, t("x"), t("ts"), t("lab"), t("ctx"), t("fs"))
+    assert y.shape == (2, 4, 4, 16, 16)
+    assert float((y - t("y")).abs().max()) < 5e-5
+    # else-branch: context length != 77 + 16*T  (openaimodel3d.py:586-587)
+    y2 = O.unet_forward(sd, cfg, t("x"), t("ts"), t("lab"), t("ctx2"), t("fs"))
+    assert float((y2 - t("y2")).abs().max()) < 5e-5
+    assert float(t("y").abs().max()) > 0.5          # non-vacuous (zero-inits were re-randomised)
+
+
+def test_vae_decode_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "vae_small.npz"))
+    cfg = O.VaeCfg(ch=64)
+    sd = O.seeded_state_dict(O.vae_param_shapes(cfg), seed=2)
+    dec = O.vae_decode(sd, cfg, torch.from_numpy(g["z"]))
+    assert dec.shape == (2, 3, 64, 96)
+    assert float((dec - torch.from_numpy(g["dec"])).abs().max()) < 1e-5
+
+
+def test_schedule_tables(golden_dir):
+    g = np.load(os.path.join(golden_dir, "tables.npz"))
+    tab = O.make_tables(base_scale=0.3)
+    assert np.array_equal(tab.alphas_cumprod.numpy(), g["alphas_cumprod"])
+    assert np.array_equal(tab.scale_arr.numpy(), g["scale_arr"])
+    # closed forms
+    assert float(tab.alphas_cumprod[999]) == 0.0                      # zero terminal SNR
+    assert np.array_equal(O.ddim_timesteps("uniform_trailing", 50, 1000), np.arange(19, 1000, 20))
+    sc = tab.scale_arr.numpy()
+    assert np.allclose(sc[:400], np.linspace(1.0, 0.3, 400)) and np.all(sc[400:1000] == np.float32(0.3))
+    d = np.load(os.path.join(golden_dir, "ddim_small.npz"))
+    sch = O.make_ddim_schedule(tab, 50, "uniform_trailing", 1.0)
+    assert np.array_equal(sch.timesteps, d["timesteps50"])
+    assert np.array_equal(sch.sigmas, d["sigmas50"])                  # bit-exact incl. the fp32 reciprocal quirk
+    assert np.array_equal(sch.alphas_prev, d["alphas_prev50"])
+
+
+def test_ddim_first_step_closed_form():
+    """At t=999 (alphas_cumprod = 0): pred_x0 = -v * rescale and e_t = x."""
+    tab = O.make_tables(base_scale=0.3)
+    sch = O.make_ddim_schedule(tab, 50, "uniform_trailing", 1.0)
+    g = torch.Generator().manual_seed(0)
+    x, v, n = (torch.randn(1, 4, 2, 4, 4, generator=g) for _ in range(3))
+    _, pred = O.ddim_step(tab, sch, 49, x, v, None, n, 1.0, 0.0)
+    assert torch.allclose(pred, -v * (sch.scale_arr_prev[49] / sch.scale_arr[49]), atol=1e-6)
+
+
+def test_ddim_sample_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "unet_small.npz"))
+    d = np.load(os.path.join(golden_dir, "ddim_small.npz"))
+    cfg = O.UNetCfg(model_channels=64, temporal_length=4)
+    sd = O.seeded_state_dict(O.unet_param_shapes(cfg), seed=1)
+    tab = O.make_tables(base_scale=0.3)
+    t = lambda a: torch.from_numpy(a)
+    torch.manual_seed(123)
+    out = O.ddim_sample(sd, cfg, tab, S=3, shape=(2, 4, 4, 16, 16), c_concat=t(d["c_concat"]), context=t(g["ctx"]),
+                        uc_context=t(d["uc_ctx"]), class_label=t(g["lab"]), fs=t(g["fs"]), cfg_scale=7.5,
+                        guidance_rescale=0.7, eta=1.0)
+    assert float((out - t(d["samples"])).abs().max()) < 5e-4
+    vcfg = O.VaeCfg(ch=64)
+    vsd = O.seeded_state_dict(O.vae_param_shapes(vcfg), seed=2)
+    frames = O.decode_first_stage(vsd, vcfg, t(d["samples"]))
+    assert float((frames - t(d["frames"]).float()).abs().max()) < 5e-3    # fixture stored as fp16
