@@ -1,0 +1,107 @@
+/* libmudg_sm100.so -- C ABI of the B200-native MuDG sampler hot path.
+ *
+ * The reference (heiheishuang/MuDG) is pure Python/PyTorch and has no FFI of its own; its extension point is
+ * utils/utils.py:27-42 (instantiate_from_config).  This ABI is what the drop-in Python classes
+ * (lvdm.modules.networks.openaimodel3d.UNetModel, lvdm.models.autoencoder.AutoencoderKL,
+ * lvdm.models.samplers.ddim.DDIMSampler) bind with ctypes; each entry point names the reference code it replaces.
+ *
+ * Conventions: plain C symbols, int return (0 = ok, negative = error, text via mudg_last_error(), thread local);
+ * no exceptions / torch types cross the ABI; every tensor is a caller-owned, contiguous DEVICE pointer; the library
+ * owns only packed fp16 weights + a workspace arena (freed by mudg_destroy); every call enqueues on the caller's
+ * cudaStream_t (passed as void*) and never synchronises the host; one context per (process, device).
+ */
+#ifndef MUDG_H_
+#define MUDG_H_
+#include <stddef.h>
+#include <stdint.h>
+#if defined(__GNUC__)
+#define MUDG_EXPORT __attribute__((visibility("default")))
+#else
+#define MUDG_EXPORT
+#endif
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct MudgCtx MudgCtx;
+
+enum { MUDG_F32 = 0, MUDG_F16 = 1 };
+enum { MUDG_UNET = 0, MUDG_VAE = 1 };
+
+/* unet_config.params of configs/stage{1,2}-*_infer.yaml:26-56 (only the keys that shape the graph) */
+typedef struct {
+  int in_channels, out_channels, model_channels, num_res_blocks;
+  int channel_mult[8], n_channel_mult;
+  int attention_resolutions[8], n_attention_resolutions;
+  int num_head_channels;   /* must be 64 */
+  int context_dim;
+  int init_attn_heads;     /* openaimodel3d.py:408 hard-codes 8 */
+  int text_context_len;    /* attention.py:45: 77 */
+} MudgUNetConfig;
+
+/* first_stage_config.params.ddconfig (infer yaml :63-77) */
+typedef struct {
+  int ch;
+  int ch_mult[8], n_ch_mult;
+  int num_res_blocks, z_channels, out_ch, embed_dim;
+} MudgVaeConfig;
+
+MUDG_EXPORT const char* mudg_last_error(void);
+MUDG_EXPORT int mudg_create(int device, const MudgUNetConfig* unet, const MudgVaeConfig* vae, MudgCtx** out);
+MUDG_EXPORT void mudg_destroy(MudgCtx* ctx);
+
+/* One state_dict entry (reference key names, e.g. "input_blocks.1.0.temopral_conv.conv1.2.weight").  Replaces
+ * nn.Module.load_state_dict for UNetModel (openaimodel3d.py:281-565) / AutoencoderKL (autoencoder.py:27-32).
+ * The tensor is converted to the kernels' fp16 layout immediately; the source may be freed after the call's
+ * stream work completes.  `which` = MUDG_UNET | MUDG_VAE. */
+MUDG_EXPORT int mudg_load_weight(MudgCtx* ctx, int which, const char* key, const void* dev_ptr, int dtype,
+                                 const int64_t* shape, int ndim, void* stream);
+/* Validates that every key the graph needs is present and builds the fused layouts (QKV, K|V, GEGLU interleave). */
+MUDG_EXPORT int mudg_finalize_weights(MudgCtx* ctx, int which, void* stream);
+
+/* Cross-attention context, constant over the DDIM steps: context [N, L, context_dim] (the `context` argument of
+ * UNetModel.forward, openaimodel3d.py:567,580-587).  Precomputes to_k/to_v/to_k_ip/to_v_ip of all 16
+ * SpatialTransformers (attention.py:89-94) once per clip.  T = frames; L == 77 + 16*T selects per-frame image tokens. */
+MUDG_EXPORT int mudg_set_context(MudgCtx* ctx, const void* context, int dtype, int N, int L, int T, void* stream);
+
+/* UNetModel.forward (openaimodel3d.py:567-628).  x [N, in_channels, T, h, w] fp32, t/c_label/fs [N] int64 (device),
+ * out [N, out_channels, T, h, w] fp16 (the reference returns fp16 under autocast). */
+MUDG_EXPORT int mudg_unet_forward(MudgCtx* ctx, const void* x, const int64_t* t, const int64_t* c_label,
+                                  const int64_t* fs, int N, int T, int h, int w, void* out, void* stream);
+
+/* DDIMSampler.p_sample_ddim after the UNet calls (ddim.py:226-277) + rescale_noise_cfg (utils_diffusion.py:147-158)
+ * + predict_{eps,start}_from_z_and_v (ddpm3d.py:239-251).  x/noise/x_prev/pred_x0 fp32 [B, n]; v_* fp16 [B, n];
+ * v_uncond may be NULL (no guidance).  Scalars are the per-step table entries. */
+MUDG_EXPORT int mudg_ddim_step(const void* x, const void* v_cond, const void* v_uncond, const void* noise,
+                               void* x_prev, void* pred_x0, int B, int64_t n, float cfg_scale, float guidance_rescale,
+                               float sqrt_alphas_cumprod_t, float sqrt_one_minus_alphas_cumprod_t, float rescale,
+                               float a_prev, float sigma_t, void* stream);
+
+/* AutoencoderKL.decode (autoencoder.py:104-107) + Decoder.forward (ae_modules.py:539-578), frame by frame like
+ * decode_core with perframe_ae (ddpm3d.py:646-667).  z [F, z_channels, h, w] fp32 ALREADY divided by scale_factor;
+ * out [F, out_ch, 8h, 8w] fp16. */
+MUDG_EXPORT int mudg_vae_decode(MudgCtx* ctx, const void* z, int F, int h, int w, void* out, void* stream);
+
+/* Workspace the library needs (and will allocate on first use) for a forward of this shape. */
+MUDG_EXPORT size_t mudg_workspace_bytes(MudgCtx* ctx, int N, int T, int h, int w);
+/* Kernels launched by this context since creation (bench.py's gpu_launches). */
+MUDG_EXPORT int64_t mudg_launch_count(MudgCtx* ctx);
+
+/* ---- single-kernel test hooks (tests/ only) ---- */
+MUDG_EXPORT int mudg_test_tapgemm(const void* A, int B, int T, int H, int W, int Cin, int mode, const void* Wt, int N,
+                                  void* D, const void* R, const float* bias, const float* bias2, int bias2_div, int nb2,
+                                  float alpha, int geglu, int backend, void* stream);
+MUDG_EXPORT int mudg_test_flash(const void* Q, int q_pitch, void* O, int o_pitch, int F, int Nq, int heads,
+                                const void* K0, const void* V0, int pitch0, int len0, int nbatch0, int div0,
+                                const void* K1, const void* V1, int pitch1, int len1, int nbatch1, int div1, float scale,
+                                int backend, void* stream);
+MUDG_EXPORT int mudg_test_temporal_attn(const void* qkv, void* out, int B, int T, int HW, int heads, float scale,
+                                        void* stream);
+MUDG_EXPORT int mudg_test_groupnorm(const void* x, void* y, int S, int64_t rows_per_sample, int C, const float* gamma,
+                                    const float* beta, float eps, int silu, void* stream);
+MUDG_EXPORT int mudg_test_layernorm(const void* x, void* y, const float* gamma, const float* beta, int64_t rows, int C,
+                                    void* stream);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,39 @@
+"""ctypes loader for libmudg_sm100.so.  Fails loudly: there is no CPU or PyTorch fallback for the product path."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmudg_sm100.so")
+_lib = None
+
+
+class MudgError(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MudgError(f"{LIB_PATH} is missing: run `python -m mudg_b200.build` (or __graft_entry__.build()) first; "
+                            "the CUDA extension is mandatory, there is no fallback path")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.mudg_last_error.restype = ctypes.c_char_p
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise MudgError(lib().mudg_last_error().decode("utf-8", "replace"))
+
+
+def ptr(t):
+    """torch tensor (or None) -> void*"""
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def cur_stream():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

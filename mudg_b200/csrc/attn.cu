@@ -1,0 +1,447 @@
+// Attention kernels of the UNet (head dim 64 everywhere on the path: num_head_channels 64).
+//
+// flash_attention: spatial self-attention (N up to 9216 tokens/frame) and text/image cross-attention.
+//   One CTA = 128 queries of one (frame, head); 2 CTAs per SM.
+//   warp 0: TMA producer (Q once, then K/V 128-token blocks through a 2-stage ring)
+//   warp 1: tcgen05 issuer: S = Q K^T (M128 N128 K64) into TMEM, then O_blk = P V (M128 N64 K128,
+//           V consumed MN-major straight from its row-major TMA tile)
+//   warps 2-5: softmax, thread == query row == TMEM lane: two passes over S (max, then exp2/sum),
+//           P written as fp16 into a SWIZZLE_128B K-major smem tile, O rescaled/accumulated in registers.
+//   Two K/V segments keep separate softmax statistics and are summed at the end (attention.py:129-142).
+// temporal_attention: T<=64 tokens per (pixel, head); CUDA cores, K/V staged in smem (HBM-bound op).
+#include "ops.h"
+#include "ptx.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+
+namespace mudg {
+
+namespace {
+
+constexpr int FA_THREADS = 192;
+constexpr int TILE = 128 * 64 * 2;                       // 16 KB: 128 rows x 64 fp16
+constexpr int FA_SMEM = TILE /*Q*/ + 2 * 2 * TILE /*K,V ring*/ + 2 * TILE /*P*/ + 1024 + 256;
+
+struct FaParams {
+  int nseg;
+  int len[2];
+  int kv_div[2];
+  float scale_log2;   // scale * log2(e)
+};
+
+template <int NSEG>
+__global__ void __launch_bounds__(FA_THREADS, 2)
+flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmO,
+                const __grid_constant__ CUtensorMap tmK0, const __grid_constant__ CUtensorMap tmV0,
+                const __grid_constant__ CUtensorMap tmK1, const __grid_constant__ CUtensorMap tmV1, const FaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + TILE;              // stage s: K at sKV + s*2*TILE, V at + TILE
+  uint8_t* sP = smem + 5 * TILE;           // 2 atoms of 64 kv columns
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * TILE);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;            // [2]
+  uint64_t* kv_empty = bars + 3;           // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_ready = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, head = blockIdx.y, f = blockIdx.z;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(&kv_full[0], 1); mbar_init(&kv_full[1], 1);
+    mbar_init(&kv_empty[0], 1); mbar_init(&kv_empty[1], 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 128);
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+
+  int nblk[2];
+  nblk[0] = (p.len[0] + 127) >> 7;
+  nblk[1] = NSEG > 1 ? (p.len[1] + 127) >> 7 : 0;
+  const int nb = nblk[0] + nblk[1];
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, TILE);
+      tma_load_5d(sQ, &tmQ, q_full, head * 64, q0, f, 0, 0);
+      int it = 0;
+      for (int sg = 0; sg < NSEG; sg++) {
+        const CUtensorMap* mk = sg ? &tmK1 : &tmK0;
+        const CUtensorMap* mv = sg ? &tmV1 : &tmV0;
+        const int kb = f / p.kv_div[sg];
+        for (int j = 0; j < nblk[sg]; j++, it++) {
+          const int s = it & 1;
+          mbar_wait(&kv_empty[s], ((it >> 1) & 1) ^ 1);
+          mbar_expect_tx(&kv_full[s], 2 * TILE);
+          uint8_t* k_s = sKV + s * 2 * TILE;
+          tma_load_5d(k_s, mk, &kv_full[s], head * 64, j * 128, kb, 0, 0);
+          tma_load_5d(k_s + TILE, mv, &kv_full[s], head * 64, j * 128, kb, 0, 0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(128, 128, 0, 0);    // S = Q K^T : A,B K-major
+      constexpr uint32_t idesc_o = umma_idesc_f16(128, 64, 0, 1);     // O = P V   : B (V) MN-major
+      const uint64_t dq = umma_desc_sw128(smem_u32(sQ), 16, 1024);
+      const uint64_t dp = umma_desc_sw128(smem_u32(sP), 16, 1024);
+      mbar_wait(q_full, 0);
+      auto issue_s = [&](int it) {
+        const int s = it & 1;
+        mbar_wait(&kv_full[s], (it >> 1) & 1);
+        tc_fence_after();
+        const uint64_t dk = umma_desc_sw128(smem_u32(sKV + s * 2 * TILE), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; k++) umma_f16(tmem_S, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(s_full);
+      };
+      issue_s(0);
+      for (int it = 0; it < nb; it++) {
+        const int s = it & 1;
+        mbar_wait(p_ready, it & 1);
+        tc_fence_after();
+        // V tile: 128 kv rows x 128 B, MN-major (d contiguous); 8-row groups 1024 B apart (SBO); K=16 -> +2048 B
+        const uint64_t dv = umma_desc_sw128(smem_u32(sKV + s * 2 * TILE + TILE), 1024, 1024);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          // P: two 64-column K-major atoms (16 KB apart); inside an atom +32 B per K=16
+          const uint64_t dpk = dp + (uint64_t)((k >> 2) * (TILE >> 4) + (k & 3) * 2);
+          umma_f16(tmem_O, dpk, dv + (uint64_t)(k * (2048 >> 4)), idesc_o, k != 0 ? 1u : 0u);
+        }
+        umma_commit(o_full);
+        umma_commit(&kv_empty[s]);
+        if (it + 1 < nb) issue_s(it + 1);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    float O[64];
+    uint32_t acc[NSEG > 1 ? 32 : 1];       // fp16x2 running sum of the finished segments' outputs
+    if (NSEG > 1) {
+#pragma unroll
+      for (int i = 0; i < 32; i++) acc[i] = 0u;
+    }
+    int it = 0;
+#pragma unroll 1
+    for (int sg = 0; sg < NSEG; sg++) {
+      float m = -INFINITY, l = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; i++) O[i] = 0.f;
+#pragma unroll 1
+      for (int j = 0; j < nblk[sg]; j++, it++) {
+        const int valid = p.len[sg] - j * 128;          // columns >= valid are padding (TMA zero fill)
+        mbar_wait(s_full, it & 1);
+        __syncwarp();
+        tc_fence_after();
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 4; c++) {
+          uint32_t v[32];
+          tmem_ld32(tmem_S + lane_off + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++)
+            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+        const float m_new = fmaxf(m, mx * p.scale_log2);
+        const float alpha = exp2f(m - m_new);
+        float lsum = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 4; c++) {
+          uint32_t v[32];
+          tmem_ld32(tmem_S + lane_off + c * 32, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float p0 = (c * 32 + i < valid) ? exp2f(__uint_as_float(v[i]) * p.scale_log2 - m_new) : 0.f;
+            float p1 = (c * 32 + i + 1 < valid) ? exp2f(__uint_as_float(v[i + 1]) * p.scale_log2 - m_new) : 0.f;
+            lsum += p0 + p1;
+            pk[i >> 1] = pack_half2(p0, p1);
+          }
+          uint8_t* atom = sP + (c >> 1) * TILE + row * 128;
+#pragma unroll
+          for (int jj = 0; jj < 4; jj++) {
+            const int chunk = (c & 1) * 4 + jj;
+            *reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) =
+                make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+          }
+        }
+        l = l * alpha + lsum;
+        m = m_new;
+        fence_proxy_async_smem();          // P (generic-proxy writes) -> visible to the tensor core
+        tc_fence_before();                 // orders this thread's tcgen05.ld of S before the next S MMA
+        mbar_arrive(p_ready);
+        mbar_wait(o_full, it & 1);
+        __syncwarp();
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          uint32_t v[32];
+          tmem_ld32(tmem_O + lane_off + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++) O[c * 32 + i] = O[c * 32 + i] * alpha + __uint_as_float(v[i]);
+        }
+      }
+      const float inv = 1.f / l;
+      if (NSEG > 1) {
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          const float2 a = unpack_half2(acc[i]);
+          acc[i] = pack_half2(a.x + O[2 * i] * inv, a.y + O[2 * i + 1] * inv);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; i++) O[i] *= inv;
+      }
+    }
+    // ---- epilogue: fp16 tile -> swizzled smem (P buffer is free: the last PV MMA has retired) -> TMA store
+    uint8_t* stg = sP + row * 128;
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) {
+      uint4 val;
+      if (NSEG > 1) val = make_uint4(acc[4 * jj], acc[4 * jj + 1], acc[4 * jj + 2], acc[4 * jj + 3]);
+      else val = make_uint4(pack_half2(O[8 * jj], O[8 * jj + 1]), pack_half2(O[8 * jj + 2], O[8 * jj + 3]),
+                            pack_half2(O[8 * jj + 4], O[8 * jj + 5]), pack_half2(O[8 * jj + 6], O[8 * jj + 7]));
+      *reinterpret_cast<uint4*>(stg + ((jj ^ (row & 7)) << 4)) = val;
+    }
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (warp == 2 && lane == 0) {
+      tma_store_5d(&tmO, sP, head * 64, q0, f, 0, 0);
+      tma_store_commit();
+      tma_store_wait_read0();
+    }
+    __syncwarp();
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------- SIMT checker: thread per (frame, head, query)
+__global__ void flash_simt_kernel(FlashArgs a) {
+  const int64_t total = (int64_t)a.F * a.heads * a.Nq;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int qi = idx % a.Nq;
+  const int head = (idx / a.Nq) % a.heads;
+  const int f = idx / ((int64_t)a.Nq * a.heads);
+  const __half* qp = a.Q + ((int64_t)f * a.Nq + qi) * a.q_pitch + head * 64;
+  float q[64], out[64];
+  for (int i = 0; i < 64; i++) { q[i] = __half2float(qp[i]); out[i] = 0.f; }
+  for (int sg = 0; sg < a.nseg; sg++) {
+    const FlashSeg& s = a.seg[sg];
+    const int kb = f / s.kv_div;
+    float m = -INFINITY, l = 0.f, o[64];
+    for (int i = 0; i < 64; i++) o[i] = 0.f;
+    for (int j = 0; j < s.len; j++) {
+      const __half* kp = s.K + ((int64_t)kb * s.len + j) * s.pitch + head * 64;
+      const __half* vp = s.V + ((int64_t)kb * s.len + j) * s.pitch + head * 64;
+      float d = 0.f;
+      for (int i = 0; i < 64; i++) d += q[i] * __half2float(kp[i]);
+      d *= a.scale;
+      const float mn = fmaxf(m, d);
+      const float al = expf(m - mn), pj = expf(d - mn);
+      l = l * al + pj;
+      for (int i = 0; i < 64; i++) o[i] = o[i] * al + pj * __half2float(vp[i]);
+      m = mn;
+    }
+    for (int i = 0; i < 64; i++) out[i] += o[i] / l;
+  }
+  __half* op = a.O + ((int64_t)f * a.Nq + qi) * a.o_pitch + head * 64;
+  for (int i = 0; i < 64; i++) op[i] = __float2half_rn(out[i]);
+}
+
+// ---------------------------------------------------------------- temporal attention
+// qkv rows are ordered (b, t, pixel); a warp handles `pairs` (pixel, head) problems at once: lane -> (pair, t)
+// for T <= 32, and lane -> t, t+32 for T in (32, 64].  K/V of the warp's pairs are staged in shared memory.
+__global__ void temporal_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int B, int T, int HW,
+                                     int heads, float scale_log2, int group, int pairs_per_warp) {
+  extern __shared__ uint4 tsm[];
+  const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int inner = heads * 64;
+  const int pitch = 3 * inner;
+  const int64_t npairs = (int64_t)B * HW * heads;
+  const int64_t first = ((int64_t)blockIdx.x * warps_per_block + warp_in_block) * pairs_per_warp;
+  // smem per warp: pairs * T rows * (8 K chunks + 8 V chunks)
+  uint4* wsm = tsm + (size_t)warp_in_block * pairs_per_warp * T * 16;
+
+  for (int i = lane; i < pairs_per_warp * T * 16; i += 32) {
+    const int ch = i & 7;
+    const int kv = (i >> 3) & 1;
+    const int t = (i >> 4) % T;
+    const int pp = (i >> 4) / T;
+    const int64_t pr = first + pp;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (pr < npairs) {
+      const int head = pr % heads;
+      const int64_t bp = pr / heads;
+      const int px = bp % HW;
+      const int b = bp / HW;
+      const __half* src = qkv + (((int64_t)b * T + t) * HW + px) * pitch + (1 + kv) * inner + head * 64;
+      val = __ldg(reinterpret_cast<const uint4*>(src) + ch);
+    }
+    wsm[((pp * T + t) * 2 + kv) * 8 + ch] = val;
+  }
+  __syncwarp();
+
+  const int pp = (group < 32) ? lane / group : 0;
+  const int tl = (group < 32) ? lane % group : lane;
+  const int64_t pr = first + pp;
+  if (pp >= pairs_per_warp || pr >= npairs) return;
+  const int head = pr % heads;
+  const int64_t bp = pr / heads;
+  const int px = bp % HW;
+  const int b = bp / HW;
+  for (int t = tl; t < T; t += 32) {
+    if (group < 32 && t != tl) break;
+    const int64_t rowi = ((int64_t)b * T + t) * HW + px;
+    const uint4* qp = reinterpret_cast<const uint4*>(qkv + rowi * pitch + head * 64);
+    __half2 qh[32];
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      const uint4 v = __ldg(qp + c);
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+      qh[4 * c] = h[0]; qh[4 * c + 1] = h[1]; qh[4 * c + 2] = h[2]; qh[4 * c + 3] = h[3];
+    }
+    float o[64];
+#pragma unroll
+    for (int i = 0; i < 64; i++) o[i] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < T; j++) {
+      const uint4* kr = wsm + ((pp * T + j) * 2 + 0) * 8;
+      const uint4* vr = wsm + ((pp * T + j) * 2 + 1) * 8;
+      float d = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        const uint4 kv4 = kr[c];
+        const __half2* kh = reinterpret_cast<const __half2*>(&kv4);
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const float2 kf = __half22float2(kh[e]);
+          const float2 qf = __half22float2(qh[4 * c + e]);
+          d += qf.x * kf.x + qf.y * kf.y;
+        }
+      }
+      d *= scale_log2;
+      const float mn = fmaxf(m, d);
+      const float al = exp2f(m - mn), pj = exp2f(d - mn);
+      l = l * al + pj;
+      m = mn;
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        const uint4 vv4 = vr[c];
+        const __half2* vh = reinterpret_cast<const __half2*>(&vv4);
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const float2 vf = __half22float2(vh[e]);
+          o[8 * c + 2 * e] = o[8 * c + 2 * e] * al + pj * vf.x;
+          o[8 * c + 2 * e + 1] = o[8 * c + 2 * e + 1] * al + pj * vf.y;
+        }
+      }
+    }
+    const float inv = 1.f / l;
+    uint4* op = reinterpret_cast<uint4*>(out + rowi * inner + head * 64);
+#pragma unroll
+    for (int c = 0; c < 8; c++)
+      op[c] = make_uint4(pack_half2(o[8 * c] * inv, o[8 * c + 1] * inv), pack_half2(o[8 * c + 2] * inv, o[8 * c + 3] * inv),
+                         pack_half2(o[8 * c + 4] * inv, o[8 * c + 5] * inv), pack_half2(o[8 * c + 6] * inv, o[8 * c + 7] * inv));
+  }
+}
+
+const CUtensorMap* rows_map(const __half* base, int width, int pitch, int rows, int batches) {
+  const uint64_t dims[5] = {(uint64_t)width, (uint64_t)rows, (uint64_t)batches, 1, 1};
+  const uint64_t pb = (uint64_t)pitch * 2;
+  const uint64_t str[4] = {pb, pb * rows, pb * rows * batches, pb * rows * batches};
+  const uint32_t box[5] = {64, 128, 1, 1, 1};
+  return get_tmap(base, dims, str, box);
+}
+
+}  // namespace
+
+void flash_attention_simt(const FlashArgs& a, cudaStream_t st) {
+  const int64_t total = (int64_t)a.F * a.heads * a.Nq;
+  flash_simt_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(a);
+  MUDG_CUDA(cudaGetLastError());
+}
+
+void flash_attention(const FlashArgs& a, cudaStream_t st) {
+  static const bool force_simt = [] {
+    const char* e = getenv("MUDG_FORCE_SIMT");
+    return e && e[0] == '1';
+  }();
+  if (force_simt) return flash_attention_simt(a, st);
+  MUDG_REQUIRE(a.nseg == 1 || a.nseg == 2, "nseg");
+  MUDG_REQUIRE(a.q_pitch % 8 == 0 && a.o_pitch % 8 == 0, "pitch alignment");
+  const int width = a.heads * 64;
+  const CUtensorMap* mq = rows_map(a.Q, width, a.q_pitch, a.Nq, a.F);
+  const CUtensorMap* mo = rows_map(a.O, width, a.o_pitch, a.Nq, a.F);
+  const CUtensorMap* mk[2];
+  const CUtensorMap* mv[2];
+  FaParams p{};
+  p.nseg = a.nseg;
+  p.scale_log2 = a.scale * 1.4426950408889634f;
+  for (int i = 0; i < 2; i++) {
+    const FlashSeg& s = a.seg[i < a.nseg ? i : 0];
+    MUDG_REQUIRE(s.pitch % 8 == 0 && s.len > 0, "kv segment");
+    mk[i] = rows_map(s.K, width, s.pitch, s.len, s.nbatch);
+    mv[i] = rows_map(s.V, width, s.pitch, s.len, s.nbatch);
+    p.len[i] = s.len;
+    p.kv_div[i] = s.kv_div > 0 ? s.kv_div : 1;
+  }
+  static bool attr = false;
+  if (!attr) {
+    MUDG_CUDA(cudaFuncSetAttribute(flash_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    MUDG_CUDA(cudaFuncSetAttribute(flash_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    attr = true;
+  }
+  dim3 grid((a.Nq + 127) / 128, a.heads, a.F);
+  if (a.nseg == 1) flash_tc_kernel<1><<<grid, FA_THREADS, FA_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
+  else flash_tc_kernel<2><<<grid, FA_THREADS, FA_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
+  MUDG_CUDA(cudaGetLastError());
+}
+
+void temporal_attention(const __half* qkv, __half* out, int B, int T, int HW, int heads, float scale, cudaStream_t st) {
+  MUDG_REQUIRE(T >= 1 && T <= 64, "temporal attention supports T <= 64 (T=%d)", T);
+  int group = 1;
+  while (group < T && group < 32) group *= 2;
+  const int ppw = group < 32 ? 32 / group : 1;
+  const int warps = 4;
+  const size_t smem = (size_t)warps * ppw * T * 16 * sizeof(uint4);
+  const int64_t npairs = (int64_t)B * HW * heads;
+  const int64_t blocks = (npairs + (int64_t)warps * ppw - 1) / ((int64_t)warps * ppw);
+  static size_t attr_smem = 0;
+  if (smem > 48 * 1024 && smem > attr_smem) {
+    MUDG_CUDA(cudaFuncSetAttribute(temporal_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  temporal_attn_kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(qkv, out, B, T, HW, heads,
+                                                                  scale * 1.4426950408889634f, group, ppw);
+  MUDG_CUDA(cudaGetLastError());
+}
+
+}  // namespace mudg

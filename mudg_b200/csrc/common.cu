@@ -1,0 +1,146 @@
+#include "common.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+namespace mudg {
+
+static thread_local std::string g_last_error;
+
+std::string fmt(const char* f, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, f);
+  vsnprintf(buf, sizeof(buf), f, ap);
+  va_end(ap);
+  return std::string(buf);
+}
+void set_last_error(const std::string& s) { g_last_error = s; }
+const char* last_error_cstr() { return g_last_error.c_str(); }
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ---------------------------------------------------------------- Arena
+Arena::~Arena() {
+  if (base_) cudaFree(base_);
+}
+void Arena::reserve(size_t bytes) {
+  if (base_) {
+    cudaFree(base_);
+    base_ = nullptr;
+  }
+  cap_ = 0;
+  if (bytes) {
+    MUDG_CUDA(cudaMalloc(&base_, bytes));
+    cap_ = bytes;
+  }
+  reset();
+  clear_tmap_cache();
+}
+void Arena::reset() {
+  top_ = 0;
+  free_.clear();
+  live_.clear();
+}
+void* Arena::alloc(size_t bytes) {
+  size_t sz = (bytes + 1023) & ~size_t(1023);
+  if (sz == 0) sz = 1024;
+  size_t off;
+  auto it = free_.find(sz);
+  if (it != free_.end() && !it->second.empty()) {
+    off = it->second.back();
+    it->second.pop_back();
+  } else {
+    off = top_;
+    top_ += sz;
+    if (top_ > high_) high_ = top_;
+    if (!planning && top_ > cap_)
+      throw Error(fmt("arena exhausted: need %zu bytes, capacity %zu", top_, cap_));
+  }
+  live_[off] = sz;
+  // planning mode hands out fake (never dereferenced) addresses with the same offsets
+  return (planning ? reinterpret_cast<char*>(uintptr_t(1) << 40) : base_) + off;
+}
+void Arena::free(void* p) {
+  if (!p) return;
+  char* b = planning ? reinterpret_cast<char*>(uintptr_t(1) << 40) : base_;
+  size_t off = static_cast<char*>(p) - b;
+  auto it = live_.find(off);
+  if (it == live_.end()) throw Error("arena: free of unknown block");
+  free_[it->second].push_back(off);
+  live_.erase(it);
+}
+
+// ---------------------------------------------------------------- tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    MUDG_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    MUDG_REQUIRE(p != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+using TmapKey = std::array<uint64_t, 15>;
+static std::map<TmapKey, CUtensorMap>& tmap_cache() {
+  static std::map<TmapKey, CUtensorMap> c;
+  return c;
+}
+void clear_tmap_cache() { tmap_cache().clear(); }
+
+const CUtensorMap* get_tmap(const void* base, const uint64_t dims[5], const uint64_t strides_bytes[4],
+                            const uint32_t box[5]) {
+  TmapKey key;
+  key[0] = reinterpret_cast<uint64_t>(base);
+  for (int i = 0; i < 5; i++) key[1 + i] = dims[i];
+  for (int i = 0; i < 4; i++) key[6 + i] = strides_bytes[i];
+  for (int i = 0; i < 5; i++) key[10 + i] = box[i];
+  auto& cache = tmap_cache();
+  auto it = cache.find(key);
+  if (it != cache.end()) return &it->second;
+  MUDG_REQUIRE((reinterpret_cast<uint64_t>(base) & 15) == 0, "TMA base must be 16B aligned");
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < 5; i++) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    MUDG_REQUIRE(box[i] >= 1 && box[i] <= 256, "TMA box dim %d = %u out of range", i, box[i]);
+  }
+  for (int i = 0; i < 4; i++) {
+    gstr[i] = strides_bytes[i];
+    MUDG_REQUIRE((strides_bytes[i] & 15) == 0, "TMA stride %d = %llu not a multiple of 16 bytes", i,
+                 (unsigned long long)strides_bytes[i]);
+  }
+  MUDG_REQUIRE(box[0] * 2 <= 128, "inner box exceeds the 128B swizzle span");
+  CUtensorMap m;
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), gdim, gstr, bx, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    throw Error(fmt("cuTensorMapEncodeTiled failed (%d): dims %llu %llu %llu %llu %llu box %u %u %u %u %u", (int)r,
+                    (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+                    (unsigned long long)dims[3], (unsigned long long)dims[4], box[0], box[1], box[2], box[3], box[4]));
+  auto ins = cache.emplace(key, m);
+  return &ins.first->second;
+}
+
+}  // namespace mudg

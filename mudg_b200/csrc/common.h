@@ -1,0 +1,81 @@
+// Host-side plumbing shared by every translation unit of libmudg_sm100.so:
+// error convention, device arena, tensor views, TMA tensor-map factory.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <array>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace mudg {
+
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+std::string fmt(const char* f, ...);
+void set_last_error(const std::string& s);
+
+#define MUDG_CUDA(expr)                                                                              \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess)                                                                           \
+      throw ::mudg::Error(::mudg::fmt("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e))); \
+  } while (0)
+#define MUDG_REQUIRE(cond, ...)                                                                      \
+  do {                                                                                               \
+    if (!(cond)) throw ::mudg::Error(::mudg::fmt("%s:%d require(%s): ", __FILE__, __LINE__, #cond) + ::mudg::fmt(__VA_ARGS__)); \
+  } while (0)
+
+// ---------------------------------------------------------------- activations
+// Channels-last activation: element (b,t,h,w,c) at ((((b*T+t)*H+h)*W+w)*C + c).  Spatial ops see
+// frames F=B*T; temporal ops see the (B,T) split; linear ops see rows M = B*T*H*W.
+struct Act {
+  __half* p = nullptr;
+  int B = 1, T = 1, H = 1, W = 1, C = 1;
+  int64_t rows() const { return (int64_t)B * T * H * W; }
+  int64_t numel() const { return rows() * C; }
+  size_t bytes() const { return (size_t)numel() * sizeof(__half); }
+  int frames() const { return B * T; }
+};
+
+// ---------------------------------------------------------------- arena
+// Size-bucketed caching sub-allocator over one cudaMalloc'd slab.  Deterministic (same call sequence ->
+// same addresses), so tensor maps can be cached and the step can be captured in a CUDA graph.
+// In planning mode nothing is allocated; only the high-water mark is recorded.
+class Arena {
+ public:
+  ~Arena();
+  void reserve(size_t bytes);          // (re)allocate the slab; invalidates everything
+  void reset();                        // drop all live blocks (start of a forward)
+  void* alloc(size_t bytes);
+  void free(void* p);
+  size_t capacity() const { return cap_; }
+  size_t high_water() const { return high_; }
+  bool planning = false;
+
+ private:
+  char* base_ = nullptr;
+  size_t cap_ = 0, top_ = 0, high_ = 0;
+  std::map<size_t, std::vector<size_t>> free_;    // size -> offsets
+  std::unordered_map<size_t, size_t> live_;       // offset -> size
+};
+
+// ---------------------------------------------------------------- TMA tensor maps
+// rank-5 fp16 tiled map, SWIZZLE_128B, zero OOB fill.  dims/box innermost first; strides in BYTES for dims 1..4.
+const CUtensorMap* get_tmap(const void* base, const uint64_t dims[5], const uint64_t strides_bytes[4],
+                            const uint32_t box[5]);
+void clear_tmap_cache();
+
+struct Stream {
+  cudaStream_t s = nullptr;
+};
+
+int sm_count();
+
+}  // namespace mudg

@@ -1,0 +1,437 @@
+// HBM-bound kernels of the path: GroupNorm (stats / finalize / apply+SiLU), LayerNorm, channel concat,
+// nearest 2x upsample, stride-2 im2col, row softmax, weight packing, embedding MLP pieces.
+// All activations are channels-last fp16 with C % 8 == 0 -> every access is a 128-bit vector.
+#include "ops.h"
+
+#include <algorithm>
+
+namespace mudg {
+
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 v;
+  __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; i++) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+
+// ---------------------------------------------------------------- GroupNorm statistics
+// x: [S samples][R rows][C]; sums: [S][32][2] doubles (sum, sum of squares), pre-zeroed.
+// block = (C/8) x rows_per_iter threads; a thread owns one 8-channel vector column and strides over rows,
+// so partial sums stay in registers until one flush at the end.
+__global__ void gn_stats_kernel(const __half* __restrict__ x, double* __restrict__ sums, int64_t R, int C, int cpg,
+                                int rows_per_block) {
+  __shared__ float acc[32][2];
+  const int vecs = C >> 3;
+  const int v = threadIdx.x % vecs, r0 = threadIdx.x / vecs, rstep = blockDim.x / vecs;
+  if (threadIdx.x < 64) (&acc[0][0])[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int s = blockIdx.y;
+  const int64_t row_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t row_end = min(R, row_begin + rows_per_block);
+  float sm[8], sq[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) sm[i] = sq[i] = 0.f;
+  const __half* base = x + ((int64_t)s * R) * C + v * 8;
+  if (r0 < rstep) {
+    for (int64_t r = row_begin + r0; r < row_end; r += rstep) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(base + r * C));
+      float f[8];
+      unpack8(raw, f);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        sm[i] += f[i];
+        sq[i] += f[i] * f[i];
+      }
+    }
+    // flush: merge channels of the same group first
+    int g_cur = (v * 8) / cpg;
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int g = (v * 8 + i) / cpg;
+      if (g != g_cur) {
+        atomicAdd(&acc[g_cur][0], a);
+        atomicAdd(&acc[g_cur][1], b);
+        a = b = 0.f;
+        g_cur = g;
+      }
+      a += sm[i];
+      b += sq[i];
+    }
+    atomicAdd(&acc[g_cur][0], a);
+    atomicAdd(&acc[g_cur][1], b);
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int g = threadIdx.x >> 1, k = threadIdx.x & 1;
+    atomicAdd(&sums[((int64_t)s * 32 + g) * 2 + k], (double)acc[g][k]);
+  }
+}
+
+// scale/shift per (sample, channel): y = x * scale + shift  ==  (x - mean) * rstd * gamma + beta
+__global__ void gn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift,
+                                   int S, int C, int cpg, double count, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S * C) return;
+  const int s = i / C, c = i % C, g = c / cpg;
+  const double mean = sums[(s * 32 + g) * 2] / count;
+  double var = sums[(s * 32 + g) * 2 + 1] / count - mean * mean;
+  if (var < 0) var = 0;
+  const float rstd = rsqrtf((float)var + eps);
+  const float sc = gamma[c] * rstd;
+  scale[i] = sc;
+  shift[i] = beta[c] - (float)mean * sc;
+}
+
+__global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ scale,
+                                const float* __restrict__ shift, int64_t total_vecs, int C, int64_t rows_per_sample,
+                                int act) {
+  const int vecs = C >> 3;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vecs; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / vecs;
+    const int v = i - row * vecs;
+    const int s = row / rows_per_sample;
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(x) + i);
+    float f[8];
+    unpack8(raw, f);
+    const float4* sc = reinterpret_cast<const float4*>(scale + (int64_t)s * C + v * 8);
+    const float4* sh = reinterpret_cast<const float4*>(shift + (int64_t)s * C + v * 8);
+    const float4 s0 = __ldg(sc), s1 = __ldg(sc + 1), h0 = __ldg(sh), h1 = __ldg(sh + 1);
+    f[0] = f[0] * s0.x + h0.x; f[1] = f[1] * s0.y + h0.y; f[2] = f[2] * s0.z + h0.z; f[3] = f[3] * s0.w + h0.w;
+    f[4] = f[4] * s1.x + h1.x; f[5] = f[5] * s1.y + h1.y; f[6] = f[6] * s1.z + h1.z; f[7] = f[7] * s1.w + h1.w;
+    if (act) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) f[k] = silu(f[k]);
+    }
+    reinterpret_cast<uint4*>(y)[i] = pack8(f);
+  }
+}
+
+// ---------------------------------------------------------------- LayerNorm (warp per row, row kept in registers)
+template <int MAXV>
+__global__ void layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, int64_t rows, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int vecs = C >> 3;
+  float f[MAXV][8];
+  float sum = 0.f;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * C);
+#pragma unroll
+  for (int k = 0; k < MAXV; k++) {
+    const int v = lane + 32 * k;
+    if (v < vecs) {
+      unpack8(__ldg(xr + v), f[k]);
+#pragma unroll
+      for (int i = 0; i < 8; i++) sum += f[k][i];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / C;
+  float var = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; k++) {
+    const int v = lane + 32 * k;
+    if (v < vecs) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const float d = f[k][i] - mean;
+        var += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / C + eps);
+  uint4* yr = reinterpret_cast<uint4*>(y + row * C);
+#pragma unroll
+  for (int k = 0; k < MAXV; k++) {
+    const int v = lane + 32 * k;
+    if (v < vecs) {
+      const float4* g4 = reinterpret_cast<const float4*>(gamma + v * 8);
+      const float4* b4 = reinterpret_cast<const float4*>(beta + v * 8);
+      const float4 g0 = __ldg(g4), g1 = __ldg(g4 + 1), b0 = __ldg(b4), b1 = __ldg(b4 + 1);
+      float o[8];
+      o[0] = (f[k][0] - mean) * rstd * g0.x + b0.x; o[1] = (f[k][1] - mean) * rstd * g0.y + b0.y;
+      o[2] = (f[k][2] - mean) * rstd * g0.z + b0.z; o[3] = (f[k][3] - mean) * rstd * g0.w + b0.w;
+      o[4] = (f[k][4] - mean) * rstd * g1.x + b1.x; o[5] = (f[k][5] - mean) * rstd * g1.y + b1.y;
+      o[6] = (f[k][6] - mean) * rstd * g1.z + b1.z; o[7] = (f[k][7] - mean) * rstd * g1.w + b1.w;
+      yr[v] = pack8(o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- layout helpers
+__global__ void concat_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ o,
+                              int64_t rows, int va, int vb) {
+  const int vo = va + vb;
+  const int64_t total = rows * vo;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / vo;
+    const int v = i - r * vo;
+    o[i] = v < va ? __ldg(a + r * va + v) : __ldg(b + r * vb + (v - va));
+  }
+}
+
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int F, int H, int W, int vecs) {
+  const int64_t total = (int64_t)F * 2 * H * 2 * W * vecs;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    const int v = t % vecs; t /= vecs;
+    const int w = t % (2 * W); t /= 2 * W;
+    const int h = t % (2 * H);
+    const int f = t / (2 * H);
+    y[i] = __ldg(x + (((int64_t)f * H + (h >> 1)) * W + (w >> 1)) * vecs + v);
+  }
+}
+
+// 3x3 stride-2 pad-1 patches: out[f, ho, wo, (kh*3+kw)*C + c] = x[f, 2ho+kh-1, 2wo+kw-1, c] (0 outside)
+__global__ void im2col_s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int F, int H, int W, int Ho, int Wo,
+                                 int vecs) {
+  const int64_t total = (int64_t)F * Ho * Wo * 9 * vecs;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    const int v = t % vecs; t /= vecs;
+    const int tap = t % 9; t /= 9;
+    const int wo = t % Wo; t /= Wo;
+    const int ho = t % Ho;
+    const int f = t / Ho;
+    const int h = 2 * ho + tap / 3 - 1, w = 2 * wo + tap % 3 - 1;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (h >= 0 && h < H && w >= 0 && w < W) val = __ldg(x + (((int64_t)f * H + h) * W + w) * vecs + v);
+    y[i] = val;
+  }
+}
+
+// in-place softmax over rows of length n (fp16 storage, fp32 math); one block per row
+__global__ void softmax_rows_kernel(__half* __restrict__ x, int64_t rows, int n) {
+  __shared__ float red[32];
+  const int64_t row = blockIdx.x;
+  __half* xr = x + row * n;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, __half2float(xr[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+  for (int i = 1; i < (blockDim.x >> 5); i++) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += __expf(__half2float(xr[i]) - m);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  s = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); i++) s += red[i];
+  const float inv = 1.f / s;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) xr[i] = __float2half_rn(__expf(__half2float(xr[i]) - m) * inv);
+}
+
+// ---------------------------------------------------------------- weights
+// src [O][I][taps] (fp32 or fp16, PyTorch conv layout flattened) -> dst [O][taps][Ipad] fp16, zero padded
+template <typename TS>
+__global__ void pack_weight_kernel(const TS* __restrict__ src, __half* __restrict__ dst, int O, int I, int taps,
+                                   int Ipad) {
+  const int64_t total = (int64_t)O * taps * Ipad;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    const int c = t % Ipad; t /= Ipad;
+    const int tap = t % taps;
+    const int o = t / taps;
+    float v = 0.f;
+    if (c < I) v = static_cast<float>(src[((int64_t)o * I + c) * taps + tap]);
+    dst[i] = __float2half_rn(v);
+  }
+}
+
+template <typename TS, typename TD>
+__global__ void cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    d[i] = static_cast<TD>(static_cast<float>(s[i]));
+}
+
+// rows of `src` [rows][cols] gathered into dst in blocks: used to interleave GEGLU value/gate rows.
+// dst row (g*128 + j) = src row (g*64 + j) for j<64 (value), src row (half + g*64 + j-64) for j>=64 (gate)
+__global__ void geglu_interleave_kernel(const __half* __restrict__ w, const float* __restrict__ b,
+                                        __half* __restrict__ wo, float* __restrict__ bo, int half_rows, int cols) {
+  const int64_t total = (int64_t)2 * half_rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols;
+    const int c = i - r * cols;
+    const int g = r / 128, j = r % 128;
+    const int64_t sr = j < 64 ? (int64_t)g * 64 + j : (int64_t)half_rows + g * 64 + (j - 64);
+    wo[i] = w[sr * cols + c];
+    if (c == 0 && b != nullptr) bo[r] = b[sr];
+  }
+}
+
+// ---------------------------------------------------------------- embeddings
+// [cos | sin] sinusoid of an int64 index (utils_diffusion.py:8-28)
+__global__ void sinusoid_kernel(const int64_t* __restrict__ t, float* __restrict__ out, int B, int dim) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim / 2;
+  if (i >= B * half) return;
+  const int b = i / half, k = i % half;
+  const float freq = expf(-logf(10000.f) * (float)k / (float)half);
+  const float arg = (float)t[b] * freq;
+  out[b * dim + k] = cosf(arg);
+  out[b * dim + half + k] = sinf(arg);
+}
+
+// y[b][n] (+)= sum_k act(x[b][k]) * W[n][k] + bias[n]; warp per output; fp32 activations, fp16 weights
+__global__ void small_linear_kernel(const float* __restrict__ x, const __half* __restrict__ W,
+                                    const float* __restrict__ bias, float* __restrict__ y, int Bn, int N, int K,
+                                    int silu_in, int accumulate) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= Bn * N) return;
+  const int b = warp / N, n = warp % N;
+  const float* xr = x + (int64_t)b * K;
+  const __half* wr = W + (int64_t)n * K;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    float xv = xr[k];
+    if (silu_in) xv = xv / (1.f + expf(-xv));
+    acc += xv * __half2float(wr[k]);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    float v = acc + (bias ? bias[n] : 0.f);
+    if (accumulate) v += y[(int64_t)b * N + n];
+    y[(int64_t)b * N + n] = v;
+  }
+}
+
+inline int grid_for(int64_t work, int threads) {
+  int64_t b = (work + threads - 1) / threads;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(b, (int64_t)sm_count() * 16));
+}
+
+}  // namespace
+
+// ================================================================ launchers
+void gn_scale_shift(const __half* x, int S, int64_t rows_per_sample, int C, const float* gamma, const float* beta,
+                    float eps, double* sums_ws, float* scale, float* shift, cudaStream_t st) {
+  MUDG_REQUIRE(C % 32 == 0 && C % 8 == 0, "GroupNorm needs C %% 32 == 0 (C=%d)", C);
+  const int cpg = C / 32, vecs = C / 8;
+  MUDG_REQUIRE(vecs <= 1024, "C too large for gn_stats");
+  MUDG_CUDA(cudaMemsetAsync(sums_ws, 0, sizeof(double) * S * 64, st));
+  const int rpi = std::max(1, 256 / vecs);
+  const int threads = vecs * rpi;
+  // enough blocks to fill the machine, at least 32 rows per block
+  int64_t want_blocks = std::max<int64_t>(1, (int64_t)sm_count() * 8 / std::max(1, S));
+  int64_t rpb = std::max<int64_t>(32, (rows_per_sample + want_blocks - 1) / want_blocks);
+  rpb = (rpb + rpi - 1) / rpi * rpi;
+  const int chunks = (int)((rows_per_sample + rpb - 1) / rpb);
+  gn_stats_kernel<<<dim3(chunks, S), threads, 0, st>>>(x, sums_ws, rows_per_sample, C, cpg, (int)rpb);
+  MUDG_CUDA(cudaGetLastError());
+  gn_finalize_kernel<<<(S * C + 255) / 256, 256, 0, st>>>(sums_ws, gamma, beta, scale, shift, S, C, cpg,
+                                                         (double)rows_per_sample * cpg, eps);
+  MUDG_CUDA(cudaGetLastError());
+}
+
+void gn_apply(const __half* x, __half* y, const float* scale, const float* shift, int64_t rows, int C,
+              int64_t rows_per_sample, bool silu_act, cudaStream_t st) {
+  const int64_t total = rows * (C / 8);
+  gn_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, y, scale, shift, total, C, rows_per_sample, silu_act ? 1 : 0);
+  MUDG_CUDA(cudaGetLastError());
+}
+
+void layernorm(const __half* x, __half* y, const float* gamma, const float* beta, int64_t rows, int C, float eps,
+               cudaStream_t st) {
+  MUDG_REQUIRE(C % 8 == 0 && C <= 2560, "LayerNorm width %d unsupported", C);
+  const int wpb = 8;
+  const int64_t blocks = (rows + wpb - 1) / wpb;
+  const int vecs = C / 8;
+  if (vecs <= 64) layernorm_kernel<2><<<(unsigned)blocks, wpb * 32, 0, st>>>(x, y, gamma, beta, rows, C, eps);
+  else if (vecs <= 160) layernorm_kernel<5><<<(unsigned)blocks, wpb * 32, 0, st>>>(x, y, gamma, beta, rows, C, eps);
+  else layernorm_kernel<10><<<(unsigned)blocks, wpb * 32, 0, st>>>(x, y, gamma, beta, rows, C, eps);
+  MUDG_CUDA(cudaGetLastError());
+}
+
+void concat_channels(const __half* a, int Ca, const __half* b, int Cb, __half* out, int64_t rows, cudaStream_t st) {
+  MUDG_REQUIRE(Ca % 8 == 0 && Cb % 8 == 0, "concat needs C %% 8 == 0");
+  const int64_t total = rows * ((Ca + Cb) / 8);
+  concat_kernel<<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b),
+                                                      reinterpret_cast<uint4*>(out), rows, Ca / 8, Cb / 8);
+  MUDG_CUDA(cudaGetLastError());
+}
+
+void upsample2x(const __half* x, __half* y, int F, int H, int W, int C, cudaStream_t st) {
+  const int64_t total = (int64_t)F * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), F,
+                                                          H, W, C / 8);
+  MUDG_CUDA(cudaGetLastError());
+}
+
+void im2col_s2(const __half* x, __half* y, int F, int H, int W, int C, cudaStream_t st) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const int64_t total = (int64_t)F * Ho * Wo * 9 * (C / 8);
+  im2col_s2_kernel<<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), F,
+                                                         H, W, Ho, Wo, C / 8);
+  MUDG_CUDA(cudaGetLastError());
+}
+
+void softmax_rows(__half* x, int64_t rows, int n, cudaStream_t st) {
+  softmax_rows_kernel<<<(unsigned)rows, 256, 0, st>>>(x, rows, n);
+  MUDG_CUDA(cudaGetLastError());
+}
+
+void pack_weight(const void* src, bool src_fp32, __half* dst, int O, int I, int taps, int Ipad, cudaStream_t st) {
+  const int64_t total = (int64_t)O * taps * Ipad;
+  if (src_fp32)
+    pack_weight_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const float*>(src), dst, O, I, taps, Ipad);
+  else
+    pack_weight_kernel<__half><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const __half*>(src), dst, O, I, taps, Ipad);
+  MUDG_CUDA(cudaGetLastError());
+}
+
+void cast_to_f32(const void* src, bool src_fp32, float* dst, int64_t n, cudaStream_t st) {
+  if (src_fp32) cast_kernel<float, float><<<grid_for(n, 256), 256, 0, st>>>(static_cast<const float*>(src), dst, n);
+  else cast_kernel<__half, float><<<grid_for(n, 256), 256, 0, st>>>(static_cast<const __half*>(src), dst, n);
+  MUDG_CUDA(cudaGetLastError());
+}
+
+void cast_to_f16(const void* src, bool src_fp32, __half* dst, int64_t n, cudaStream_t st) {
+  if (src_fp32) cast_kernel<float, __half><<<grid_for(n, 256), 256, 0, st>>>(static_cast<const float*>(src), dst, n);
+  else cast_kernel<__half, __half><<<grid_for(n, 256), 256, 0, st>>>(static_cast<const __half*>(src), dst, n);
+  MUDG_CUDA(cudaGetLastError());
+}
+
+void geglu_interleave(const __half* w, const float* b, __half* wo, float* bo, int half_rows, int cols, cudaStream_t st) {
+  MUDG_REQUIRE(half_rows % 64 == 0, "GEGLU inner dim must be a multiple of 64");
+  const int64_t total = (int64_t)2 * half_rows * cols;
+  geglu_interleave_kernel<<<grid_for(total, 256), 256, 0, st>>>(w, b, wo, bo, half_rows, cols);
+  MUDG_CUDA(cudaGetLastError());
+}
+
+void sinusoid(const int64_t* t, float* out, int B, int dim, cudaStream_t st) {
+  const int n = B * (dim / 2);
+  sinusoid_kernel<<<(n + 127) / 128, 128, 0, st>>>(t, out, B, dim);
+  MUDG_CUDA(cudaGetLastError());
+}
+
+void small_linear(const float* x, const __half* W, const float* bias, float* y, int Bn, int N, int K, bool silu_in,
+                  bool accumulate, cudaStream_t st) {
+  const int64_t threads = (int64_t)Bn * N * 32;
+  small_linear_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, W, bias, y, Bn, N, K, silu_in ? 1 : 0,
+                                                                        accumulate ? 1 : 0);
+  MUDG_CUDA(cudaGetLastError());
+}
+
+}  // namespace mudg

@@ -1,0 +1,60 @@
+// "Tap GEMM": the one contraction every Linear / Conv2d 3x3 / Conv3d (3,1,1) / 1x1 conv of the path maps to.
+//
+//   D[b,t,h,w,n] = epi( alpha * sum_{tap, c} A[b, t+dt, h+dh, w+dw, c] * Wt[n, tap*Cin + c] )
+//
+// A, D, R are channels-last fp16 (see Act); out-of-range taps read zeros (== conv zero padding).
+// epi: + bias[n] + bias2[sample(b,t)][n] + R[b,t,h,w,n]; or GEGLU (weights pre-interleaved 64 value rows /
+// 64 gate rows): D[.., j] = (v + bv) * gelu_erf(g + bg).
+#pragma once
+#include "common.h"
+
+namespace mudg {
+
+struct TapGemm {
+  // A geometry (channels-last, contiguous)
+  const __half* A = nullptr;
+  int B = 1, T = 1, H = 1, W = 1, Cin = 0;
+  int ntaps = 1;
+  int8_t taps[9][3] = {{0, 0, 0}};   // (dw, dh, dt)
+  // weights [N][ntaps*Cin] fp16, K-major
+  const __half* Wt = nullptr;
+  int N = 0;
+  // output [B,T,H,W,n_out] (n_out == N, or N/2 with geglu)
+  __half* D = nullptr;
+  const __half* R = nullptr;       // optional residual, same shape as D
+  const float* bias = nullptr;     // [N]
+  const float* bias2 = nullptr;    // [nb2][N]; row = (b*T + t) / bias2_div
+  int bias2_div = 1, nb2 = 0;
+  float alpha = 1.f;
+  bool geglu = false;
+};
+
+// generic-stride variant for the irregular layers (tiny Cin / tiny N, fp32 NCTHW in/out)
+struct TapGemmGeneric {
+  const void* A = nullptr;
+  bool a_fp32 = false;
+  int B = 1, T = 1, H = 1, W = 1, Cin = 0;
+  int64_t a_sb = 0, a_st = 0, a_sh = 0, a_sw = 0, a_sc = 1;   // element strides
+  int ntaps = 1;
+  int8_t taps[9][3] = {{0, 0, 0}};
+  const __half* Wt = nullptr;     // [N][ntaps*CinW]
+  int CinW = 0;                   // weight row pitch per tap (>= Cin, padded)
+  int N = 0;
+  void* D = nullptr;
+  bool d_fp32 = false;
+  int64_t d_sb = 0, d_st = 0, d_sh = 0, d_sw = 0, d_sn = 1;
+  const float* bias = nullptr;
+  float alpha = 1.f;
+};
+
+bool tapgemm_tc_eligible(const TapGemm& g);
+void tapgemm_tc(const TapGemm& g, cudaStream_t st);        // tcgen05 + TMA path
+void tapgemm_simt(const TapGemm& g, cudaStream_t st);      // CUDA-core checker of the same contract (debug)
+void tapgemm_generic(const TapGemmGeneric& g, cudaStream_t st);
+// dispatch: tensor cores unless MUDG_FORCE_SIMT=1 (debug) or the layer is not eligible
+void tapgemm(const TapGemm& g, cudaStream_t st);
+
+void set_taps_3x3(int8_t taps[9][3]);      // (dw,dh) in {-1,0,1}^2, tap index = kh*3+kw (weight layout [N][kh][kw][Cin])
+void set_taps_t3(int8_t taps[9][3]);       // dt in {-1,0,1}
+
+}  // namespace mudg

@@ -1,0 +1,69 @@
+// Launchers of the non-GEMM kernels (elem.cu, attn.cu, sampler.cu).  All take raw device pointers + a stream.
+#pragma once
+#include "common.h"
+
+namespace mudg {
+
+// GroupNorm over [S samples][rows_per_sample][C] (32 groups): per-(sample,channel) scale/shift, then apply (+SiLU)
+void gn_scale_shift(const __half* x, int S, int64_t rows_per_sample, int C, const float* gamma, const float* beta,
+                    float eps, double* sums_ws /*[S*64]*/, float* scale /*[S*C]*/, float* shift, cudaStream_t st);
+void gn_apply(const __half* x, __half* y, const float* scale, const float* shift, int64_t rows, int C,
+              int64_t rows_per_sample, bool silu_act, cudaStream_t st);
+void layernorm(const __half* x, __half* y, const float* gamma, const float* beta, int64_t rows, int C, float eps,
+               cudaStream_t st);
+void concat_channels(const __half* a, int Ca, const __half* b, int Cb, __half* out, int64_t rows, cudaStream_t st);
+void upsample2x(const __half* x, __half* y, int F, int H, int W, int C, cudaStream_t st);
+void im2col_s2(const __half* x, __half* y, int F, int H, int W, int C, cudaStream_t st);
+void softmax_rows(__half* x, int64_t rows, int n, cudaStream_t st);
+void pack_weight(const void* src, bool src_fp32, __half* dst, int O, int I, int taps, int Ipad, cudaStream_t st);
+void cast_to_f32(const void* src, bool src_fp32, float* dst, int64_t n, cudaStream_t st);
+void cast_to_f16(const void* src, bool src_fp32, __half* dst, int64_t n, cudaStream_t st);
+void geglu_interleave(const __half* w, const float* b, __half* wo, float* bo, int half_rows, int cols, cudaStream_t st);
+void sinusoid(const int64_t* t, float* out, int B, int dim, cudaStream_t st);
+void small_linear(const float* x, const __half* W, const float* bias, float* y, int Bn, int N, int K, bool silu_in,
+                  bool accumulate, cudaStream_t st);
+
+// ---- attention (attn.cu)
+// Flash attention, head dim 64, fp16 in/out, tcgen05.  Q rows: [F frames][Nq tokens], row pitch q_pitch elements,
+// head h at columns [h*64, h*64+64).  Up to two K/V segments with SEPARATE softmaxes whose outputs are summed
+// (text + image cross-attention, attention.py:129-142).  KV batch index of frame f = f / kv_div.
+struct FlashSeg {
+  const __half* K = nullptr;
+  const __half* V = nullptr;
+  int pitch = 0;       // row pitch (elements)
+  int len = 0;         // tokens per kv batch
+  int nbatch = 0;      // number of kv batches
+  int kv_div = 1;
+};
+struct FlashArgs {
+  const __half* Q = nullptr;
+  int q_pitch = 0;
+  __half* O = nullptr;
+  int o_pitch = 0;
+  int F = 0, Nq = 0, heads = 0;
+  int nseg = 1;
+  FlashSeg seg[2];
+  float scale = 0.125f;
+};
+void flash_attention(const FlashArgs& a, cudaStream_t st);
+void flash_attention_simt(const FlashArgs& a, cudaStream_t st);   // CUDA-core checker (debug / MUDG_FORCE_SIMT)
+
+// Temporal self-attention over T for every (b, h, w, head): qkv rows [B*T*HW][3*inner] (q | k | v), out [rows][inner]
+void temporal_attention(const __half* qkv, __half* out, int B, int T, int HW, int heads, float scale, cudaStream_t st);
+
+// ---- sampler (sampler.cu): fused CFG + guidance rescale + v-pred DDIM update (ddim.py:226-277)
+struct DdimStepArgs {
+  const float* x = nullptr;        // [B][n] fp32
+  const __half* v_cond = nullptr;  // [B][n] fp16 (UNet output)
+  const __half* v_uncond = nullptr;  // or null
+  const float* noise = nullptr;    // [B][n] fp32
+  float* x_prev = nullptr;
+  float* pred_x0 = nullptr;
+  int B = 0;
+  int64_t n = 0;
+  float cfg_scale = 1.f, guidance_rescale = 0.f;
+  float sqrt_ac = 0.f, sqrt_1mac = 0.f, rescale = 1.f, sqrt_a_prev = 0.f, dir_coef = 0.f, sigma = 0.f;
+};
+void ddim_step(const DdimStepArgs& a, cudaStream_t st);
+
+}  // namespace mudg
