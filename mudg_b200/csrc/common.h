@@ -57,6 +57,7 @@ class Arena {
   void free(void* p);
   size_t capacity() const { return cap_; }
   size_t high_water() const { return high_; }
+  void reset_high() { high_ = 0; }
   bool planning = false;
 
  private:

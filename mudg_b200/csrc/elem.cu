@@ -317,6 +317,32 @@ __global__ void small_linear_kernel(const float* __restrict__ x, const __half* _
   }
 }
 
+// x [B][C][R] (fp32 or fp16; R = T*H*W rows, NCTHW) -> y [B][R][Cpad] fp16 channels-last, zero padded
+template <typename TS>
+__global__ void to_channels_last_kernel(const TS* __restrict__ x, __half* __restrict__ y, int B, int C, int64_t R,
+                                        int Cpad) {
+  const int64_t total = (int64_t)B * R * Cpad;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = i % Cpad;
+    const int64_t r = (i / Cpad) % R;
+    const int b = i / (Cpad * R);
+    y[i] = __float2half_rn(c < C ? static_cast<float>(x[((int64_t)b * C + c) * R + r]) : 0.f);
+  }
+}
+
+// dst[b][r][c] = (fp16) src[b][r0 + r][c]; src rows have pitch `cols`, batch pitch `src_rows * cols`
+template <typename TS>
+__global__ void gather_rows_kernel(const TS* __restrict__ src, __half* __restrict__ dst, int B, int src_rows, int r0,
+                                   int nrows, int cols) {
+  const int64_t total = (int64_t)B * nrows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = i % cols;
+    const int r = (i / cols) % nrows;
+    const int b = i / ((int64_t)cols * nrows);
+    dst[i] = __float2half_rn(static_cast<float>(src[((int64_t)b * src_rows + r0 + r) * cols + c]));
+  }
+}
+
 inline int grid_for(int64_t work, int threads) {
   int64_t b = (work + threads - 1) / threads;
   return (int)std::max<int64_t>(1, std::min<int64_t>(b, (int64_t)sm_count() * 16));
@@ -431,6 +457,25 @@ void small_linear(const float* x, const __half* W, const float* bias, float* y, 
   const int64_t threads = (int64_t)Bn * N * 32;
   small_linear_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, W, bias, y, Bn, N, K, silu_in ? 1 : 0,
                                                                         accumulate ? 1 : 0);
+  MUDG_CUDA(cudaGetLastError());
+}
+
+void to_channels_last(const void* x, bool x_fp32, __half* y, int B, int C, int64_t R, int Cpad, cudaStream_t st) {
+  const int64_t total = (int64_t)B * R * Cpad;
+  if (x_fp32)
+    to_channels_last_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const float*>(x), y, B, C, R, Cpad);
+  else
+    to_channels_last_kernel<__half><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const __half*>(x), y, B, C, R, Cpad);
+  MUDG_CUDA(cudaGetLastError());
+}
+
+void gather_rows_f16(const void* src, bool src_fp32, __half* dst, int B, int src_rows, int r0, int nrows, int cols,
+                     cudaStream_t st) {
+  const int64_t total = (int64_t)B * nrows * cols;
+  if (src_fp32)
+    gather_rows_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const float*>(src), dst, B, src_rows, r0, nrows, cols);
+  else
+    gather_rows_kernel<__half><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const __half*>(src), dst, B, src_rows, r0, nrows, cols);
   MUDG_CUDA(cudaGetLastError());
 }
 

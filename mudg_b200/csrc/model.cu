@@ -1,0 +1,841 @@
+#include "model.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace mudg {
+
+static int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ================================================================ WeightStore
+WeightStore::~WeightStore() {
+  for (auto& kv : w_) cudaFree(kv.second.w);
+  for (auto& kv : v_) cudaFree(kv.second.p);
+}
+
+void WeightStore::load(const std::string& key, const void* dev_ptr, int dtype, const int64_t* shape, int ndim,
+                       cudaStream_t st) {
+  MUDG_REQUIRE(ndim >= 1 && ndim <= 5, "weight %s: ndim %d", key.c_str(), ndim);
+  MUDG_REQUIRE(dtype == MUDG_F32 || dtype == MUDG_F16, "weight %s: dtype %d", key.c_str(), dtype);
+  drop(key);
+  if (ndim == 1) {
+    Vec v;
+    v.n = (int)shape[0];
+    MUDG_CUDA(cudaMalloc(&v.p, sizeof(float) * v.n));
+    cast_to_f32(dev_ptr, dtype == MUDG_F32, v.p, v.n, st);
+    v_[key] = v;
+    bytes_ += sizeof(float) * v.n;
+    return;
+  }
+  Weight w;
+  w.O = (int)shape[0];
+  w.I = (int)shape[1];
+  w.taps = 1;
+  for (int i = 2; i < ndim; i++) w.taps *= (int)shape[i];
+  w.Ipad = round_up(w.I, 8);
+  const size_t n = (size_t)w.O * w.taps * w.Ipad;
+  MUDG_CUDA(cudaMalloc(&w.w, n * sizeof(__half)));
+  pack_weight(dev_ptr, dtype == MUDG_F32, w.w, w.O, w.I, w.taps, w.Ipad, st);
+  w_[key] = w;
+  bytes_ += n * sizeof(__half);
+}
+
+const Weight& WeightStore::W(const std::string& key) const {
+  auto it = w_.find(key);
+  if (it == w_.end()) throw Error("missing weight: " + key);
+  return it->second;
+}
+const Vec& WeightStore::V(const std::string& key) const {
+  auto it = v_.find(key);
+  if (it == v_.end()) throw Error("missing weight: " + key);
+  return it->second;
+}
+void WeightStore::drop(const std::string& key) {
+  auto a = w_.find(key);
+  if (a != w_.end()) {
+    bytes_ -= (size_t)a->second.O * a->second.K() * sizeof(__half);
+    cudaFree(a->second.w);
+    w_.erase(a);
+  }
+  auto b = v_.find(key);
+  if (b != v_.end()) {
+    bytes_ -= sizeof(float) * b->second.n;
+    cudaFree(b->second.p);
+    v_.erase(b);
+  }
+}
+
+void WeightStore::stack_rows(const std::string& out_key, const std::vector<std::string>& keys, cudaStream_t st) {
+  if (hasW(out_key)) return;   // already fused
+  Weight o;
+  const Weight& f = W(keys[0]);
+  o.I = f.I; o.Ipad = f.Ipad; o.taps = f.taps;
+  for (auto& k : keys) {
+    const Weight& w = W(k);
+    MUDG_REQUIRE(w.K() == f.K(), "stack_rows: K mismatch for %s", k.c_str());
+    o.O += w.O;
+  }
+  MUDG_CUDA(cudaMalloc(&o.w, (size_t)o.O * o.K() * sizeof(__half)));
+  size_t off = 0;
+  for (auto& k : keys) {
+    const Weight& w = W(k);
+    const size_t n = (size_t)w.O * w.K();
+    MUDG_CUDA(cudaMemcpyAsync(o.w + off, w.w, n * sizeof(__half), cudaMemcpyDeviceToDevice, st));
+    off += n;
+  }
+  MUDG_CUDA(cudaStreamSynchronize(st));   // weight-load time only; the sources are freed right below
+  for (auto& k : keys) drop(k);
+  w_[out_key] = o;
+  bytes_ += off * sizeof(__half);
+}
+
+void WeightStore::make_geglu(const std::string& p, cudaStream_t st) {
+  if (hasW(p + ".geglu.weight")) return;
+  const Weight& w = W(p + ".weight");
+  const Vec& b = V(p + ".bias");
+  MUDG_REQUIRE(w.O % 128 == 0 && w.taps == 1, "GEGLU proj rows %d", w.O);
+  Weight o = w;
+  Vec ob;
+  ob.n = b.n;
+  MUDG_CUDA(cudaMalloc(&o.w, (size_t)w.O * w.K() * sizeof(__half)));
+  MUDG_CUDA(cudaMalloc(&ob.p, sizeof(float) * b.n));
+  geglu_interleave(w.w, b.p, o.w, ob.p, w.O / 2, w.K(), st);
+  MUDG_CUDA(cudaStreamSynchronize(st));
+  drop(p + ".weight");
+  drop(p + ".bias");
+  w_[p + ".geglu.weight"] = o;
+  v_[p + ".geglu.bias"] = ob;
+  bytes_ += (size_t)o.O * o.K() * sizeof(__half) + sizeof(float) * ob.n;
+}
+
+// ================================================================ Model: construction / plan
+Model::Model(int device, const MudgUNetConfig& u, const MudgVaeConfig& v) : ucfg_(u), vcfg_(v), device_(device) {
+  MUDG_REQUIRE(u.num_head_channels == 64, "kernels are specialised for num_head_channels == 64 (got %d)",
+               u.num_head_channels);
+  MUDG_REQUIRE(u.model_channels % 32 == 0, "model_channels must be a multiple of 32");
+  build_plan();
+}
+Model::~Model() {
+  for (auto& kv : kv_) {
+    cudaFree(kv.second.text);
+    cudaFree(kv.second.img);
+  }
+}
+
+// mirrors UNetModel.__init__ (openaimodel3d.py:398-565)
+void Model::build_plan() {
+  const MudgUNetConfig& c = ucfg_;
+  const int mc = c.model_channels;
+  auto has_attn = [&](int ds) {
+    for (int i = 0; i < c.n_attention_resolutions; i++)
+      if (c.attention_resolutions[i] == ds) return true;
+    return false;
+  };
+  auto pfx = [](const char* root, int a, int b) { return std::string(root) + "." + std::to_string(a) + "." + std::to_string(b); };
+  int res_count = 0;
+  auto res = [&](const std::string& p, int cin, int cout) {
+    Layer l; l.kind = "res"; l.prefix = p; l.cin = cin; l.cout = cout; l.res_index = res_count++;
+    return l;
+  };
+  auto spatial = [&](const std::string& p, int ch) {
+    Layer l; l.kind = "spatial"; l.prefix = p; l.ch = ch; l.heads = ch / 64; l.inner = ch;
+    return l;
+  };
+  auto temporal = [&](const std::string& p, int ch) {
+    Layer l; l.kind = "temporal"; l.prefix = p; l.ch = ch; l.heads = ch / 64; l.inner = ch; l.linear_proj = true;
+    return l;
+  };
+  in_blocks_.clear(); out_blocks_.clear();
+  {
+    Block b; Layer l; l.kind = "conv"; l.prefix = "input_blocks.0.0"; l.cin = c.in_channels; l.cout = mc;
+    b.layers.push_back(l); in_blocks_.push_back(b);
+  }
+  std::vector<int> chans{mc};
+  int ch = mc, ds = 1, idx = 1;
+  for (int level = 0; level < c.n_channel_mult; level++) {
+    const int mult = c.channel_mult[level];
+    for (int r = 0; r < c.num_res_blocks; r++) {
+      Block b;
+      b.layers.push_back(res(pfx("input_blocks", idx, 0), ch, mult * mc));
+      ch = mult * mc;
+      if (has_attn(ds)) {
+        b.layers.push_back(spatial(pfx("input_blocks", idx, 1), ch));
+        b.layers.push_back(temporal(pfx("input_blocks", idx, 2), ch));
+      }
+      in_blocks_.push_back(b); chans.push_back(ch); idx++;
+    }
+    if (level != c.n_channel_mult - 1) {
+      Block b; Layer l; l.kind = "down"; l.prefix = pfx("input_blocks", idx, 0); l.ch = ch;
+      b.layers.push_back(l); in_blocks_.push_back(b); chans.push_back(ch); idx++; ds *= 2;
+    }
+  }
+  mid_.layers.clear();
+  mid_.layers.push_back(res("middle_block.0", ch, ch));
+  mid_.layers.push_back(spatial("middle_block.1", ch));
+  mid_.layers.push_back(temporal("middle_block.2", ch));
+  mid_.layers.push_back(res("middle_block.3", ch, ch));
+  int oidx = 0;
+  for (int level = c.n_channel_mult - 1; level >= 0; level--) {
+    const int mult = c.channel_mult[level];
+    for (int i = 0; i <= c.num_res_blocks; i++) {
+      const int ich = chans.back(); chans.pop_back();
+      Block b; int li = 0;
+      b.layers.push_back(res(pfx("output_blocks", oidx, li++), ch + ich, mc * mult));
+      ch = mc * mult;
+      if (has_attn(ds)) {
+        b.layers.push_back(spatial(pfx("output_blocks", oidx, li++), ch));
+        b.layers.push_back(temporal(pfx("output_blocks", oidx, li++), ch));
+      }
+      if (level && i == c.num_res_blocks) {
+        Layer l; l.kind = "up"; l.prefix = pfx("output_blocks", oidx, li++); l.ch = ch;
+        b.layers.push_back(l); ds /= 2;
+      }
+      out_blocks_.push_back(b); oidx++;
+    }
+  }
+  n_res_ = res_count;
+}
+
+void Model::finalize(int which, cudaStream_t st) {
+  if (which == MUDG_VAE) {
+    // touch every key Decoder.forward needs (throws on a missing one)
+    const MudgVaeConfig& v = vcfg_;
+    auto need_res = [&](const std::string& p, int ci, int co) {
+      vae_w.V(p + ".norm1.weight"); vae_w.W(p + ".conv1.weight"); vae_w.V(p + ".norm2.bias"); vae_w.W(p + ".conv2.weight");
+      if (ci != co) vae_w.W(p + ".nin_shortcut.weight");
+    };
+    int block_in = v.ch * v.ch_mult[v.n_ch_mult - 1];
+    vae_w.W("post_quant_conv.weight"); vae_w.W("decoder.conv_in.weight");
+    need_res("decoder.mid.block_1", block_in, block_in);
+    for (const char* n : {"q", "k", "v", "proj_out"}) vae_w.W(std::string("decoder.mid.attn_1.") + n + ".weight");
+    need_res("decoder.mid.block_2", block_in, block_in);
+    for (int lvl = v.n_ch_mult - 1; lvl >= 0; lvl--) {
+      const int block_out = v.ch * v.ch_mult[lvl];
+      for (int ib = 0; ib <= v.num_res_blocks; ib++) {
+        need_res("decoder.up." + std::to_string(lvl) + ".block." + std::to_string(ib), block_in, block_out);
+        block_in = block_out;
+      }
+      if (lvl != 0) vae_w.W("decoder.up." + std::to_string(lvl) + ".upsample.conv.weight");
+    }
+    vae_w.V("decoder.norm_out.weight"); vae_w.W("decoder.conv_out.weight");
+    vae_ready_ = true;
+    return;
+  }
+  WeightStore& w = unet_w;
+  auto fuse_block = [&](const std::string& tb, bool cross) {
+    w.stack_rows(tb + ".attn1.qkv.weight", {tb + ".attn1.to_q.weight", tb + ".attn1.to_k.weight", tb + ".attn1.to_v.weight"}, st);
+    if (cross) {
+      w.stack_rows(tb + ".attn2.kv_text.weight", {tb + ".attn2.to_k.weight", tb + ".attn2.to_v.weight"}, st);
+      w.stack_rows(tb + ".attn2.kv_img.weight", {tb + ".attn2.to_k_ip.weight", tb + ".attn2.to_v_ip.weight"}, st);
+      w.W(tb + ".attn2.to_q.weight");
+    } else {
+      w.stack_rows(tb + ".attn2.qkv.weight", {tb + ".attn2.to_q.weight", tb + ".attn2.to_k.weight", tb + ".attn2.to_v.weight"}, st);
+    }
+    w.make_geglu(tb + ".ff.net.0.proj", st);
+    for (const char* n : {".attn1.to_out.0", ".attn2.to_out.0", ".ff.net.2"}) { w.W(tb + n + ".weight"); w.V(tb + n + ".bias"); }
+    for (const char* n : {".norm1", ".norm2", ".norm3"}) { w.V(tb + n + ".weight"); w.V(tb + n + ".bias"); }
+  };
+  auto visit = [&](const Layer& l) {
+    if (l.kind == "spatial" || l.kind == "temporal") {
+      fuse_block(l.prefix + ".transformer_blocks.0", l.kind == "spatial");
+      w.V(l.prefix + ".norm.weight"); w.W(l.prefix + ".proj_in.weight"); w.W(l.prefix + ".proj_out.weight");
+    } else if (l.kind == "res") {
+      w.V(l.prefix + ".in_layers.0.weight"); w.W(l.prefix + ".in_layers.2.weight"); w.W(l.prefix + ".emb_layers.1.weight");
+      w.V(l.prefix + ".out_layers.0.weight"); w.W(l.prefix + ".out_layers.3.weight");
+      if (l.cin != l.cout) w.W(l.prefix + ".skip_connection.weight");
+      for (int j = 1; j <= 4; j++) {
+        const std::string q = l.prefix + ".temopral_conv.conv" + std::to_string(j);
+        w.V(q + ".0.weight"); w.W(q + (j == 1 ? ".2" : ".3") + ".weight");
+      }
+    } else if (l.kind == "down") w.W(l.prefix + ".op.weight");
+    else if (l.kind == "up") w.W(l.prefix + ".conv.weight");
+    else if (l.kind == "conv") w.W(l.prefix + ".weight");
+  };
+  for (auto& b : in_blocks_) for (auto& l : b.layers) visit(l);
+  for (auto& l : mid_.layers) visit(l);
+  for (auto& b : out_blocks_) for (auto& l : b.layers) visit(l);
+  Layer ia; ia.kind = "temporal"; ia.prefix = "init_attn.0";
+  visit(ia);
+  for (const char* n : {"time_embed", "class_embed", "fps_embedding"})
+    for (const char* k : {".0", ".2"}) { w.W(std::string(n) + k + ".weight"); w.V(std::string(n) + k + ".bias"); }
+  w.V("out.0.weight"); w.W("out.2.weight");
+  unet_ready_ = true;
+}
+
+// ================================================================ allocation helpers
+void Model::ensure_arena(size_t bytes) {
+  if (arena_.capacity() < bytes) {
+    MUDG_CUDA(cudaDeviceSynchronize());
+    arena_.reserve(bytes + (bytes >> 4));
+  }
+}
+Act Model::alloc(int B, int T, int H, int W, int C) {
+  Act a; a.B = B; a.T = T; a.H = H; a.W = W; a.C = C;
+  a.p = static_cast<__half*>(arena_.alloc(a.bytes()));
+  return a;
+}
+void Model::release(Act& a) {
+  if (a.p) arena_.free(a.p);
+  a.p = nullptr;
+}
+void* Model::alloc_bytes(size_t n) { return arena_.alloc(n); }
+void Model::release_bytes(void* p) { arena_.free(p); }
+
+// ================================================================ ops
+Act Model::group_norm(const Act& x, const std::string& p, float eps, bool silu, bool over_time) {
+  const int S = over_time ? x.B : x.B * x.T;
+  const int64_t rps = over_time ? (int64_t)x.T * x.H * x.W : (int64_t)x.H * x.W;
+  Act y = alloc(x.B, x.T, x.H, x.W, x.C);
+  double* sums = static_cast<double*>(alloc_bytes(sizeof(double) * S * 64));
+  float* scale = static_cast<float*>(alloc_bytes(sizeof(float) * S * x.C * 2));
+  if (live()) {
+    const Vec& g = ws_->V(p + ".weight");
+    const Vec& b = ws_->V(p + ".bias");
+    MUDG_REQUIRE(g.n == x.C, "GroupNorm %s: %d channels vs activation %d", p.c_str(), g.n, x.C);
+    gn_scale_shift(x.p, S, rps, x.C, g.p, b.p, eps, sums, scale, scale + (size_t)S * x.C, st_);
+    gn_apply(x.p, y.p, scale, scale + (size_t)S * x.C, x.rows(), x.C, rps, silu, st_);
+    launches += 4;
+  }
+  release_bytes(sums);
+  release_bytes(scale);
+  return y;
+}
+
+Act Model::layer_norm(const Act& x, const std::string& p) {
+  Act y = alloc(x.B, x.T, x.H, x.W, x.C);
+  if (live()) {
+    layernorm(x.p, y.p, ws_->V(p + ".weight").p, ws_->V(p + ".bias").p, x.rows(), x.C, 1e-5f, st_);
+    launches++;
+  }
+  return y;
+}
+
+Act Model::linear(const Act& x, const std::string& wkey, const std::string& bkey, const Act* residual, bool geglu,
+                  float alpha) {
+  const Weight& w0 = ws_->W(wkey);
+  MUDG_REQUIRE(w0.K() == x.C, "linear %s: K %d vs activation width %d", wkey.c_str(), w0.K(), x.C);
+  const int n_out = geglu ? w0.O / 2 : w0.O;
+  Act y = alloc(x.B, x.T, x.H, x.W, n_out);
+  if (live()) {
+    const Weight& w = ws_->W(wkey);
+    MUDG_REQUIRE(x.rows() < (int64_t(1) << 31), "too many rows");
+    TapGemm g;
+    g.A = x.p; g.B = 1; g.T = 1; g.H = 1; g.W = (int)x.rows(); g.Cin = x.C;
+    g.ntaps = 1;
+    g.Wt = w.w; g.N = w.O;
+    g.D = y.p;
+    g.R = residual ? residual->p : nullptr;
+    g.bias = bkey.empty() ? nullptr : ws_->V(bkey).p;
+    g.alpha = alpha; g.geglu = geglu;
+    if (residual) MUDG_REQUIRE(residual->C == n_out && residual->rows() == x.rows(), "linear %s: residual shape", wkey.c_str());
+    tapgemm(g, st_);
+    launches++;
+  }
+  return y;
+}
+
+Act Model::conv3x3(const Act& x, const std::string& p, const Act* residual, const float* bias2) {
+  const Weight& w = ws_->W(p + ".weight");
+  Act y = alloc(x.B, x.T, x.H, x.W, w.O);
+  if (live()) {
+    MUDG_REQUIRE(w.taps == 9 && w.Ipad == x.C, "conv3x3 %s: weight [%d][%d][%d] vs activation C=%d", p.c_str(), w.O, w.taps,
+                 w.Ipad, x.C);
+    TapGemm g;
+    g.A = x.p; g.B = 1; g.T = x.B * x.T; g.H = x.H; g.W = x.W; g.Cin = x.C;   // frames are independent
+    g.ntaps = 9; set_taps_3x3(g.taps);
+    g.Wt = w.w; g.N = w.O; g.D = y.p;
+    g.R = residual ? residual->p : nullptr;
+    g.bias = ws_->V(p + ".bias").p;
+    if (bias2) { g.bias2 = bias2; g.bias2_div = T_real_; g.nb2 = N_; }
+    tapgemm(g, st_);
+    launches++;
+  }
+  return y;
+}
+
+Act Model::conv_t3(const Act& x, const std::string& p, const Act* residual) {
+  const Weight& w = ws_->W(p + ".weight");
+  Act y = alloc(x.B, x.T, x.H, x.W, w.O);
+  if (live()) {
+    MUDG_REQUIRE(w.taps == 3 && w.Ipad == x.C, "temporal conv %s: weight shape", p.c_str());
+    TapGemm g;
+    g.A = x.p; g.B = x.B; g.T = x.T; g.H = x.H; g.W = x.W; g.Cin = x.C;
+    g.ntaps = 3; set_taps_t3(g.taps);
+    g.Wt = w.w; g.N = w.O; g.D = y.p;
+    g.R = residual ? residual->p : nullptr;
+    g.bias = ws_->V(p + ".bias").p;
+    tapgemm(g, st_);
+    launches++;
+  }
+  return y;
+}
+
+Act Model::concat(const Act& a, const Act& b) {
+  Act y = alloc(a.B, a.T, a.H, a.W, a.C + b.C);
+  if (live()) {
+    concat_channels(a.p, a.C, b.p, b.C, y.p, a.rows(), st_);
+    launches++;
+  }
+  return y;
+}
+
+Act Model::upsample(const Act& x) {
+  Act y = alloc(x.B, x.T, 2 * x.H, 2 * x.W, x.C);
+  if (live()) {
+    upsample2x(x.p, y.p, x.B * x.T, x.H, x.W, x.C, st_);
+    launches++;
+  }
+  return y;
+}
+
+Act Model::downsample(const Act& x, const std::string& p) {   // Conv2d 3x3 stride 2 pad 1 (openaimodel3d.py:66-70)
+  const int Ho = (x.H - 1) / 2 + 1, Wo = (x.W - 1) / 2 + 1;
+  Act col = alloc(x.B, x.T, Ho, Wo, 9 * x.C);
+  if (live()) {
+    im2col_s2(x.p, col.p, x.B * x.T, x.H, x.W, x.C, st_);
+    launches++;
+  }
+  Act y = linear(col, p + ".op.weight", p + ".op.bias", nullptr);
+  release(col);
+  return y;
+}
+
+// ================================================================ UNet blocks
+Act Model::res_block(const Act& x, const Layer& l) {   // ResBlock._forward (openaimodel3d.py:210-236)
+  const std::string& p = l.prefix;
+  Act a = group_norm(x, p + ".in_layers.0", 1e-5f, true, false);
+  Act h = conv3x3(a, p + ".in_layers.2", nullptr, emb_out_[l.res_index]);
+  release(a);
+  Act a2 = group_norm(h, p + ".out_layers.0", 1e-5f, true, false);
+  release(h);
+  Act skip;
+  const bool has_skip = l.cin != l.cout;
+  if (has_skip) skip = linear(x, p + ".skip_connection.weight", p + ".skip_connection.bias", nullptr);
+  Act h2 = conv3x3(a2, p + ".out_layers.3", has_skip ? &skip : &x, nullptr);
+  release(a2);
+  if (has_skip) release(skip);
+  // TemporalConvBlock (openaimodel3d.py:272-279): GroupNorm statistics span (C/32, T, H, W)
+  Act y = h2;
+  for (int j = 1; j <= 4; j++) {
+    const std::string q = p + ".temopral_conv.conv" + std::to_string(j);
+    Act n = group_norm(y, q + ".0", 1e-5f, true, true);
+    if (j > 1) release(y);
+    y = conv_t3(n, q + (j == 1 ? ".2" : ".3"), j == 4 ? &h2 : nullptr);
+    release(n);
+  }
+  release(h2);
+  return y;
+}
+
+// LN3 -> GEGLU FF -> +x   (BasicTransformerBlock._forward last line, attention.py:399); consumes x
+Act Model::transformer_block_tail(Act x, const std::string& tb) {
+  Act n3 = layer_norm(x, tb + ".norm3");
+  Act hid = linear(n3, tb + ".ff.net.0.proj.geglu.weight", tb + ".ff.net.0.proj.geglu.bias", nullptr, true);
+  release(n3);
+  Act y = linear(hid, tb + ".ff.net.2.weight", tb + ".ff.net.2.bias", &x);
+  release(hid);
+  release(x);
+  return y;
+}
+
+Act Model::spatial_transformer(const Act& xin, const Layer& l) {   // attention.py:451-467, use_linear=True
+  const std::string& p = l.prefix;
+  const std::string tb = p + ".transformer_blocks.0";
+  const int C = l.ch, F = xin.B * xin.T, HW = xin.H * xin.W;
+  Act g = group_norm(xin, p + ".norm", 1e-6f, false, false);
+  Act x = linear(g, p + ".proj_in.weight", p + ".proj_in.bias", nullptr);
+  release(g);
+  // attn1: self-attention over the H*W tokens of each frame
+  Act n1 = layer_norm(x, tb + ".norm1");
+  Act qkv = linear(n1, tb + ".attn1.qkv.weight", "", nullptr);
+  release(n1);
+  Act a1 = alloc(xin.B, xin.T, xin.H, xin.W, C);
+  if (live()) {
+    FlashArgs fa;
+    fa.Q = qkv.p; fa.q_pitch = 3 * C; fa.O = a1.p; fa.o_pitch = C; fa.F = F; fa.Nq = HW; fa.heads = l.heads;
+    fa.nseg = 1;
+    fa.seg[0].K = qkv.p + C; fa.seg[0].V = qkv.p + 2 * C; fa.seg[0].pitch = 3 * C; fa.seg[0].len = HW;
+    fa.seg[0].nbatch = F; fa.seg[0].kv_div = 1;
+    fa.scale = 0.125f;
+    flash_attention(fa, st_);
+    launches++;
+  }
+  release(qkv);
+  Act x1 = linear(a1, tb + ".attn1.to_out.0.weight", tb + ".attn1.to_out.0.bias", &x);
+  release(a1);
+  release(x);
+  // attn2: text (77 tokens, shared by the frames of a sample) + image tokens, separate softmaxes summed
+  Act n2 = layer_norm(x1, tb + ".norm2");
+  Act q = linear(n2, tb + ".attn2.to_q.weight", "", nullptr);
+  release(n2);
+  Act a2 = alloc(xin.B, xin.T, xin.H, xin.W, C);
+  if (live()) {
+    auto it = kv_.find(p);
+    MUDG_REQUIRE(it != kv_.end() && ctx_N_ == N_ && ctx_T_ == T_real_, "mudg_set_context(N=%d, T=%d) must precede the forward",
+                 N_, T_real_);
+    const KvCache& kc = it->second;
+    FlashArgs fa;
+    fa.Q = q.p; fa.q_pitch = C; fa.O = a2.p; fa.o_pitch = C; fa.F = F; fa.Nq = HW; fa.heads = l.heads;
+    fa.nseg = 2;
+    fa.seg[0].K = kc.text; fa.seg[0].V = kc.text + C; fa.seg[0].pitch = 2 * C; fa.seg[0].len = ucfg_.text_context_len;
+    fa.seg[0].nbatch = N_; fa.seg[0].kv_div = T_real_;
+    fa.seg[1].K = kc.img; fa.seg[1].V = kc.img + C; fa.seg[1].pitch = 2 * C;
+    if (ctx_per_frame_) { fa.seg[1].len = 16; fa.seg[1].nbatch = N_ * T_real_; fa.seg[1].kv_div = 1; }
+    else { fa.seg[1].len = ctx_Limg_; fa.seg[1].nbatch = N_; fa.seg[1].kv_div = T_real_; }
+    fa.scale = 0.125f;
+    flash_attention(fa, st_);
+    launches++;
+  }
+  release(q);
+  Act x2 = linear(a2, tb + ".attn2.to_out.0.weight", tb + ".attn2.to_out.0.bias", &x1);
+  release(a2);
+  release(x1);
+  Act x3 = transformer_block_tail(x2, tb);
+  Act y = linear(x3, p + ".proj_out.weight", p + ".proj_out.bias", &xin);
+  release(x3);
+  return y;
+}
+
+Act Model::temporal_transformer(const Act& xin, const Layer& l) {   // attention.py:529-576
+  const std::string& p = l.prefix;
+  const std::string tb = p + ".transformer_blocks.0";
+  const int HW = xin.H * xin.W;
+  Act g = group_norm(xin, p + ".norm", 1e-6f, false, true);
+  Act x = linear(g, p + ".proj_in.weight", p + ".proj_in.bias", nullptr);
+  release(g);
+  for (int k = 1; k <= 2; k++) {   // attn1 and attn2 are both self-attention over T (only_self_att)
+    const std::string an = tb + ".attn" + std::to_string(k);
+    Act n = layer_norm(x, tb + ".norm" + std::to_string(k));
+    Act qkv = linear(n, an + ".qkv.weight", "", nullptr);
+    release(n);
+    Act a = alloc(xin.B, xin.T, xin.H, xin.W, l.inner);
+    if (live()) {
+      temporal_attention(qkv.p, a.p, xin.B, xin.T, HW, l.heads, 0.125f, st_);
+      launches++;
+    }
+    release(qkv);
+    Act xn = linear(a, an + ".to_out.0.weight", an + ".to_out.0.bias", &x);
+    release(a);
+    release(x);
+    x = xn;
+  }
+  Act x3 = transformer_block_tail(x, tb);
+  Act y = linear(x3, p + ".proj_out.weight", p + ".proj_out.bias", &xin);
+  release(x3);
+  return y;
+}
+
+// TimestepEmbedSequential dispatch (openaimodel3d.py:36-48).  Frees the intermediate tensors; the block input
+// is freed only when `owns_input` (skip tensors stay alive until the output path consumes them).
+Act Model::run_block(Act h, const Block& b, bool owns_input) {
+  bool owned = owns_input;
+  for (const Layer& l : b.layers) {
+    Act y;
+    if (l.kind == "res") y = res_block(h, l);
+    else if (l.kind == "spatial") y = spatial_transformer(h, l);
+    else if (l.kind == "temporal") y = temporal_transformer(h, l);
+    else if (l.kind == "down") y = downsample(h, l.prefix);
+    else if (l.kind == "up") { Act u = upsample(h); y = conv3x3(u, l.prefix + ".conv", nullptr, nullptr); release(u); }
+    else if (l.kind == "conv") y = conv3x3(h, l.prefix, nullptr, nullptr);
+    else throw Error("unknown layer kind " + l.kind);
+    if (owned) release(h);
+    owned = true;
+    h = y;
+  }
+  return h;
+}
+
+// time_embed(t) + class_embed(label) + fps_embedding(fs), then every ResBlock's Linear(SiLU(emb))
+// (openaimodel3d.py:569-576,594-602 and :219).  Computed on N rows, not N*T (emb is repeated over frames).
+void Model::compute_embeddings(const int64_t* t, const int64_t* label, const int64_t* fs, int N) {
+  const int mc = ucfg_.model_channels, ted = 4 * mc;
+  float* sin_buf = static_cast<float*>(alloc_bytes(sizeof(float) * N * mc));
+  float* hid = static_cast<float*>(alloc_bytes(sizeof(float) * N * ted));
+  float* emb = static_cast<float*>(alloc_bytes(sizeof(float) * N * ted));
+  const char* names[3] = {"time_embed", "class_embed", "fps_embedding"};
+  const int64_t* idx[3] = {t, label, fs};
+  if (live()) {
+    for (int i = 0; i < 3; i++) {
+      const std::string n = names[i];
+      sinusoid(idx[i], sin_buf, N, mc, st_);
+      small_linear(sin_buf, ws_->W(n + ".0.weight").w, ws_->V(n + ".0.bias").p, hid, N, ted, mc, false, false, st_);
+      small_linear(hid, ws_->W(n + ".2.weight").w, ws_->V(n + ".2.bias").p, emb, N, ted, ted, true, i > 0, st_);
+      launches += 3;
+    }
+  }
+  emb_out_.assign(n_res_, nullptr);
+  auto visit = [&](const Layer& l) {
+    if (l.kind != "res") return;
+    float* e = static_cast<float*>(alloc_bytes(sizeof(float) * N * l.cout));
+    emb_out_[l.res_index] = e;
+    if (live()) {
+      small_linear(emb, ws_->W(l.prefix + ".emb_layers.1.weight").w, ws_->V(l.prefix + ".emb_layers.1.bias").p, e, N, l.cout,
+                   ted, true, false, st_);
+      launches++;
+    }
+  };
+  for (auto& b : in_blocks_) for (auto& l : b.layers) visit(l);
+  for (auto& l : mid_.layers) visit(l);
+  for (auto& b : out_blocks_) for (auto& l : b.layers) visit(l);
+  release_bytes(sin_buf);
+  release_bytes(hid);
+  release_bytes(emb);
+}
+
+void Model::unet_body(const void* x, const int64_t* t, const int64_t* label, const int64_t* fs, int N, int T, int h, int w,
+                      void* out) {
+  ws_ = &unet_w;
+  N_ = N; T_real_ = T;
+  arena_.reset();
+  compute_embeddings(t, label, fs, N);
+  const int cpad = round_up(ucfg_.in_channels, 8);
+  Act xin = alloc(N, T, h, w, cpad);
+  if (live()) {
+    to_channels_last(x, true, xin.p, N, ucfg_.in_channels, (int64_t)T * h * w, cpad, st_);
+    launches++;
+  }
+  std::vector<Act> hs;
+  Act cur = run_block(xin, in_blocks_[0], true);
+  {
+    Layer ia; ia.kind = "temporal"; ia.prefix = "init_attn.0"; ia.ch = ucfg_.model_channels;
+    ia.heads = ucfg_.init_attn_heads; ia.inner = ucfg_.init_attn_heads * 64; ia.linear_proj = false;
+    Act y = temporal_transformer(cur, ia);
+    release(cur);
+    cur = y;
+  }
+  hs.push_back(cur);
+  for (size_t i = 1; i < in_blocks_.size(); i++) {
+    cur = run_block(cur, in_blocks_[i], false);   // the input is a skip tensor: keep it
+    hs.push_back(cur);
+  }
+  cur = run_block(cur, mid_, false);              // hs.back() is still needed by output block 0
+  for (const Block& b : out_blocks_) {
+    Act skip = hs.back(); hs.pop_back();
+    Act cat = concat(cur, skip);
+    release(cur);
+    release(skip);
+    cur = run_block(cat, b, true);
+  }
+  // out: GroupNorm32 + SiLU + Conv3x3(model_channels -> out_channels), written as [N, Cout, T, h, w] fp16
+  Act o = group_norm(cur, "out.0", 1e-5f, true, false);
+  release(cur);
+  if (live()) {
+    const Weight& wt = ws_->W("out.2.weight");
+    TapGemmGeneric g;
+    g.A = o.p; g.a_fp32 = false;
+    g.B = N; g.T = T; g.H = h; g.W = w; g.Cin = o.C;
+    g.a_sc = 1; g.a_sw = o.C; g.a_sh = (int64_t)w * o.C; g.a_st = (int64_t)h * w * o.C; g.a_sb = (int64_t)T * h * w * o.C;
+    g.ntaps = 9; set_taps_3x3(g.taps);
+    g.Wt = wt.w; g.CinW = wt.Ipad; g.N = wt.O;
+    g.D = out; g.d_fp32 = false;
+    g.d_sw = 1; g.d_sh = w; g.d_st = (int64_t)h * w; g.d_sn = (int64_t)T * h * w; g.d_sb = (int64_t)wt.O * T * h * w;
+    g.bias = ws_->V("out.2.bias").p;
+    tapgemm_generic(g, st_);
+    launches++;
+  }
+  release(o);
+}
+
+// ================================================================ context (cross-attention K/V cache)
+void Model::set_context(const void* ctx, int dtype, int N, int L, int T, cudaStream_t st) {
+  MUDG_REQUIRE(unet_ready_, "weights not finalized");
+  const int tl = ucfg_.text_context_len, D = ucfg_.context_dim;
+  MUDG_REQUIRE(L > tl, "context needs image tokens after the %d text tokens (L=%d)", tl, L);
+  const int Limg = L - tl;
+  const bool per_frame = (L == tl + 16 * T);     // openaimodel3d.py:581 hard-coded split
+  __half *text = nullptr, *img = nullptr;
+  MUDG_CUDA(cudaMalloc(&text, sizeof(__half) * (size_t)N * tl * D));
+  MUDG_CUDA(cudaMalloc(&img, sizeof(__half) * (size_t)N * Limg * D));
+  gather_rows_f16(ctx, dtype == MUDG_F32, text, N, L, 0, tl, D, st);
+  gather_rows_f16(ctx, dtype == MUDG_F32, img, N, L, tl, Limg, D, st);
+  auto visit = [&](const Layer& l) {
+    if (l.kind != "spatial") return;
+    const int C = l.ch;
+    KvCache& kc = kv_[l.prefix];
+    const size_t tb = sizeof(__half) * (size_t)N * tl * 2 * C, ib = sizeof(__half) * (size_t)N * Limg * 2 * C;
+    if (kc.text_bytes < tb) { cudaFree(kc.text); MUDG_CUDA(cudaMalloc(&kc.text, tb)); kc.text_bytes = tb; }
+    if (kc.img_bytes < ib) { cudaFree(kc.img); MUDG_CUDA(cudaMalloc(&kc.img, ib)); kc.img_bytes = ib; }
+    const std::string tbp = l.prefix + ".transformer_blocks.0.attn2.";
+    for (int k = 0; k < 2; k++) {
+      const Weight& w = unet_w.W(tbp + (k ? "kv_img.weight" : "kv_text.weight"));
+      MUDG_REQUIRE(w.K() == D, "context_dim mismatch");
+      TapGemm g;
+      g.A = k ? img : text; g.B = 1; g.T = 1; g.H = 1; g.W = N * (k ? Limg : tl); g.Cin = D;
+      g.ntaps = 1; g.Wt = w.w; g.N = w.O; g.D = k ? kc.img : kc.text;
+      tapgemm(g, st);
+      launches++;
+    }
+  };
+  for (auto& b : in_blocks_) for (auto& l : b.layers) visit(l);
+  for (auto& l : mid_.layers) visit(l);
+  for (auto& b : out_blocks_) for (auto& l : b.layers) visit(l);
+  MUDG_CUDA(cudaStreamSynchronize(st));   // once per clip; the staging buffers are freed here
+  cudaFree(text);
+  cudaFree(img);
+  ctx_N_ = N; ctx_L_ = L; ctx_T_ = T; ctx_Limg_ = Limg; ctx_per_frame_ = per_frame;
+}
+
+// ================================================================ entry points
+size_t Model::plan_unet(int N, int T, int h, int w) {
+  MUDG_REQUIRE(unet_ready_, "weights not finalized");
+  arena_.planning = true;
+  planning_ = true;
+  arena_.reset_high();
+  unet_body(nullptr, nullptr, nullptr, nullptr, N, T, h, w, nullptr);
+  const size_t need = arena_.high_water();
+  arena_.planning = false;
+  planning_ = false;
+  arena_.reset();
+  return need;
+}
+
+void Model::unet_forward(const void* x, const int64_t* t, const int64_t* label, const int64_t* fs, int N, int T, int h, int w,
+                         void* out, cudaStream_t st) {
+  MUDG_REQUIRE(unet_ready_, "weights not finalized");
+  std::array<int, 4> key{N, T, h, w};
+  auto it = unet_plans_.find(key);
+  if (it == unet_plans_.end()) it = unet_plans_.emplace(key, plan_unet(N, T, h, w)).first;
+  ensure_arena(it->second);
+  st_ = st;
+  unet_body(x, t, label, fs, N, T, h, w, out);
+}
+
+// ================================================================ VAE decoder (ae_modules.py:466-578)
+Act Model::gemm_raw(const __half* A, int M, int K, const __half* Wt, int N, const float* bias, const Act* residual,
+                    float alpha) {
+  Act y = alloc(1, 1, 1, M, N);
+  if (live()) {
+    TapGemm g;
+    g.A = A; g.B = 1; g.T = 1; g.H = 1; g.W = M; g.Cin = K; g.ntaps = 1;
+    g.Wt = Wt; g.N = N; g.D = y.p; g.R = residual ? residual->p : nullptr; g.bias = bias; g.alpha = alpha;
+    tapgemm(g, st_);
+    launches++;
+  }
+  return y;
+}
+
+Act Model::vae_res(const Act& x, const std::string& p) {   // ResnetBlock.forward, temb=None (ae_modules.py:190-210)
+  Act a = group_norm(x, p + ".norm1", 1e-6f, true, false);
+  Act h = conv3x3(a, p + ".conv1", nullptr, nullptr);
+  release(a);
+  Act a2 = group_norm(h, p + ".norm2", 1e-6f, true, false);
+  release(h);
+  const bool has_skip = ws_->hasW(p + ".nin_shortcut.weight");
+  Act skip;
+  if (has_skip) skip = linear(x, p + ".nin_shortcut.weight", p + ".nin_shortcut.bias", nullptr);
+  Act y = conv3x3(a2, p + ".conv2", has_skip ? &skip : &x, nullptr);
+  release(a2);
+  if (has_skip) release(skip);
+  return y;
+}
+
+// AttnBlock.forward (ae_modules.py:53-78): one head, d = C.  Scores are materialised once per frame
+// (N x N fp16, 170 MB at 72x128) -- 0.05 % of a clip's FLOPs, so three plain GEMMs + a row softmax.
+Act Model::vae_attn(const Act& x, const std::string& p) {
+  const int M = (int)x.rows(), C = x.C;
+  Act y = group_norm(x, p + ".norm", 1e-6f, false, false);
+  Act q = linear(y, p + ".q.weight", p + ".q.bias", nullptr);
+  Act k = linear(y, p + ".k.weight", p + ".k.bias", nullptr);
+  // V^T[c, token] = Wv[c, :] . y[token, :]  (bias added after P V: softmax rows sum to 1)
+  const Weight& wv = ws_->W(p + ".v.weight");
+  Act vt = gemm_raw(wv.w, C, C, y.p, M, nullptr, nullptr, 1.f);
+  release(y);
+  Act s = gemm_raw(q.p, M, C, k.p, M, nullptr, nullptr, 1.f / sqrtf((float)C));
+  release(q);
+  release(k);
+  if (live()) {
+    softmax_rows(s.p, M, M, st_);
+    launches++;
+  }
+  Act o = gemm_raw(s.p, M, M, vt.p, C, ws_->V(p + ".v.bias").p, nullptr, 1.f);
+  release(s);
+  release(vt);
+  o.B = x.B; o.T = x.T; o.H = x.H; o.W = x.W;
+  Act out = linear(o, p + ".proj_out.weight", p + ".proj_out.bias", &x);
+  release(o);
+  return out;
+}
+
+void Model::vae_body(const void* z, int h, int w, void* out) {
+  ws_ = &vae_w;
+  N_ = 1; T_real_ = 1;
+  arena_.reset();
+  const MudgVaeConfig& v = vcfg_;
+  const int cpad = round_up(v.z_channels, 8);
+  Act zin = alloc(1, 1, h, w, cpad);
+  Act zq = alloc(1, 1, h, w, cpad);
+  if (live()) {
+    to_channels_last(z, true, zin.p, 1, v.z_channels, (int64_t)h * w, cpad, st_);
+    MUDG_CUDA(cudaMemsetAsync(zq.p, 0, zq.bytes(), st_));
+    const Weight& wt = ws_->W("post_quant_conv.weight");       // 1x1 conv (autoencoder.py:105)
+    TapGemmGeneric g;
+    g.A = zin.p; g.B = 1; g.T = 1; g.H = h; g.W = w; g.Cin = wt.Ipad;
+    g.a_sc = 1; g.a_sw = cpad; g.a_sh = (int64_t)w * cpad;
+    g.ntaps = 1; g.Wt = wt.w; g.CinW = wt.Ipad; g.N = wt.O;
+    g.D = zq.p; g.d_sn = 1; g.d_sw = cpad; g.d_sh = (int64_t)w * cpad;
+    g.bias = ws_->V("post_quant_conv.bias").p;
+    tapgemm_generic(g, st_);
+    launches += 3;
+  }
+  release(zin);
+  Act cur = conv3x3(zq, "decoder.conv_in", nullptr, nullptr);
+  release(zq);
+  auto step = [&](Act y) { release(cur); cur = y; };
+  step(vae_res(cur, "decoder.mid.block_1"));
+  step(vae_attn(cur, "decoder.mid.attn_1"));
+  step(vae_res(cur, "decoder.mid.block_2"));
+  for (int lvl = v.n_ch_mult - 1; lvl >= 0; lvl--) {
+    for (int ib = 0; ib <= v.num_res_blocks; ib++)
+      step(vae_res(cur, "decoder.up." + std::to_string(lvl) + ".block." + std::to_string(ib)));
+    if (lvl != 0) {
+      Act u = upsample(cur);
+      release(cur);
+      cur = conv3x3(u, "decoder.up." + std::to_string(lvl) + ".upsample.conv", nullptr, nullptr);
+      release(u);
+    }
+  }
+  Act o = group_norm(cur, "decoder.norm_out", 1e-6f, true, false);
+  release(cur);
+  if (live()) {
+    const Weight& wt = ws_->W("decoder.conv_out.weight");
+    const int H = o.H, W = o.W;
+    TapGemmGeneric g;
+    g.A = o.p; g.B = 1; g.T = 1; g.H = H; g.W = W; g.Cin = o.C;
+    g.a_sc = 1; g.a_sw = o.C; g.a_sh = (int64_t)W * o.C;
+    g.ntaps = 9; set_taps_3x3(g.taps);
+    g.Wt = wt.w; g.CinW = wt.Ipad; g.N = wt.O;
+    g.D = out; g.d_sw = 1; g.d_sh = W; g.d_sn = (int64_t)H * W;
+    g.bias = ws_->V("decoder.conv_out.bias").p;
+    tapgemm_generic(g, st_);
+    launches++;
+  }
+  release(o);
+}
+
+size_t Model::plan_vae(int h, int w) {
+  MUDG_REQUIRE(vae_ready_, "VAE weights not finalized");
+  arena_.planning = true;
+  planning_ = true;
+  arena_.reset_high();
+  vae_body(nullptr, h, w, nullptr);
+  const size_t need = arena_.high_water();
+  arena_.planning = false;
+  planning_ = false;
+  arena_.reset();
+  return need;
+}
+
+void Model::vae_decode(const void* z, int F, int h, int w, void* out, cudaStream_t st) {
+  MUDG_REQUIRE(vae_ready_, "VAE weights not finalized");
+  std::array<int, 2> key{h, w};
+  auto it = vae_plans_.find(key);
+  if (it == vae_plans_.end()) it = vae_plans_.emplace(key, plan_vae(h, w)).first;
+  ensure_arena(it->second);
+  st_ = st;
+  const MudgVaeConfig& v = vcfg_;
+  for (int f = 0; f < F; f++)   // perframe_ae loop (ddpm3d.py:659-664)
+    vae_body(static_cast<const float*>(z) + (size_t)f * v.z_channels * h * w, h, w,
+             static_cast<__half*>(out) + (size_t)f * v.out_ch * 64 * h * w);
+}
+
+}  // namespace mudg

@@ -1,0 +1,137 @@
+// Host-side graph walker: holds the packed weights and sequences the kernels of UNetModel.forward
+// (openaimodel3d.py:567-628) and Decoder.forward (ae_modules.py:539-578) on the caller's stream.
+#pragma once
+#include <array>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.h"
+#include "gemm.h"
+#include "mudg.h"
+#include "ops.h"
+
+namespace mudg {
+
+struct Weight {          // fp16 [O][taps][Ipad], K-major rows
+  __half* w = nullptr;
+  int O = 0, I = 0, Ipad = 0, taps = 1;
+  int K() const { return taps * Ipad; }
+};
+struct Vec {             // fp32 [n]
+  float* p = nullptr;
+  int n = 0;
+};
+
+struct Layer {
+  std::string kind;      // conv | res | spatial | temporal | down | up
+  std::string prefix;
+  int cin = 0, cout = 0, ch = 0, heads = 0, inner = 0;
+  bool linear_proj = true;
+  int res_index = -1;    // index into the per-forward emb_out table
+};
+struct Block {
+  std::vector<Layer> layers;
+};
+
+class WeightStore {
+ public:
+  ~WeightStore();
+  void load(const std::string& key, const void* dev_ptr, int dtype, const int64_t* shape, int ndim, cudaStream_t st);
+  const Weight& W(const std::string& key) const;
+  const Vec& V(const std::string& key) const;
+  bool hasW(const std::string& key) const { return w_.count(key) != 0; }
+  bool hasV(const std::string& key) const { return v_.count(key) != 0; }
+  // out = rows of keys stacked ([sum O][K]); sources are released
+  void stack_rows(const std::string& out_key, const std::vector<std::string>& keys, cudaStream_t st);
+  void make_geglu(const std::string& proj_prefix, cudaStream_t st);   // "<p>.weight"/".bias" -> "<p>.geglu.weight"/".bias"
+  void drop(const std::string& key);
+  size_t bytes() const { return bytes_; }
+
+ private:
+  std::unordered_map<std::string, Weight> w_;
+  std::unordered_map<std::string, Vec> v_;
+  size_t bytes_ = 0;
+};
+
+struct KvCache {          // per SpatialTransformer: [N][77][2C] and [Nimg_batches][Limg][2C]
+  __half* text = nullptr;
+  __half* img = nullptr;
+  size_t text_bytes = 0, img_bytes = 0;
+};
+
+class Model {
+ public:
+  Model(int device, const MudgUNetConfig& u, const MudgVaeConfig& v);
+  ~Model();
+
+  WeightStore unet_w, vae_w;
+  void finalize(int which, cudaStream_t st);
+  void set_context(const void* ctx, int dtype, int N, int L, int T, cudaStream_t st);
+  void unet_forward(const void* x, const int64_t* t, const int64_t* label, const int64_t* fs, int N, int T, int h, int w,
+                    void* out, cudaStream_t st);
+  void vae_decode(const void* z, int F, int h, int w, void* out, cudaStream_t st);
+  size_t plan_unet(int N, int T, int h, int w);
+  size_t plan_vae(int h, int w);
+  int64_t launches = 0;
+
+ private:
+  // ---- graph
+  void build_plan();
+  MudgUNetConfig ucfg_;
+  MudgVaeConfig vcfg_;
+  int device_;
+  std::vector<Block> in_blocks_, out_blocks_;
+  Block mid_;
+  int n_res_ = 0;
+  bool unet_ready_ = false, vae_ready_ = false;
+
+  // ---- per-call state
+  Arena arena_;
+  cudaStream_t st_ = nullptr;
+  bool planning_ = false;
+  const WeightStore* ws_ = nullptr;
+  int ctx_N_ = 0, ctx_L_ = 0, ctx_T_ = 0, ctx_Limg_ = 0;
+  bool ctx_per_frame_ = false;
+  std::unordered_map<std::string, KvCache> kv_;
+  std::vector<float*> emb_out_;   // per ResBlock [N][Cout]
+  int T_real_ = 1;                // frames per sample of the current forward
+  int N_ = 1;
+  std::map<std::array<int, 4>, size_t> unet_plans_;
+  std::map<std::array<int, 2>, size_t> vae_plans_;
+
+  void ensure_arena(size_t bytes);
+  Act alloc(int B, int T, int H, int W, int C);
+  void release(Act& a);
+  void* alloc_bytes(size_t n);
+  void release_bytes(void* p);
+  bool live() const { return !planning_; }
+
+  // ---- ops (all no-ops apart from allocation when planning)
+  Act group_norm(const Act& x, const std::string& p, float eps, bool silu, bool over_time);
+  Act layer_norm(const Act& x, const std::string& p);
+  Act linear(const Act& x, const std::string& wkey, const std::string& bkey, const Act* residual, bool geglu = false,
+             float alpha = 1.f);
+  Act conv3x3(const Act& x, const std::string& p, const Act* residual, const float* bias2);
+  Act conv_t3(const Act& x, const std::string& p, const Act* residual);
+  Act gemm_raw(const __half* A, int M, int K, const __half* Wt, int N, const float* bias, const Act* residual, float alpha);
+  Act concat(const Act& a, const Act& b);
+  Act upsample(const Act& x);
+  Act downsample(const Act& x, const std::string& p);
+
+  Act res_block(const Act& x, const Layer& l);
+  Act transformer_block_tail(Act x, const std::string& p);   // LN3 + GEGLU FF + residual (consumes x)
+  Act spatial_transformer(const Act& x, const Layer& l);
+  Act temporal_transformer(const Act& x, const Layer& l);
+  Act run_block(Act h, const Block& b, bool owns_input);
+  void compute_embeddings(const int64_t* t, const int64_t* label, const int64_t* fs, int N);
+  void unet_body(const void* x, const int64_t* t, const int64_t* label, const int64_t* fs, int N, int T, int h, int w,
+                 void* out);
+  Act vae_res(const Act& x, const std::string& p);
+  Act vae_attn(const Act& x, const std::string& p);
+  void vae_body(const void* z, int h, int w, void* out);
+};
+
+}  // namespace mudg

@@ -1,0 +1,132 @@
+"""Standalone GPU probe for attention / norm kernels (one case per process).  usage: python tests/gpu_probe_ops.py <case>|all"""
+import ctypes
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+CASES = ["flash_self_small", "flash_self_l1", "flash_self_ragged", "flash_cross", "flash_cross_else", "tattn16", "tattn4",
+         "tattn64", "gn_frame", "gn_time", "ln320", "ln1280", "ln512"]
+
+
+def ref_attn(q, k, v, heads, scale):
+    import torch
+    F, Nq, C = q.shape
+    d = C // heads
+    qh = q.float().reshape(F, Nq, heads, d).permute(0, 2, 1, 3)
+    kh = k.float().reshape(F, -1, heads, d).permute(0, 2, 1, 3)
+    vh = v.float().reshape(F, -1, heads, d).permute(0, 2, 1, 3)
+    s = torch.matmul(qh, kh.transpose(-1, -2)) * scale
+    o = torch.matmul(s.softmax(-1), vh)
+    return o.permute(0, 2, 1, 3).reshape(F, Nq, C)
+
+
+def report(name, label, out, ref):
+    import torch
+    err = (out.float() - ref).abs()
+    nan = int(torch.isnan(out.float()).sum())
+    mx = float(err[~torch.isnan(err)].max()) if nan < err.numel() else float("nan")
+    print(f"{name:18s} {label:5s} max|d|={mx:.5f} nans={nan} ref_absmax={float(ref.abs().max()):.3f}", flush=True)
+    if mx > 0.02 or nan:
+        bad = (err > 0.02) | torch.isnan(out.float())
+        print("   n_bad", int(bad.sum()), "of", err.numel(), "first", bad.nonzero()[:4].tolist(), flush=True)
+
+
+def run_case(name):
+    import torch
+    import torch.nn.functional as Fn
+    from mudg_b200._lib import lib, check, ptr, cur_stream
+    torch.manual_seed(0)
+    dev = "cuda"
+    L = lib()
+    f32 = ctypes.c_float
+    if name.startswith("flash_self"):
+        F, Nq, heads = {"flash_self_small": (2, 256, 1), "flash_self_l1": (3, 2304, 10), "flash_self_ragged": (2, 200, 2)}[name]
+        C = heads * 64
+        qkv = torch.randn(F, Nq, 3 * C, device=dev).half()
+        ref = ref_attn(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], heads, 0.125)
+        for backend, label in ((1, "simt"), (0, "tc")):
+            O = torch.full((F, Nq, C), float("nan"), device=dev).half()
+            flat = qkv.reshape(-1)
+            check(L.mudg_test_flash(ptr(qkv), 3 * C, ptr(O), C, F, Nq, heads,
+                                    ctypes.c_void_p(qkv.data_ptr() + 2 * C), ctypes.c_void_p(qkv.data_ptr() + 4 * C), 3 * C, Nq, F, 1,
+                                    None, None, 0, 0, 0, 1, f32(0.125), backend, cur_stream()))
+            torch.cuda.synchronize()
+            report(name, label, O, ref)
+    elif name.startswith("flash_cross"):
+        N, T, HW, heads = 2, 4, 320, 5
+        C = heads * 64
+        F = N * T
+        q = torch.randn(F, HW, C, device=dev).half()
+        kv_t = torch.randn(N, 77, 2 * C, device=dev).half()
+        if name == "flash_cross":
+            kv_i = torch.randn(N * T, 16, 2 * C, device=dev).half()
+            len1, nb1, div1 = 16, N * T, 1
+            ki = kv_i[..., :C]; vi = kv_i[..., C:]
+        else:
+            kv_i = torch.randn(N, 24, 2 * C, device=dev).half()
+            len1, nb1, div1 = 24, N, T
+            ki = kv_i[..., :C].repeat_interleave(T, 0); vi = kv_i[..., C:].repeat_interleave(T, 0)
+        kt = kv_t[..., :C].repeat_interleave(T, 0); vt = kv_t[..., C:].repeat_interleave(T, 0)
+        ref = ref_attn(q, kt, vt, heads, 0.125) + ref_attn(q, ki, vi, heads, 0.125)
+        for backend, label in ((1, "simt"), (0, "tc")):
+            O = torch.full((F, HW, C), float("nan"), device=dev).half()
+            check(L.mudg_test_flash(ptr(q), C, ptr(O), C, F, HW, heads,
+                                    ptr(kv_t), ctypes.c_void_p(kv_t.data_ptr() + 2 * C), 2 * C, 77, N, T,
+                                    ptr(kv_i), ctypes.c_void_p(kv_i.data_ptr() + 2 * C), 2 * C, len1, nb1, div1,
+                                    f32(0.125), backend, cur_stream()))
+            torch.cuda.synchronize()
+            report(name, label, O, ref)
+    elif name.startswith("tattn"):
+        T = int(name[5:])
+        B, HW, heads = 2, 37, 5
+        C = heads * 64
+        qkv = torch.randn(B, T, HW, 3 * C, device=dev).half()
+        # reference: sequences over T per (b, pixel)
+        x = qkv.permute(0, 2, 1, 3).reshape(B * HW, T, 3 * C)
+        ref = ref_attn(x[..., :C], x[..., C:2 * C], x[..., 2 * C:], heads, 0.125)
+        ref = ref.reshape(B, HW, T, C).permute(0, 2, 1, 3)
+        O = torch.full((B, T, HW, C), float("nan"), device=dev).half()
+        check(L.mudg_test_temporal_attn(ptr(qkv), ptr(O), B, T, HW, heads, f32(0.125), cur_stream()))
+        torch.cuda.synchronize()
+        report(name, "cuda", O, ref)
+    elif name.startswith("gn_"):
+        over_time = name == "gn_time"
+        B, T, H, W, C = 2, 4, 9, 16, 320
+        x = (torch.randn(B, T, H, W, C, device=dev) * 2 + 0.5).half()
+        g = torch.randn(C, device=dev); b = torch.randn(C, device=dev)
+        if over_time:
+            xr = x.float().permute(0, 4, 1, 2, 3)
+            ref = Fn.silu(Fn.group_norm(xr, 32, g, b, 1e-5)).permute(0, 2, 3, 4, 1)
+            S, rps = B, T * H * W
+        else:
+            xr = x.float().reshape(B * T, H, W, C).permute(0, 3, 1, 2)
+            ref = Fn.silu(Fn.group_norm(xr, 32, g, b, 1e-5)).permute(0, 2, 3, 1).reshape(B, T, H, W, C)
+            S, rps = B * T, H * W
+        y = torch.full_like(x, float("nan"))
+        check(L.mudg_test_groupnorm(ptr(x), ptr(y), S, ctypes.c_int64(rps), C, ptr(g), ptr(b), f32(1e-5), 1, cur_stream()))
+        torch.cuda.synchronize()
+        report(name, "cuda", y, ref)
+    elif name.startswith("ln"):
+        C = int(name[2:])
+        rows = 1000
+        x = (torch.randn(rows, C, device=dev) * 3 + 1).half()
+        g = torch.randn(C, device=dev); b = torch.randn(C, device=dev)
+        ref = Fn.layer_norm(x.float(), (C,), g, b, 1e-5)
+        y = torch.full_like(x, float("nan"))
+        check(L.mudg_test_layernorm(ptr(x), ptr(y), ptr(g), ptr(b), ctypes.c_int64(rows), C, cur_stream()))
+        torch.cuda.synchronize()
+        report(name, "cuda", y, ref)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which == "all":
+        for name in CASES:
+            r = subprocess.run([sys.executable, __file__, name], timeout=300)
+            if r.returncode != 0:
+                print(f"{name}: FAILED rc={r.returncode}", flush=True)
+    else:
+        run_case(which)
