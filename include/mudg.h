@@ -87,6 +87,11 @@ MUDG_EXPORT size_t mudg_workspace_bytes(MudgCtx* ctx, int N, int T, int h, int w
 /* Kernels launched by this context since creation (bench.py's gpu_launches). */
 MUDG_EXPORT int64_t mudg_launch_count(MudgCtx* ctx);
 
+/* Per-launch CUDA-event timing of the tcgen05 GEMM kernel on its launching stream (bench.py roofline leg):
+ * enable, run, then read {sum of launch durations in ms, sum of algorithmic FLOPs, launches}; read() synchronises. */
+MUDG_EXPORT int mudg_profile_gemm(int enable);
+MUDG_EXPORT int mudg_profile_gemm_read(double* ms_total, double* flops_total, int64_t* launches);
+
 /* ---- single-kernel test hooks (tests/ only) ---- */
 MUDG_EXPORT int mudg_test_tapgemm(const void* A, int B, int T, int H, int W, int Cin, int mode, const void* Wt, int N,
                                   void* D, const void* R, const float* bias, const float* bias2, int bias2_div, int nb2,

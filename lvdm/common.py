@@ -1,0 +1,26 @@
+"""Helpers with the reference's semantics (lvdm/common.py:25-44)."""
+from inspect import isfunction
+
+import torch
+
+
+def exists(v):
+    return v is not None
+
+
+def default(v, d):
+    if v is not None:
+        return v
+    return d() if isfunction(d) else d
+
+
+def extract_into_tensor(a, t, x_shape):
+    """a[t] broadcast to x_shape's rank: [b] -> [b,1,1,...] (common.py:25-28)."""
+    return a.gather(-1, t).reshape(t.shape[0], *((1,) * (len(x_shape) - 1)))
+
+
+def noise_like(shape, device, repeat=False):
+    """Fresh Gaussian noise on `device` from the global generator (common.py:31-34)."""
+    if repeat:
+        return torch.randn((1, *shape[1:]), device=device).repeat(shape[0], *((1,) * (len(shape) - 1)))
+    return torch.randn(shape, device=device)

@@ -1,0 +1,109 @@
+"""B200-native `UNetModel`: same constructor keys, attributes and state-dict layout as the reference's
+lvdm/modules/networks/openaimodel3d.py:281-628, but the forward is ONE call into libmudg_sm100.so
+(hand-written sm_100a kernels); the nn.Module only holds the checkpoint-compatible parameters.
+
+There is deliberately no PyTorch implementation of the forward here: on a machine without the CUDA
+extension / a Blackwell GPU the model raises instead of silently running something else.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from mudg_b200._lib import MudgError
+from mudg_b200.layout import unet_layout, unet_zero_init_keys
+from mudg_b200.paramtree import build_param_tree, mark_dirty_on_load
+
+
+class UNetModel(nn.Module):
+    def __init__(self, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions, dropout=0.0,
+                 channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, context_dim=None, use_scale_shift_norm=False,
+                 resblock_updown=False, num_heads=-1, num_head_channels=-1, transformer_depth=1, use_linear=False,
+                 use_checkpoint=False, temporal_conv=False, tempspatial_aware=False, temporal_attention=True,
+                 use_relative_position=True, use_causal_attention=False, temporal_length=None, use_fp16=False,
+                 addition_attention=False, temporal_selfatt_only=True, image_cross_attention=False,
+                 image_cross_attention_scale_learnable=False, default_fs=4, fs_condition=False,
+                 class_label_condition=False, domain_cross_attention=False, num_tasks=1, temporal_frozen=False):
+        super().__init__()
+        # The kernels implement the graph the shipped *_infer.yaml configs build; anything else
+        # is rejected up front rather than computed differently.
+        unsupported = {
+            "dims != 2": dims != 2, "use_scale_shift_norm": use_scale_shift_norm, "resblock_updown": resblock_updown,
+            "num_head_channels != 64": num_head_channels != 64, "transformer_depth != 1": transformer_depth != 1,
+            "use_linear=False": not use_linear, "temporal_conv=False": not temporal_conv,
+            "tempspatial_aware": tempspatial_aware, "temporal_attention=False": not temporal_attention,
+            "use_relative_position": use_relative_position, "use_causal_attention": use_causal_attention,
+            "addition_attention=False": not addition_attention, "image_cross_attention=False": not image_cross_attention,
+            "image_cross_attention_scale_learnable": image_cross_attention_scale_learnable,
+            "fs_condition=False": not fs_condition, "class_label_condition=False": not class_label_condition,
+            "domain_cross_attention": domain_cross_attention, "conv_resample=False": not conv_resample,
+            "context_dim is None": context_dim is None,
+        }
+        bad = [k for k, v in unsupported.items() if v]
+        if bad:
+            raise NotImplementedError("mudg_b200 UNetModel supports the MuDG inference graph only; unsupported: " + ", ".join(bad))
+        self.in_channels, self.model_channels, self.out_channels = in_channels, model_channels, out_channels
+        self.num_res_blocks = num_res_blocks
+        self.attention_resolutions = list(attention_resolutions)
+        self.channel_mult = list(channel_mult)
+        self.dropout, self.conv_resample, self.temporal_attention = dropout, conv_resample, temporal_attention
+        self.use_checkpoint = use_checkpoint
+        self.dtype = torch.float16 if use_fp16 else torch.float32
+        self.addition_attention, self.temporal_length = addition_attention, temporal_length
+        self.image_cross_attention = image_cross_attention
+        self.image_cross_attention_scale_learnable = image_cross_attention_scale_learnable
+        self.default_fs, self.fs_condition, self.class_label_condition = default_fs, fs_condition, class_label_condition
+        self.domain_cross_attention, self.num_tasks = domain_cross_attention, num_tasks
+        self.context_dim = context_dim
+        self._cfg = dict(in_channels=in_channels, out_channels=out_channels, model_channels=model_channels,
+                         num_res_blocks=num_res_blocks, attention_resolutions=self.attention_resolutions,
+                         channel_mult=self.channel_mult, num_head_channels=num_head_channels, context_dim=context_dim)
+        layout = unet_layout(**self._cfg)
+        build_param_tree(self, layout, zero_keys=unet_zero_init_keys(layout))
+        self._engine = None
+        self._ctx_key = None
+        mark_dirty_on_load(self)
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _apply(self, fn, *a, **k):            # .cuda()/.to()/.half() move the parameters: re-pack lazily
+        self._engine_dirty = True
+        return super()._apply(fn, *a, **k)
+
+    def engine(self):
+        p = next(self.parameters())
+        if not p.is_cuda:
+            raise MudgError("UNetModel runs only on a CUDA (B200) device: call .cuda() first; no CPU fallback exists")
+        if self._engine is None:
+            from mudg_b200.engine import Engine
+            self._engine = Engine(self._cfg, None, device=p.device.index)
+        if self._engine_dirty:
+            from mudg_b200.engine import MUDG_UNET
+            self._engine.load_state_dict(self.state_dict(), MUDG_UNET)
+            self._engine_dirty = False
+            self._ctx_key = None
+        return self._engine
+
+    def set_context(self, context, T):
+        """Cross-attention K/V are constant over the DDIM steps: recompute only when the tensor changes."""
+        key = (context.data_ptr(), context._version, tuple(context.shape), context.dtype, int(T))
+        eng = self.engine()
+        if key != self._ctx_key:
+            eng.set_context(context, T)
+            self._ctx_key = key
+            self._ctx_ref = context          # keep the storage alive so data_ptr stays unique
+        return eng
+
+    # ------------------------------------------------------------------ reference signature (openaimodel3d.py:567)
+    @torch.no_grad()
+    def forward(self, x, timesteps, c_label=None, context=None, features_adapter=None, fs=None, **kwargs):
+        if features_adapter is not None:
+            raise NotImplementedError("features_adapter is not part of the MuDG sampler path")
+        if c_label is None:
+            raise AssertionError("class_label is required for class_label_condition")
+        b, _, t, _, _ = x.shape
+        if fs is None:
+            fs = torch.full((b,), self.default_fs, dtype=torch.long, device=x.device)
+        eng = self.set_context(context, t)
+        y = eng.unet_forward(x, timesteps, c_label, fs)
+        # the reference returns fp16 under autocast (last conv) and the input dtype otherwise
+        return y if (torch.is_autocast_enabled() or x.dtype == torch.float16) else y.to(x.dtype)

@@ -241,6 +241,289 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
+// ================================================================ flash attention v2 (FA4-style schedule)
+// One CTA per SM, 256 queries (two 128-row tiles) of one (frame, head):
+//   warp 0      TMA producer: Q0,Q1 once; K/V 128-token blocks through a 3-stage ring (shared by both tiles)
+//   warp 1      tcgen05 issuer: per kv block S_i = Q_i K^T (N128 K64) and O_i += P_i V (N64 K128, V MN-major)
+//               plus l_i += P_i 1 (N16: the row sums come from the tensor core, consistent with the fp16 P)
+//   warps 2-5   softmax group 0 (tile 0);  warps 6-9 softmax group 1 (tile 1): thread == row == TMEM lane.
+//               While group 0 works on S_0 the tensor core runs the other tile's GEMMs (ping-pong).
+//   O and l stay in TMEM across kv blocks; the running max is only raised when it grows by > 2^8 (lazy
+//   rescale: P <= 256 fits fp16), in which case the warp rescales its O/l rows in place (tcgen05.ld/st).
+//   exp2 is evaluated two-at-a-time (ex2.approx.ftz.f16x2) directly into the fp16 P operand.
+constexpr int F2_THREADS = 320;
+constexpr int F2_KV_STAGES = 3;
+constexpr int F2_SMEM = 2 * TILE /*Q0,Q1*/ + F2_KV_STAGES * 2 * TILE + 2 * 2 * TILE /*P0,P1*/ + 4096 /*ones*/ + 1024 + 256;
+constexpr float F2_LAZY = 8.0f;
+
+template <int NSEG>
+__global__ void __launch_bounds__(F2_THREADS, 1)
+flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmO,
+              const __grid_constant__ CUtensorMap tmK0, const __grid_constant__ CUtensorMap tmV0,
+              const __grid_constant__ CUtensorMap tmK1, const __grid_constant__ CUtensorMap tmV1, const FaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                  // 2 tiles
+  uint8_t* sKV = smem + 2 * TILE;                      // stage s: K at + s*2*TILE, V at + TILE
+  uint8_t* sP = sKV + F2_KV_STAGES * 2 * TILE;         // tile i: 2 atoms (32 KB) at + i*2*TILE
+  uint8_t* sOnes = sP + 4 * TILE;                      // 4 KB of fp16 1.0
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + 4096);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;                        // [3]
+  uint64_t* kv_empty = bars + 4;                       // [3]
+  uint64_t* s_full = bars + 7;                         // [2]
+  uint64_t* p_ready = bars + 9;                        // [2]
+  uint64_t* o_done = bars + 11;                        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256, head = blockIdx.y, f = blockIdx.z;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < F2_KV_STAGES; i++) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); mbar_init(&o_done[i], 1); }
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < 4096 / 4; i += F2_THREADS) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3C003C00u;
+  fence_proxy_async_smem();
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: S0 [0,128) S1 [128,256) | O0 [256,320) l0 [320,336) | O1 [384,448) l1 [448,464)
+
+  int nblk[2];
+  nblk[0] = (p.len[0] + 127) >> 7;
+  nblk[1] = NSEG > 1 ? (p.len[1] + 127) >> 7 : 0;
+  const int nb = nblk[0] + nblk[1];
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2 * TILE);
+      tma_load_5d(sQ, &tmQ, q_full, head * 64, q0, f, 0, 0);
+      tma_load_5d(sQ + TILE, &tmQ, q_full, head * 64, q0 + 128, f, 0, 0);
+      int it = 0;
+      for (int sg = 0; sg < NSEG; sg++) {
+        const CUtensorMap* mk = sg ? &tmK1 : &tmK0;
+        const CUtensorMap* mv = sg ? &tmV1 : &tmV0;
+        const int kb = f / p.kv_div[sg];
+        for (int j = 0; j < nblk[sg]; j++, it++) {
+          const int s = it % F2_KV_STAGES;
+          mbar_wait(&kv_empty[s], ((it / F2_KV_STAGES) & 1) ^ 1);
+          mbar_expect_tx(&kv_full[s], 2 * TILE);
+          uint8_t* k_s = sKV + s * 2 * TILE;
+          tma_load_5d(k_s, mk, &kv_full[s], head * 64, j * 128, kb, 0, 0);
+          tma_load_5d(k_s + TILE, mv, &kv_full[s], head * 64, j * 128, kb, 0, 0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(128, 128, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_f16(128, 64, 0, 1);     // V MN-major
+      constexpr uint32_t idesc_l = umma_idesc_f16(128, 16, 0, 0);     // ones, K-major
+      const uint64_t d_ones = umma_desc_sw128(smem_u32(sOnes), 16, 1024);
+      mbar_wait(q_full, 0);
+      auto issue_s = [&](int i, int it) {
+        const int s = it % F2_KV_STAGES;
+        const uint64_t dq = umma_desc_sw128(smem_u32(sQ + i * TILE), 16, 1024);
+        const uint64_t dk = umma_desc_sw128(smem_u32(sKV + s * 2 * TILE), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; k++) umma_f16(tmem_base + i * 128, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[i]);
+      };
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      issue_s(1, 0);
+      int seg_first = 0;   // global index of the first block of the current segment
+      for (int it = 0; it < nb; it++) {
+        if (NSEG > 1 && it == nblk[0]) seg_first = nblk[0];
+        const int s = it % F2_KV_STAGES;
+        const bool next = it + 1 < nb;
+        if (next) {
+          mbar_wait(&kv_full[(it + 1) % F2_KV_STAGES], ((it + 1) / F2_KV_STAGES) & 1);
+          tc_fence_after();
+        }
+        const uint64_t dv = umma_desc_sw128(smem_u32(sKV + s * 2 * TILE + TILE), 1024, 1024);
+        for (int i = 0; i < 2; i++) {
+          mbar_wait(&p_ready[i], it & 1);
+          tc_fence_after();
+          const uint64_t dp = umma_desc_sw128(smem_u32(sP + i * 2 * TILE), 16, 1024);
+          const uint32_t tO = tmem_base + 256 + i * 128;
+          const uint32_t acc0 = it != seg_first ? 1u : 0u;
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            const uint64_t dpk = dp + (uint64_t)((k >> 2) * (TILE >> 4) + (k & 3) * 2);
+            umma_f16(tO, dpk, dv + (uint64_t)(k * (2048 >> 4)), idesc_o, (k != 0) ? 1u : acc0);
+            umma_f16(tO + 64, dpk, d_ones, idesc_l, (k != 0) ? 1u : acc0);
+          }
+          umma_commit(&o_done[i]);
+          if (next) issue_s(i, it + 1);
+        }
+        umma_commit(&kv_empty[s]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int grp = (warp - 2) >> 2;                 // query tile handled by this softmax group
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t tS = tmem_base + grp * 128 + lane_off;
+    const uint32_t tO = tmem_base + 256 + grp * 128 + lane_off;
+    uint8_t* myP = sP + grp * 2 * TILE;
+    uint32_t acc[NSEG > 1 ? 32 : 1];
+    if (NSEG > 1) {
+#pragma unroll
+      for (int i = 0; i < 32; i++) acc[i] = 0u;
+    }
+    float o_final[64];
+    int it = 0;
+#pragma unroll 1
+    for (int sg = 0; sg < NSEG; sg++) {
+      float m_used = -INFINITY;
+#pragma unroll 1
+      for (int j = 0; j < nblk[sg]; j++, it++) {
+        const int valid = p.len[sg] - j * 128;
+        mbar_wait(&s_full[grp], it & 1);
+        __syncwarp();
+        tc_fence_after();
+        // ---- pass 1: row max (scaled to the log2 domain)
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 4; c++) {
+          uint32_t v[32];
+          tmem_ld32(tS + c * 32, v);
+          tmem_ld_wait();
+          if (valid >= 128) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i++)
+              if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+          }
+        }
+        mx *= p.scale_log2;
+        // the previous P V of this tile must have retired before P (and possibly O) are overwritten
+        if (j > 0) {
+          mbar_wait(&o_done[grp], (it - 1) & 1);
+          __syncwarp();
+          tc_fence_after();
+        }
+        if (j == 0) {
+          m_used = mx;
+        } else {
+          const bool grow = mx > m_used + F2_LAZY;
+          if (__any_sync(0xffffffffu, grow)) {       // warp-uniform: tcgen05.ld/st are warp-collective
+            const float m_new = grow ? mx : m_used;
+            const float factor = exp2f(m_used - m_new);
+#pragma unroll 1
+            for (int c = 0; c < 3; c++) {            // 64 O columns + the l columns
+              uint32_t v[32];
+              tmem_ld32(tO + c * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; i++) v[i] = __float_as_uint(__uint_as_float(v[i]) * factor);
+              tmem_st32(tO + c * 32, v);
+            }
+            tmem_st_wait();
+            m_used = m_new;
+          }
+        }
+        // ---- pass 2: P = 2^(s*scale - m_used) as fp16, into the swizzled K-major smem operand
+#pragma unroll 1
+        for (int c = 0; c < 4; c++) {
+          uint32_t v[32];
+          tmem_ld32(tS + c * 32, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+          if (valid >= 128) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2)
+              pk[i >> 1] = ex2_f16x2(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_used),
+                                     fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_used));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float a = (c * 32 + i < valid) ? fmaf(__uint_as_float(v[i]), p.scale_log2, -m_used) : -INFINITY;
+              const float b = (c * 32 + i + 1 < valid) ? fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_used) : -INFINITY;
+              pk[i >> 1] = ex2_f16x2(a, b);
+            }
+          }
+          uint8_t* atom = myP + (c >> 1) * TILE + row * 128;
+#pragma unroll
+          for (int jj = 0; jj < 4; jj++) {
+            const int chunk = (c & 1) * 4 + jj;
+            *reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) =
+                make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&p_ready[grp]);
+      }
+      // ---- segment done: O / l
+      mbar_wait(&o_done[grp], (it - 1) & 1);
+      __syncwarp();
+      tc_fence_after();
+      float inv;
+      {
+        uint32_t v[32];
+        tmem_ld32(tO + 64, v);
+        tmem_ld_wait();
+        inv = 1.f / __uint_as_float(v[0]);
+      }
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        uint32_t v[32];
+        tmem_ld32(tO + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i++) o_final[c * 32 + i] = __uint_as_float(v[i]) * inv;
+      }
+      if (NSEG > 1) {
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          const float2 a = unpack_half2(acc[i]);
+          acc[i] = pack_half2(a.x + o_final[2 * i], a.y + o_final[2 * i + 1]);
+        }
+      }
+      tc_fence_before();
+    }
+    // ---- epilogue: this group's P buffer is free (its last P V has retired)
+    uint8_t* stg = myP + row * 128;
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) {
+      uint4 val;
+      if (NSEG > 1) val = make_uint4(acc[4 * jj], acc[4 * jj + 1], acc[4 * jj + 2], acc[4 * jj + 3]);
+      else val = make_uint4(pack_half2(o_final[8 * jj], o_final[8 * jj + 1]), pack_half2(o_final[8 * jj + 2], o_final[8 * jj + 3]),
+                            pack_half2(o_final[8 * jj + 4], o_final[8 * jj + 5]), pack_half2(o_final[8 * jj + 6], o_final[8 * jj + 7]));
+      *reinterpret_cast<uint4*>(stg + ((jj ^ (row & 7)) << 4)) = val;
+    }
+    fence_proxy_async_smem();
+    if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+    else asm volatile("bar.sync 2, 128;" ::: "memory");
+    if (q == 2 && lane == 0) {       // warps 2 and 6 (first warp of each group)
+      tma_store_5d(&tmO, myP, head * 64, q0 + grp * 128, f, 0, 0);
+      tma_store_commit();
+      tma_store_wait_read0();
+    }
+    __syncwarp();
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // ---------------------------------------------------------------- SIMT checker: thread per (frame, head, query)
 __global__ void flash_simt_kernel(FlashArgs a) {
   const int64_t total = (int64_t)a.F * a.heads * a.Nq;
@@ -413,15 +696,27 @@ void flash_attention(const FlashArgs& a, cudaStream_t st) {
     p.len[i] = s.len;
     p.kv_div[i] = s.kv_div > 0 ? s.kv_div : 1;
   }
+  static const bool use_v1 = [] {
+    const char* e = getenv("MUDG_FLASH_V1");
+    return e && e[0] == '1';
+  }();
   static bool attr = false;
   if (!attr) {
     MUDG_CUDA(cudaFuncSetAttribute(flash_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
     MUDG_CUDA(cudaFuncSetAttribute(flash_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
+    MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
     attr = true;
   }
-  dim3 grid((a.Nq + 127) / 128, a.heads, a.F);
-  if (a.nseg == 1) flash_tc_kernel<1><<<grid, FA_THREADS, FA_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
-  else flash_tc_kernel<2><<<grid, FA_THREADS, FA_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
+  if (use_v1) {
+    dim3 grid((a.Nq + 127) / 128, a.heads, a.F);
+    if (a.nseg == 1) flash_tc_kernel<1><<<grid, FA_THREADS, FA_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
+    else flash_tc_kernel<2><<<grid, FA_THREADS, FA_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
+  } else {
+    dim3 grid((a.Nq + 255) / 256, a.heads, a.F);
+    if (a.nseg == 1) flash2_kernel<1><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
+    else flash2_kernel<2><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
+  }
   MUDG_CUDA(cudaGetLastError());
 }
 

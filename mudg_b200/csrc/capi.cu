@@ -119,6 +119,18 @@ MUDG_EXPORT size_t mudg_workspace_bytes(MudgCtx* ctx, int N, int T, int h, int w
 
 MUDG_EXPORT int64_t mudg_launch_count(MudgCtx* ctx) { return ctx ? ctx->model.launches : 0; }
 
+MUDG_EXPORT int mudg_profile_gemm(int enable) {
+  MUDG_API_BEGIN
+  gemm_profile_enable(enable != 0);
+  MUDG_API_END
+}
+
+MUDG_EXPORT int mudg_profile_gemm_read(double* ms_total, double* flops_total, int64_t* launches) {
+  MUDG_API_BEGIN
+  gemm_profile_read(ms_total, flops_total, launches);
+  MUDG_API_END
+}
+
 // ------------------------------------------------------------------ test hooks
 MUDG_EXPORT int mudg_test_tapgemm(const void* A, int B, int T, int H, int W, int Cin, int mode, const void* Wt, int N,
                                   void* D, const void* R, const float* bias, const float* bias2, int bias2_div, int nb2,

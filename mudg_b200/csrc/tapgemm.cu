@@ -12,6 +12,7 @@
 #include "ptx.cuh"
 
 #include <cstdlib>
+#include <vector>
 
 namespace mudg {
 
@@ -435,13 +436,64 @@ void tapgemm_generic(const TapGemmGeneric& g, cudaStream_t st) {
   MUDG_CUDA(cudaGetLastError());
 }
 
+// ---- optional per-launch timing of the tcgen05 GEMM (bench.py's roofline leg): CUDA events on the launching stream
+namespace {
+struct GemmProfiler {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;      // pairs
+  std::vector<double> flops;
+  size_t used = 0;
+} g_prof;
+}  // namespace
+
+void gemm_profile_enable(bool on) {
+  g_prof.on = on;
+  g_prof.used = 0;
+  g_prof.flops.clear();
+}
+
+void gemm_profile_read(double* ms_total, double* flops_total, int64_t* launches) {
+  MUDG_CUDA(cudaDeviceSynchronize());
+  double ms = 0, fl = 0;
+  for (size_t i = 0; i < g_prof.used; i++) {
+    float t = 0.f;
+    MUDG_CUDA(cudaEventElapsedTime(&t, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]));
+    ms += t;
+    fl += g_prof.flops[i];
+  }
+  *ms_total = ms;
+  *flops_total = fl;
+  *launches = (int64_t)g_prof.used;
+  g_prof.used = 0;
+  g_prof.flops.clear();
+}
+
 void tapgemm(const TapGemm& g, cudaStream_t st) {
   static const bool force_simt = [] {
     const char* e = getenv("MUDG_FORCE_SIMT");
     return e && e[0] == '1';
   }();
-  if (!force_simt && tapgemm_tc_eligible(g)) tapgemm_tc(g, st);
-  else tapgemm_simt(g, st);
+  if (!force_simt && tapgemm_tc_eligible(g)) {
+    if (g_prof.on) {
+      if (g_prof.ev.size() < 2 * (g_prof.used + 1)) {
+        cudaEvent_t a, b;
+        MUDG_CUDA(cudaEventCreate(&a));
+        MUDG_CUDA(cudaEventCreate(&b));
+        g_prof.ev.push_back(a);
+        g_prof.ev.push_back(b);
+      }
+      MUDG_CUDA(cudaEventRecord(g_prof.ev[2 * g_prof.used], st));
+      tapgemm_tc(g, st);
+      MUDG_CUDA(cudaEventRecord(g_prof.ev[2 * g_prof.used + 1], st));
+      // algorithmic work of the layer: 2 * rows * N * (taps * Cin), padding and tile overhang not counted
+      g_prof.flops.push_back(2.0 * (double)g.B * g.T * g.H * g.W * (double)g.N * (double)g.ntaps * g.Cin);
+      g_prof.used++;
+    } else {
+      tapgemm_tc(g, st);
+    }
+  } else {
+    tapgemm_simt(g, st);
+  }
 }
 
 }  // namespace mudg

@@ -23,11 +23,15 @@ def ref_attn(q, k, v, heads, scale):
     return o.permute(0, 2, 1, 3).reshape(F, Nq, C)
 
 
+RESULTS = {}
+
+
 def report(name, label, out, ref):
     import torch
     err = (out.float() - ref).abs()
     nan = int(torch.isnan(out.float()).sum())
     mx = float(err[~torch.isnan(err)].max()) if nan < err.numel() else float("nan")
+    RESULTS[(name, label)] = (mx, nan)
     print(f"{name:18s} {label:5s} max|d|={mx:.5f} nans={nan} ref_absmax={float(ref.abs().max()):.3f}", flush=True)
     if mx > 0.02 or nan:
         bad = (err > 0.02) | torch.isnan(out.float())

@@ -1,0 +1,117 @@
+"""CPU tests of the host side: drop-in class surface, state-dict layout, schedules, C-ABI symbol table,
+loud failure without a GPU.  No compute call is made into the CUDA library here."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from mudg_b200 import compat
+
+compat.install()
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def small_model_config():
+    from omegaconf import OmegaConf
+    cfg = OmegaConf.load(os.path.join(ROOT, "configs", "stage2-1024_mdm_waymo_infer_synthetic.yaml"))
+    p = cfg.model.params
+    p.unet_config.params.model_channels = 64
+    p.unet_config.params.temporal_length = 4
+    p.first_stage_config.params.ddconfig.ch = 64
+    p.image_size = [16, 16]
+    p.image_proj_stage_config.params.video_length = 4
+    return cfg.model
+
+
+def test_yaml_configs_cover_reference_keys():
+    from omegaconf import OmegaConf
+    for name, size, base in (("stage1-512_mdm_waymo_infer", [40, 64], 0.7), ("stage2-1024_mdm_waymo_infer", [72, 128], 0.3)):
+        cfg = OmegaConf.load(os.path.join(ROOT, "configs", name + ".yaml")).model
+        assert cfg.target == "lvdm.models.ddpm3d.LatentVisualDiffusion"
+        assert cfg.params.image_size == size and cfg.params.base_scale == base
+        assert cfg.params.unet_config.params.temporal_length == 16
+        assert cfg.params.cond_stage_config.target.endswith("FrozenOpenCLIPEmbedder")
+
+
+def test_instantiate_from_config_builds_reference_layout(golden_dir):
+    from utils.utils import instantiate_from_config
+    from oracle import mudg_oracle as O
+    model = instantiate_from_config(small_model_config())
+    assert type(model).__name__ == "LatentVisualDiffusion"
+    sd = model.state_dict()
+    want = O.unet_param_shapes(O.UNetCfg(model_channels=64, temporal_length=4))
+    got = {k[len("model.diffusion_model."):]: tuple(v.shape) for k, v in sd.items() if k.startswith("model.diffusion_model.")}
+    assert got == want
+    vae = {k[len("first_stage_model."):]: tuple(v.shape) for k, v in sd.items() if k.startswith("first_stage_model.")}
+    assert vae == O.vae_param_shapes(O.VaeCfg(ch=64))
+    with open(os.path.join(golden_dir, "meta.json")) as f:
+        meta = json.load(f)
+    buffers = sorted(k for k in sd if "." not in k)
+    assert buffers == sorted(meta["lvd_buffers"])          # same persistent buffers as the reference module
+    # attributes the driver / sampler read
+    assert model.model.conditioning_key == "hybrid" and model.model.diffusion_model.out_channels == 4
+    assert model.uncond_type == "empty_seq" and model.parameterization == "v" and model.use_dynamic_rescale
+    assert model.num_timesteps == 1000 and model.perframe_ae is True
+    tab = np.load(os.path.join(golden_dir, "tables.npz"))
+    assert np.array_equal(model.alphas_cumprod.numpy(), tab["alphas_cumprod"])
+    assert np.array_equal(model.scale_arr.numpy(), tab["scale_arr"])
+    assert np.array_equal(model.betas.numpy(), tab["betas"])
+    # strict load of a reference-layout state dict works
+    model.load_state_dict(sd, strict=True)
+
+
+def test_sampler_schedule_matches_reference(golden_dir):
+    from utils.utils import instantiate_from_config
+    from lvdm.models.samplers.ddim import DDIMSampler
+    model = instantiate_from_config(small_model_config())
+    s = DDIMSampler(model)
+    s.make_schedule(50, "uniform_trailing", 1.0, verbose=False)
+    d = np.load(os.path.join(golden_dir, "ddim_small.npz"))
+    assert np.array_equal(s.ddim_timesteps, d["timesteps50"])
+    assert np.array_equal(np.asarray(s.ddim_sigmas, dtype=np.float64), d["sigmas50"])
+    assert np.array_equal(np.asarray(s.ddim_alphas_prev, dtype=np.float64), d["alphas_prev50"])
+    assert s.ddim_scale_arr.shape == (50,)
+
+
+def test_product_path_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from utils.utils import instantiate_from_config
+    from mudg_b200._lib import MudgError
+    model = instantiate_from_config(small_model_config())
+    x = torch.zeros(1, 12, 4, 16, 16)
+    with pytest.raises(MudgError):
+        model.model.diffusion_model(x, torch.zeros(1, dtype=torch.long), c_label=torch.zeros(1, dtype=torch.long),
+                                    context=torch.zeros(1, 77 + 64, 1024))
+    with pytest.raises(MudgError):
+        model.decode_first_stage(torch.zeros(1, 4, 4, 16, 16))
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under mudg_b200/, lvdm/, utils/ may reference it."""
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|mudg_oracle", re.M)
+    for top in ("mudg_b200", "lvdm", "utils"):
+        for dp, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".h", ".cuh")):
+                    assert not pat.search(open(os.path.join(dp, f)).read()), os.path.join(dp, f)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from mudg_b200._lib import LIB_PATH
+    if not os.path.exists(LIB_PATH):
+        from mudg_b200.build import build
+        build()
+    header = open(os.path.join(ROOT, "include", "mudg.h")).read()
+    declared = set(re.findall(r"MUDG_EXPORT[^;(]*?\b(mudg_\w+)\s*\(", header))
+    assert {"mudg_create", "mudg_unet_forward", "mudg_vae_decode", "mudg_ddim_step", "mudg_set_context",
+            "mudg_load_weight", "mudg_finalize_weights", "mudg_destroy", "mudg_last_error"} <= declared
+    lib = ctypes.CDLL(LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.mudg_last_error.restype = ctypes.c_char_p
+    assert lib.mudg_last_error() is not None
