@@ -148,7 +148,8 @@ MUDG_EXPORT int mudg_test_tapgemm(const void* A, int B, int T, int H, int W, int
   g.R = static_cast<const __half*>(R);
   g.bias = bias; g.bias2 = bias2; g.bias2_div = bias2_div; g.nb2 = nb2;
   g.alpha = alpha; g.geglu = geglu != 0;
-  if (backend == 0) tapgemm_tc(g, S(stream));
+  if (backend == 0) tapgemm_tc2(g, S(stream));
+  else if (backend == 2) tapgemm_tc(g, S(stream));
   else tapgemm_simt(g, S(stream));
   MUDG_API_END
 }

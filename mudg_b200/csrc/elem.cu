@@ -343,6 +343,18 @@ __global__ void gather_rows_kernel(const TS* __restrict__ src, __half* __restric
   }
 }
 
+// y [B][R][Cp] channels-last fp16 -> out [B][C][R] fp16 (first C channels; NCTHW with R = T*H*W)
+__global__ void from_channels_last_kernel(const __half* __restrict__ y, __half* __restrict__ out, int B, int C, int64_t R,
+                                          int Cp) {
+  const int64_t total = (int64_t)B * C * R;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i % R;
+    const int c = (i / R) % C;
+    const int b = i / (R * C);
+    out[i] = y[((int64_t)b * R + r) * Cp + c];
+  }
+}
+
 inline int grid_for(int64_t work, int threads) {
   int64_t b = (work + threads - 1) / threads;
   return (int)std::max<int64_t>(1, std::min<int64_t>(b, (int64_t)sm_count() * 16));
@@ -476,6 +488,12 @@ void gather_rows_f16(const void* src, bool src_fp32, __half* dst, int B, int src
     gather_rows_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const float*>(src), dst, B, src_rows, r0, nrows, cols);
   else
     gather_rows_kernel<__half><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const __half*>(src), dst, B, src_rows, r0, nrows, cols);
+  MUDG_CUDA(cudaGetLastError());
+}
+
+void from_channels_last(const __half* y, __half* out, int B, int C, int64_t R, int Cp, cudaStream_t st) {
+  const int64_t total = (int64_t)B * C * R;
+  from_channels_last_kernel<<<grid_for(total, 256), 256, 0, st>>>(y, out, B, C, R, Cp);
   MUDG_CUDA(cudaGetLastError());
 }
 

@@ -48,7 +48,9 @@ struct TapGemmGeneric {
 };
 
 bool tapgemm_tc_eligible(const TapGemm& g);
-void tapgemm_tc(const TapGemm& g, cudaStream_t st);        // tcgen05 + TMA path
+void tapgemm_tc(const TapGemm& g, cudaStream_t st);        // tcgen05 + TMA path, v1: one tile per CTA
+void tapgemm_tc2(const TapGemm& g, cudaStream_t st);       // v2: persistent CTAs, double-buffered TMEM, 64..192-wide tiles
+void tapgemm_tc_auto(const TapGemm& g, cudaStream_t st);   // v2 unless MUDG_GEMM_V1=1
 void tapgemm_simt(const TapGemm& g, cudaStream_t st);      // CUDA-core checker of the same contract (debug)
 void tapgemm_generic(const TapGemmGeneric& g, cudaStream_t st);
 // dispatch: tensor cores unless MUDG_FORCE_SIMT=1 (debug) or the layer is not eligible

@@ -89,6 +89,28 @@ void WeightStore::stack_rows(const std::string& out_key, const std::vector<std::
   bytes_ += off * sizeof(__half);
 }
 
+// zero-padded copy with O_new rows: lets a tiny-N layer (N = 4 / 3) run on the tensor-core path
+void WeightStore::pad_rows(const std::string& wkey, const std::string& bkey, int O_new, cudaStream_t st) {
+  if (hasW(wkey + ".pad")) return;
+  const Weight& w = W(wkey);
+  const Vec& b = V(bkey);
+  MUDG_REQUIRE(O_new >= w.O, "pad_rows");
+  Weight o = w;
+  o.O = O_new;
+  Vec ob;
+  ob.n = O_new;
+  const size_t nb = (size_t)O_new * w.K() * sizeof(__half);
+  MUDG_CUDA(cudaMalloc(&o.w, nb));
+  MUDG_CUDA(cudaMalloc(&ob.p, sizeof(float) * O_new));
+  MUDG_CUDA(cudaMemsetAsync(o.w, 0, nb, st));
+  MUDG_CUDA(cudaMemsetAsync(ob.p, 0, sizeof(float) * O_new, st));
+  MUDG_CUDA(cudaMemcpyAsync(o.w, w.w, (size_t)w.O * w.K() * sizeof(__half), cudaMemcpyDeviceToDevice, st));
+  MUDG_CUDA(cudaMemcpyAsync(ob.p, b.p, sizeof(float) * b.n, cudaMemcpyDeviceToDevice, st));
+  w_[wkey + ".pad"] = o;
+  v_[bkey + ".pad"] = ob;
+  bytes_ += nb + sizeof(float) * O_new;
+}
+
 void WeightStore::make_geglu(const std::string& p, cudaStream_t st) {
   if (hasW(p + ".geglu.weight")) return;
   const Weight& w = W(p + ".weight");
@@ -259,6 +281,7 @@ void Model::finalize(int which, cudaStream_t st) {
   for (const char* n : {"time_embed", "class_embed", "fps_embedding"})
     for (const char* k : {".0", ".2"}) { w.W(std::string(n) + k + ".weight"); w.V(std::string(n) + k + ".bias"); }
   w.V("out.0.weight"); w.W("out.2.weight");
+  w.pad_rows("out.2.weight", "out.2.bias", 64, st);
   unet_ready_ = true;
 }
 
@@ -619,20 +642,20 @@ void Model::unet_body(const void* x, const int64_t* t, const int64_t* label, con
   // out: GroupNorm32 + SiLU + Conv3x3(model_channels -> out_channels), written as [N, Cout, T, h, w] fp16
   Act o = group_norm(cur, "out.0", 1e-5f, true, false);
   release(cur);
+  // 4 output channels: run the conv on the tensor cores with the weight zero-padded to 64 rows, keep 4 columns
+  Act y64 = alloc(N, T, h, w, 64);
   if (live()) {
-    const Weight& wt = ws_->W("out.2.weight");
-    TapGemmGeneric g;
-    g.A = o.p; g.a_fp32 = false;
-    g.B = N; g.T = T; g.H = h; g.W = w; g.Cin = o.C;
-    g.a_sc = 1; g.a_sw = o.C; g.a_sh = (int64_t)w * o.C; g.a_st = (int64_t)h * w * o.C; g.a_sb = (int64_t)T * h * w * o.C;
+    const Weight& wt = ws_->W("out.2.weight.pad");
+    TapGemm g;
+    g.A = o.p; g.B = 1; g.T = N * T; g.H = h; g.W = w; g.Cin = o.C;
     g.ntaps = 9; set_taps_3x3(g.taps);
-    g.Wt = wt.w; g.CinW = wt.Ipad; g.N = wt.O;
-    g.D = out; g.d_fp32 = false;
-    g.d_sw = 1; g.d_sh = w; g.d_st = (int64_t)h * w; g.d_sn = (int64_t)T * h * w; g.d_sb = (int64_t)wt.O * T * h * w;
-    g.bias = ws_->V("out.2.bias").p;
-    tapgemm_generic(g, st_);
-    launches++;
+    g.Wt = wt.w; g.N = wt.O; g.D = y64.p;
+    g.bias = ws_->V("out.2.bias.pad").p;
+    tapgemm(g, st_);
+    from_channels_last(y64.p, static_cast<__half*>(out), N, ucfg_.out_channels, (int64_t)T * h * w, 64, st_);
+    launches += 2;
   }
+  release(y64);
   release(o);
 }
 

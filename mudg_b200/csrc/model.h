@@ -46,6 +46,7 @@ class WeightStore {
   bool hasV(const std::string& key) const { return v_.count(key) != 0; }
   // out = rows of keys stacked ([sum O][K]); sources are released
   void stack_rows(const std::string& out_key, const std::vector<std::string>& keys, cudaStream_t st);
+  void pad_rows(const std::string& wkey, const std::string& bkey, int O_new, cudaStream_t st);
   void make_geglu(const std::string& proj_prefix, cudaStream_t st);   // "<p>.weight"/".bias" -> "<p>.geglu.weight"/".bias"
   void drop(const std::string& key);
   size_t bytes() const { return bytes_; }

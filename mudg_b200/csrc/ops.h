@@ -20,6 +20,7 @@ void cast_to_f32(const void* src, bool src_fp32, float* dst, int64_t n, cudaStre
 void cast_to_f16(const void* src, bool src_fp32, __half* dst, int64_t n, cudaStream_t st);
 void geglu_interleave(const __half* w, const float* b, __half* wo, float* bo, int half_rows, int cols, cudaStream_t st);
 void to_channels_last(const void* x, bool x_fp32, __half* y, int B, int C, int64_t R, int Cpad, cudaStream_t st);
+void from_channels_last(const __half* y, __half* out, int B, int C, int64_t R, int Cp, cudaStream_t st);
 void gather_rows_f16(const void* src, bool src_fp32, __half* dst, int B, int src_rows, int r0, int nrows, int cols,
                      cudaStream_t st);
 void sinusoid(const int64_t* t, float* out, int B, int dim, cudaStream_t st);

@@ -245,6 +245,307 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
+// ================================================================ tap GEMM v2: persistent, double-buffered accumulators
+// Two persistent CTAs per SM loop over output tiles (N tiles fastest so co-resident CTAs share A in L2):
+//   warp 0   TMA producer  -- 3-stage ring of {A 128x64, B 128x64} per CTA (6 stages in flight per SM)
+//   warp 1   MMA issuer    -- accumulates tile t into TMEM buffer t&1 (2 x 128 columns); the MMA N is the tile's real
+//                             width (128, or 64 for the last tile of N = 64 mod 128: N = 320 costs 128+128+64)
+//   warps 2-5 epilogue     -- drains buffer t&1 while the issuer already works on tile t+1.  Residual rows are
+//                             prefetched from global one 32-column slice ahead; 64-column chunks go through a 16 KB
+//                             swizzled staging tile and are written with TMA (clips partial tiles).
+// TMEM alloc, barrier init and descriptor prefetch are paid once per CTA instead of once per tile.
+constexpr int G2_STAGES = 3;
+constexpr int G2_BN_MAX = 128;
+constexpr int G2_A_BYTES = BM * BK * 2;                 // 16 KB
+constexpr int G2_B_BYTES = G2_BN_MAX * BK * 2;          // 16 KB
+constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES; // 32 KB
+constexpr int G2_STG_BYTES = 16384;
+// 2 CTAs/SM: 2 * (G2_SMEM + 1 KB reserved) must fit in 228 KB -> no alignment slack; the base is declared 1024-aligned
+constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + G2_STG_BYTES + 128;
+static_assert(2 * (G2_SMEM + 1024) <= 233472, "two CTAs of the persistent GEMM must fit one SM");
+constexpr int G2_THREADS = 192;
+
+struct G2Params {
+  TcParams b;            // shared fields (taps, bias, ...)
+  int nt;                // number of N tiles (all 128 wide except possibly the last)
+  int total_tiles;
+  int tiles_b;
+  int dimW, dimH, dimB;  // extents for the residual bounds check
+  const __half* R;       // residual (read straight from global / L2)
+  int alpha_is_one;
+};
+
+__device__ __forceinline__ float erf_fast(float x) {   // Abramowitz-Stegun 7.1.26, |err| <= 1.5e-7
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.f, fmaf(0.3275911f, ax, 1.f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float y = 1.f - poly * t * __expf(-ax * ax);
+  return copysignf(y, x);
+}
+__device__ __forceinline__ float gelu_fast(float x) { return 0.5f * x * (1.f + erf_fast(x * 0.70710678118654752f)); }
+
+struct G2Tile {
+  int n0, bn, w0, h0, t0, b0;
+};
+__device__ __forceinline__ G2Tile g2_decode(const G2Params& p, int tile) {
+  G2Tile t;
+  const int nt_i = tile % p.nt;
+  int m = tile / p.nt;
+  t.n0 = nt_i * G2_BN_MAX;
+  t.bn = min(G2_BN_MAX, p.b.N - t.n0);
+  const int tw = m % p.b.tiles_w; m /= p.b.tiles_w;
+  const int th = m % p.b.tiles_h; m /= p.b.tiles_h;
+  const int tt = m % p.b.tiles_t;
+  const int tb = m / p.b.tiles_t;
+  t.w0 = tw * p.b.bw; t.h0 = th * p.b.bh; t.t0 = tt * p.b.bt; t.b0 = tb * p.b.bb;
+  return t;
+}
+
+__global__ void __launch_bounds__(G2_THREADS, 2)
+tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ CUtensorMap tmD, const G2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_dyn[];
+  uint8_t* smem = smem_dyn;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();          // SWIZZLE_128B tiles need a 1024 B aligned base
+  uint8_t* stg = smem + G2_STAGES * G2_STAGE_BYTES;     // 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + G2_STG_BYTES);
+  uint64_t* full = bars;                        // [3]
+  uint64_t* empty = bars + G2_STAGES;           // [3]
+  uint64_t* tmem_full = bars + 2 * G2_STAGES;   // [2]
+  uint64_t* tmem_empty = bars + 2 * G2_STAGES + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G2_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < G2_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmD);
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int ktotal = p.b.ntaps * p.b.kchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const G2Tile tl = g2_decode(p, tile);
+        for (int k = 0; k < ktotal; k++, it++) {
+          const int s = it % G2_STAGES;
+          mbar_wait(&empty[s], ((it / G2_STAGES) & 1) ^ 1);
+          mbar_expect_tx(&full[s], G2_STAGE_BYTES);
+          const int tap = k / p.b.kchunks, kc = k - tap * p.b.kchunks;
+          uint8_t* a_s = smem + s * G2_STAGE_BYTES;
+          tma_load_5d(a_s, &tmA, &full[s], kc * BK, tl.w0 + p.b.taps[tap][0], tl.h0 + p.b.taps[tap][1],
+                      tl.t0 + p.b.taps[tap][2], tl.b0);
+          // rows past N (last tile of N = 64 mod 128) are zero-filled and never multiplied (MMA N = tl.bn)
+          tma_load_5d(a_s + G2_A_BYTES, &tmB, &full[s], tap * p.b.cin + kc * BK, tl.n0, 0, 0, 0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, lt++) {
+        const G2Tile tl = g2_decode(p, tile);
+        const uint32_t acc = lt & 1;
+        mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t idesc = umma_idesc_f16(BM, tl.bn, 0, 0);
+        const uint32_t d_tmem = tmem_base + acc * G2_BN_MAX;
+        for (int k = 0; k < ktotal; k++, it++) {
+          const int s = it % G2_STAGES;
+          mbar_wait(&full[s], (it / G2_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * G2_STAGE_BYTES);
+          const uint64_t da = umma_desc_sw128(a_addr, 16, 1024);
+          const uint64_t db = umma_desc_sw128(a_addr + G2_A_BYTES, 16, 1024);
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; kk++)
+            umma_f16(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const bool issuer = (warp == 2 && lane == 0);
+    uint8_t* srow = stg + row * 128;
+    // row -> (iw, ih, it, ib) inside the pixel box
+    int r = row;
+    const int iw = r % p.b.bw; r /= p.b.bw;
+    const int ih = r % p.b.bh; r /= p.b.bh;
+    const int it_ = r % p.b.bt;
+    const int ib_ = r / p.b.bt;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, lt++) {
+      const G2Tile tl = g2_decode(p, tile);
+      const uint32_t acc = lt & 1;
+      const uint32_t t_row = tmem_base + acc * G2_BN_MAX + lane_off;
+      const int pw = tl.w0 + iw, ph = tl.h0 + ih, pt = tl.t0 + it_, pb = tl.b0 + ib_;
+      const bool row_ok = pw < p.dimW && ph < p.dimH && pt < p.b.dimT && pb < p.dimB;
+      const int64_t pix = (((int64_t)pb * p.b.dimT + pt) * p.dimH + ph) * p.dimW + pw;
+      if (p.b.geglu) {
+        mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
+        __syncwarp();
+        tc_fence_after();
+        // weight rows interleaved 64 value / 64 gate: TMEM columns [0,64) value, [64,128) gate -> 64 output columns
+        if (issuer) tma_store_wait_read0();
+        __syncwarp();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll 1
+        for (int c = 0; c < 2; c++) {
+          uint32_t v[32], g[32];
+          tmem_ld32(t_row + c * 32, v);
+          tmem_ld32(t_row + 64 + c * 32, g);
+          tmem_ld_wait();
+          if (c == 1) {                     // all TMEM reads of this accumulator are done
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+          }
+          const float4* bv = reinterpret_cast<const float4*>(p.b.bias + tl.n0 + c * 32);
+          uint32_t o[16];
+#pragma unroll
+          for (int i4 = 0; i4 < 8; i4++) {
+            float4 b_v = make_float4(0.f, 0.f, 0.f, 0.f), b_g = b_v;
+            if (p.b.bias != nullptr) { b_v = __ldg(bv + i4); b_g = __ldg(bv + 16 + i4); }
+            const float al = p.b.alpha;
+            const float v0 = fmaf(__uint_as_float(v[4 * i4]), al, b_v.x), v1 = fmaf(__uint_as_float(v[4 * i4 + 1]), al, b_v.y);
+            const float v2 = fmaf(__uint_as_float(v[4 * i4 + 2]), al, b_v.z), v3 = fmaf(__uint_as_float(v[4 * i4 + 3]), al, b_v.w);
+            const float g0 = fmaf(__uint_as_float(g[4 * i4]), al, b_g.x), g1 = fmaf(__uint_as_float(g[4 * i4 + 1]), al, b_g.y);
+            const float g2 = fmaf(__uint_as_float(g[4 * i4 + 2]), al, b_g.z), g3 = fmaf(__uint_as_float(g[4 * i4 + 3]), al, b_g.w);
+            o[2 * i4] = pack_half2(v0 * gelu_fast(g0), v1 * gelu_fast(g1));
+            o[2 * i4 + 1] = pack_half2(v2 * gelu_fast(g2), v3 * gelu_fast(g3));
+          }
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            *reinterpret_cast<uint4*>(srow + (((c * 4 + j) ^ (row & 7)) << 4)) =
+                make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (issuer) {
+          tma_store_5d(&tmD, stg, tl.n0 / 2, tl.w0, tl.h0, tl.t0, tl.b0);
+          tma_store_commit();
+        }
+        __syncwarp();
+        continue;
+      }
+      int sample = 0;
+      if (p.b.bias2 != nullptr) {
+        sample = (pb * p.b.dimT + pt) / p.b.bias2_div;
+        if (sample >= p.b.nb2) sample = p.b.nb2 - 1;
+      }
+      const uint4* rp = (p.R != nullptr && row_ok) ? reinterpret_cast<const uint4*>(p.R + pix * p.b.n_out + tl.n0) : nullptr;
+      uint4 res_nxt[4];
+      if (rp != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) res_nxt[j] = __ldg(rp + j);
+      }
+      mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
+      __syncwarp();
+      tc_fence_after();
+      const int nh = tl.bn >> 5;             // 32-column slices (2 or 4)
+#pragma unroll 1
+      for (int hf = 0; hf < nh; hf++) {
+        uint4 res[4];
+        if (rp != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) res[j] = res_nxt[j];
+          if (hf + 1 < nh) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) res_nxt[j] = __ldg(rp + (hf + 1) * 4 + j);
+          }
+        }
+        uint32_t v[32];
+        tmem_ld32(t_row + hf * 32, v);
+        if ((hf & 1) == 0) {                 // staging tile must be free: previous TMA store has read it
+          if (issuer) tma_store_wait_read0();
+          __syncwarp();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        tmem_ld_wait();
+        if (hf == nh - 1) {                  // all TMEM reads of this accumulator are done
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[acc]);
+        }
+        const int col0 = tl.n0 + hf * 32;
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) f[i] = __uint_as_float(v[i]);
+        if (!p.alpha_is_one) {
+#pragma unroll
+          for (int i = 0; i < 32; i++) f[i] *= p.b.alpha;
+        }
+        if (p.b.bias != nullptr) {
+          const float4* bp = reinterpret_cast<const float4*>(p.b.bias + col0);
+#pragma unroll
+          for (int i4 = 0; i4 < 8; i4++) {
+            const float4 b4 = __ldg(bp + i4);
+            f[4 * i4] += b4.x; f[4 * i4 + 1] += b4.y; f[4 * i4 + 2] += b4.z; f[4 * i4 + 3] += b4.w;
+          }
+        }
+        if (p.b.bias2 != nullptr) {
+          const float4* bp = reinterpret_cast<const float4*>(p.b.bias2 + (size_t)sample * p.b.N + col0);
+#pragma unroll
+          for (int i4 = 0; i4 < 8; i4++) {
+            const float4 b4 = __ldg(bp + i4);
+            f[4 * i4] += b4.x; f[4 * i4 + 1] += b4.y; f[4 * i4 + 2] += b4.z; f[4 * i4 + 3] += b4.w;
+          }
+        }
+        if (rp != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const float2 r0 = unpack_half2(res[j].x), r1 = unpack_half2(res[j].y), r2 = unpack_half2(res[j].z),
+                         r3 = unpack_half2(res[j].w);
+            f[8 * j + 0] += r0.x; f[8 * j + 1] += r0.y; f[8 * j + 2] += r1.x; f[8 * j + 3] += r1.y;
+            f[8 * j + 4] += r2.x; f[8 * j + 5] += r2.y; f[8 * j + 6] += r3.x; f[8 * j + 7] += r3.y;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          *reinterpret_cast<uint4*>(srow + ((((hf & 1) * 4 + j) ^ (row & 7)) << 4)) =
+              make_uint4(pack_half2(f[8 * j + 0], f[8 * j + 1]), pack_half2(f[8 * j + 2], f[8 * j + 3]),
+                         pack_half2(f[8 * j + 4], f[8 * j + 5]), pack_half2(f[8 * j + 6], f[8 * j + 7]));
+        if (hf & 1) {                        // a 64-column chunk is complete
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (issuer) {
+            tma_store_5d(&tmD, stg, tl.n0 + (hf >> 1) * 64, tl.w0, tl.h0, tl.t0, tl.b0);
+            tma_store_commit();
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (issuer) tma_store_wait_read0();
+    __syncwarp();
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // SIMT checker of the same contract: one thread per output element, fp32 accumulate.
 __global__ void tapgemm_simt_kernel(const __half* __restrict__ A, const __half* __restrict__ Wt, __half* __restrict__ D,
@@ -418,6 +719,50 @@ void tapgemm_tc(const TapGemm& g, cudaStream_t st) {
   MUDG_CUDA(cudaGetLastError());
 }
 
+void tapgemm_tc2(const TapGemm& g, cudaStream_t st) {
+  MUDG_REQUIRE(tapgemm_tc_eligible(g), "layer not eligible for the tcgen05 path (Cin=%d N=%d)", g.Cin, g.N);
+  G2Params p{};
+  p.b = make_params(g);
+  int budget = BM;
+  p.b.bw = pick_box(g.W, budget); budget /= p.b.bw;
+  p.b.bh = pick_box(g.H, budget); budget /= p.b.bh;
+  p.b.bt = pick_box(g.T, budget); budget /= p.b.bt;
+  p.b.bb = budget;
+  p.b.tiles_w = (g.W + p.b.bw - 1) / p.b.bw;
+  p.b.tiles_h = (g.H + p.b.bh - 1) / p.b.bh;
+  p.b.tiles_t = (g.T + p.b.bt - 1) / p.b.bt;
+  p.tiles_b = (g.B + p.b.bb - 1) / p.b.bb;
+  p.nt = (g.N + G2_BN_MAX - 1) / G2_BN_MAX;
+  p.b.tiles_n = p.nt;
+  const int64_t total = (int64_t)p.nt * p.b.tiles_w * p.b.tiles_h * p.b.tiles_t * p.tiles_b;
+  MUDG_REQUIRE(total > 0 && total < (int64_t(1) << 31), "grid too large");
+  p.total_tiles = (int)total;
+  p.dimW = g.W; p.dimH = g.H; p.dimB = g.B;
+  p.R = g.R;
+  p.alpha_is_one = g.alpha == 1.f ? 1 : 0;
+
+  const uint64_t C = g.Cin, No = p.b.n_out, Ktot = (uint64_t)g.ntaps * g.Cin;
+  const uint64_t adims[5] = {C, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.T, (uint64_t)g.B};
+  const uint64_t astr[4] = {C * 2, C * 2 * g.W, C * 2 * g.W * g.H, C * 2 * g.W * g.H * g.T};
+  const uint32_t abox[5] = {BK, (uint32_t)p.b.bw, (uint32_t)p.b.bh, (uint32_t)p.b.bt, (uint32_t)p.b.bb};
+  const uint64_t ddims[5] = {No, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.T, (uint64_t)g.B};
+  const uint64_t dstr[4] = {No * 2, No * 2 * g.W, No * 2 * g.W * g.H, No * 2 * g.W * g.H * g.T};
+  const uint64_t bdims[5] = {Ktot, (uint64_t)g.N, 1, 1, 1};
+  const uint64_t bstr[4] = {Ktot * 2, Ktot * 2 * g.N, Ktot * 2 * g.N, Ktot * 2 * g.N};
+  const uint32_t bbox[5] = {BK, G2_BN_MAX, 1, 1, 1};
+  const CUtensorMap* ma = get_tmap(g.A, adims, astr, abox);
+  const CUtensorMap* mb = get_tmap(g.Wt, bdims, bstr, bbox);
+  const CUtensorMap* md = get_tmap(g.D, ddims, dstr, abox);
+  static bool attr_set = false;
+  if (!attr_set) {
+    MUDG_CUDA(cudaFuncSetAttribute(tapgemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
+    attr_set = true;
+  }
+  const int grid = (int)std::min<int64_t>(total, 2 * sm_count());
+  tapgemm_tc2_kernel<<<grid, G2_THREADS, G2_SMEM, st>>>(*ma, *mb, *md, p);
+  MUDG_CUDA(cudaGetLastError());
+}
+
 void tapgemm_simt(const TapGemm& g, cudaStream_t st) {
   TcParams p = make_params(g);
   const int64_t total = (int64_t)g.B * g.T * g.H * g.W * p.n_out;
@@ -434,6 +779,15 @@ void tapgemm_generic(const TapGemmGeneric& g, cudaStream_t st) {
   else if (g.d_fp32) tapgemm_generic_kernel<__half, float><<<blocks, 256, 0, st>>>(g);
   else tapgemm_generic_kernel<__half, __half><<<blocks, 256, 0, st>>>(g);
   MUDG_CUDA(cudaGetLastError());
+}
+
+void tapgemm_tc_auto(const TapGemm& g, cudaStream_t st) {
+  static const bool use_v1 = [] {
+    const char* e = getenv("MUDG_GEMM_V1");
+    return e && e[0] == '1';
+  }();
+  if (use_v1) tapgemm_tc(g, st);
+  else tapgemm_tc2(g, st);
 }
 
 // ---- optional per-launch timing of the tcgen05 GEMM (bench.py's roofline leg): CUDA events on the launching stream
@@ -483,13 +837,13 @@ void tapgemm(const TapGemm& g, cudaStream_t st) {
         g_prof.ev.push_back(b);
       }
       MUDG_CUDA(cudaEventRecord(g_prof.ev[2 * g_prof.used], st));
-      tapgemm_tc(g, st);
+      tapgemm_tc_auto(g, st);
       MUDG_CUDA(cudaEventRecord(g_prof.ev[2 * g_prof.used + 1], st));
       // algorithmic work of the layer: 2 * rows * N * (taps * Cin), padding and tile overhang not counted
       g_prof.flops.push_back(2.0 * (double)g.B * g.T * g.H * g.W * (double)g.N * (double)g.ntaps * g.Cin);
       g_prof.used++;
     } else {
-      tapgemm_tc(g, st);
+      tapgemm_tc_auto(g, st);
     }
   } else {
     tapgemm_simt(g, st);

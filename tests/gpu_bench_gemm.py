@@ -1,0 +1,73 @@
+"""Micro-benchmark of the tap-GEMM backends over the layer shapes of the MDM1024 CFG forward (N=2, T=16)."""
+import ctypes
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from mudg_b200._lib import lib, check, ptr, cur_stream   # noqa: E402
+
+# (name, B, T, H, W, Cin, N, mode, res, geglu)
+SHAPES = [
+    ("conv3 L0 320->320", 1, 32, 72, 128, 320, 320, 1, 1, 0),
+    ("conv3 L0 960->320", 1, 32, 72, 128, 960, 320, 1, 0, 0),
+    ("conv3 L1 640->640", 1, 32, 36, 64, 640, 640, 1, 1, 0),
+    ("conv3 L2 1280->1280", 1, 32, 18, 32, 1280, 1280, 1, 1, 0),
+    ("conv3 L3 1280->1280", 1, 32, 9, 16, 1280, 1280, 1, 1, 0),
+    ("conv3 L3 2560->1280", 1, 32, 9, 16, 2560, 1280, 1, 0, 0),
+    ("tconv L0 320", 2, 16, 72, 128, 320, 320, 2, 0, 0),
+    ("tconv L1 640", 2, 16, 36, 64, 640, 640, 2, 0, 0),
+    ("tconv L2 1280", 2, 16, 18, 32, 1280, 1280, 2, 0, 0),
+    ("tconv L3 1280", 2, 16, 9, 16, 1280, 1280, 2, 1, 0),
+    ("lin L0 320->320 +res", 1, 1, 1, 294912, 320, 320, 0, 1, 0),
+    ("lin L0 320->960 qkv", 1, 1, 1, 294912, 320, 960, 0, 0, 0),
+    ("lin L0 320->2560 geglu", 1, 1, 1, 294912, 320, 2560, 0, 0, 1),
+    ("lin L0 1280->320 +res", 1, 1, 1, 294912, 1280, 320, 0, 1, 0),
+    ("lin L1 640->1920 qkv", 1, 1, 1, 73728, 640, 1920, 0, 0, 0),
+    ("lin L1 640->5120 geglu", 1, 1, 1, 73728, 640, 5120, 0, 0, 1),
+    ("lin L1 2560->640 +res", 1, 1, 1, 73728, 2560, 640, 0, 1, 0),
+    ("lin L2 1280->3840 qkv", 1, 1, 1, 18432, 1280, 3840, 0, 0, 0),
+    ("lin L2 1280->10240 geglu", 1, 1, 1, 18432, 1280, 10240, 0, 0, 1),
+    ("lin L2 5120->1280 +res", 1, 1, 1, 18432, 5120, 1280, 0, 1, 0),
+    ("lin L3 1280->1280", 1, 1, 1, 4608, 1280, 1280, 0, 1, 0),
+]
+
+
+def main():
+    dev = "cuda"
+    L = lib()
+    backends = [(2, "v1"), (0, "v2")]
+    print(f"{'shape':28s} " + " ".join(f"{n:>8s}us {n:>6s}TF" for _, n in backends))
+    for name, B, T, H, W, Cin, N, mode, res, geglu in SHAPES:
+        ntaps = {0: 1, 1: 9, 2: 3}[mode]
+        A = torch.randn(B, T, H, W, Cin, device=dev).half()
+        Wt = (torch.randn(N, ntaps * Cin, device=dev) / (ntaps * Cin) ** 0.5).half()
+        n_out = N // 2 if geglu else N
+        D = torch.empty(B, T, H, W, n_out, device=dev).half()
+        R = torch.randn(B, T, H, W, n_out, device=dev).half() if res else None
+        bias = torch.randn(N, device=dev)
+        flops = 2.0 * B * T * H * W * N * ntaps * Cin
+        row = f"{name:28s} "
+        for backend, bn in backends:
+            def run():
+                check(L.mudg_test_tapgemm(ptr(A), B, T, H, W, Cin, mode, ptr(Wt), N, ptr(D), ptr(R), ptr(bias), None,
+                                          ctypes.c_int(1), ctypes.c_int(0), ctypes.c_float(1.0), int(geglu), backend, cur_stream()))
+            for _ in range(3):
+                run()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            e0.record()
+            for _ in range(reps):
+                run()
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) / reps * 1e3
+            row += f"{us:10.1f} {flops / us / 1e6:8.0f} "
+        print(row, flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -20,6 +20,11 @@ CASES = {
     "tconv": (2, 4, 8, 8, 128, 128, 2, 1, 1, 0, 0),
     "tconv_l0": (1, 16, 18, 32, 640, 640, 2, 1, 1, 0, 0),
     "cin16": (1, 2, 16, 16, 16, 64, 1, 0, 1, 0, 0),
+    "lin_persist": (1, 1, 1, 40000, 320, 320, 0, 1, 1, 0, 0),
+    "lin_n960": (1, 1, 1, 30000, 320, 960, 0, 0, 0, 0, 0),
+    "lin_n64": (1, 1, 1, 5000, 128, 64, 0, 1, 1, 0, 0),
+    "geglu_big": (1, 1, 1, 30000, 320, 2560, 0, 0, 1, 0, 1),
+    "conv_emb": (2, 4, 18, 32, 640, 640, 1, 1, 1, 1, 0),
 }
 
 
@@ -61,7 +66,7 @@ def run_case(name):
     if R is not None:
         y = y + R.float()
     out = {}
-    for backend, label in ((1, "simt"), (0, "tc")):
+    for backend, label in ((1, "simt"), (2, "tc_v1"), (0, "tc")):
         D = torch.full((B, T, H, W, n_out), float("nan"), device=dev).half()
         torch.cuda.synchronize()
         t0 = time.time()
@@ -75,7 +80,7 @@ def run_case(name):
         out[label] = (float(err[~torch.isnan(err)].max()) if nan < err.numel() else float("nan"), nan)
         print(f"{name:14s} {label:5s} max|d|={out[label][0]:.5f} nans={nan} ref_absmax={float(y.abs().max()):.3f} "
               f"({(time.time() - t0) * 1e3:.1f} ms)", flush=True)
-        if label == "tc" and (out[label][0] > 0.05 or nan):
+        if label.startswith("tc") and (out[label][0] > 0.05 or nan):
             bad = (err > 0.05) | torch.isnan(D.float())
             idx = bad.nonzero()
             print("   first bad idx:", idx[:5].tolist(), " n_bad:", int(bad.sum()), "of", err.numel(), flush=True)
@@ -89,9 +94,12 @@ def run_case(name):
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
-    if which == "all":
+    if which == "inproc":          # one process (fast); a device trap poisons the remaining cases
         for name in CASES:
-            r = subprocess.run([sys.executable, __file__, name], timeout=300)
+            run_case(name)
+    elif which == "all":
+        for name in CASES:
+            r = subprocess.run([sys.executable, __file__, name], timeout=600)
             if r.returncode != 0:
                 print(f"{name}: FAILED rc={r.returncode}", flush=True)
     else:
