@@ -656,6 +656,153 @@ __global__ void temporal_attn_kernel(const __half* __restrict__ qkv, __half* __r
   }
 }
 
+// ---------------------------------------------------------------- temporal attention, T == 16: tensor-core path
+// One warp per (b, pixel, head) problem: S = Q K^T (16x16x64) and O = P V (16x64x16) are 16 mma.sync.m16n8k16 in
+// total, so the kernel is purely HBM-bound.  Q/K/V tiles (16 tokens x 128 B, gathered with stride H*W*3C) are
+// brought in with cp.async into a 2-deep per-warp ring of XOR-swizzled smem tiles and read back with ldmatrix
+// (.trans for V); the softmax lives in the accumulator fragments (quad shuffles); P is re-packed as the A operand.
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+constexpr int TA_WARPS = 4;
+constexpr int TA_TILE = 16 * 128;                 // one 16-token x 64-dim fp16 tile
+constexpr int TA_SMEM = TA_WARPS * 2 * 3 * TA_TILE;   // 48 KB
+
+__global__ void __launch_bounds__(TA_WARPS * 32)
+temporal_attn16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int B, int HW, int heads, float scale_log2) {
+  extern __shared__ __align__(128) uint8_t ta_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int inner = heads * 64;
+  const int64_t pitch = 3 * (int64_t)inner;
+  const int64_t npairs = (int64_t)B * HW * heads;
+  const int64_t wid = (int64_t)blockIdx.x * TA_WARPS + warp;
+  const int64_t wstride = (int64_t)gridDim.x * TA_WARPS;
+  uint8_t* wbase = ta_smem + warp * (2 * 3 * TA_TILE);
+  const uint32_t wbase_u = smem_u32(wbase);
+
+  // lane -> (token row, 16 B chunk) pairs for the gathers: 16 rows x 8 chunks = 128 pieces per tile, 4 per lane
+  auto issue_loads = [&](int64_t pr, int buf) {
+    const int head = pr % heads;
+    const int64_t bp = pr / heads;
+    const int px = bp % HW;
+    const int b = bp / HW;
+    const __half* base = qkv + ((int64_t)b * 16 * HW + px) * pitch + head * 64;
+    const uint32_t sb = wbase_u + buf * (3 * TA_TILE);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int piece = lane + 32 * i;
+      const int r = piece >> 3, c = piece & 7;
+      const __half* src = base + (int64_t)r * HW * pitch + c * 8;
+      const uint32_t dst = sb + r * 128 + ((c ^ (r & 7)) << 4);
+      cp_async16(dst, src);                                  // Q
+      cp_async16(dst + TA_TILE, src + inner);                // K
+      cp_async16(dst + 2 * TA_TILE, src + 2 * inner);        // V
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int buf = 0;
+  if (wid < npairs) issue_loads(wid, 0);
+  for (int64_t pr = wid; pr < npairs; pr += wstride, buf ^= 1) {
+    const int64_t nxt = pr + wstride;
+    if (nxt < npairs) {
+      issue_loads(nxt, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+    const uint32_t sq = wbase_u + buf * (3 * TA_TILE), sk = sq + TA_TILE, sv = sq + 2 * TA_TILE;
+    // ---- S = Q K^T
+    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) {
+      uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+      {
+        const int r = (lane & 7) + 8 * ((lane >> 3) & 1), c = 2 * ks + (lane >> 4);
+        ldsm_x4(sq + r * 128 + ((c ^ (r & 7)) << 4), a0, a1, a2, a3);
+      }
+      {
+        const int r = (lane & 7) + 8 * (lane >> 4), c = 2 * ks + ((lane >> 3) & 1);
+        ldsm_x4(sk + r * 128 + ((c ^ (r & 7)) << 4), b0, b1, b2, b3);
+      }
+      mma16816(s0, a0, a1, a2, a3, b0, b1);     // keys 0..7
+      mma16816(s1, a0, a1, a2, a3, b2, b3);     // keys 8..15
+    }
+    // ---- softmax over the 16 keys of rows g (c0,c1) and g+8 (c2,c3); a row lives in one quad of lanes
+    float mA = fmaxf(fmaxf(s0[0], s0[1]), fmaxf(s1[0], s1[1]));
+    float mB = fmaxf(fmaxf(s0[2], s0[3]), fmaxf(s1[2], s1[3]));
+    mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 1)); mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 2));
+    mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 1)); mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 2));
+    const float oA = mA * scale_log2, oB = mB * scale_log2;
+    const float p00 = exp2f(fmaf(s0[0], scale_log2, -oA)), p01 = exp2f(fmaf(s0[1], scale_log2, -oA));
+    const float p10 = exp2f(fmaf(s1[0], scale_log2, -oA)), p11 = exp2f(fmaf(s1[1], scale_log2, -oA));
+    const float p02 = exp2f(fmaf(s0[2], scale_log2, -oB)), p03 = exp2f(fmaf(s0[3], scale_log2, -oB));
+    const float p12 = exp2f(fmaf(s1[2], scale_log2, -oB)), p13 = exp2f(fmaf(s1[3], scale_log2, -oB));
+    float lA = p00 + p01 + p10 + p11, lB = p02 + p03 + p12 + p13;
+    lA += __shfl_xor_sync(0xffffffffu, lA, 1); lA += __shfl_xor_sync(0xffffffffu, lA, 2);
+    lB += __shfl_xor_sync(0xffffffffu, lB, 1); lB += __shfl_xor_sync(0xffffffffu, lB, 2);
+    const uint32_t pa0 = pack_half2(p00, p01), pa1 = pack_half2(p02, p03), pa2 = pack_half2(p10, p11),
+                   pa3 = pack_half2(p12, p13);
+    // ---- O = P V
+    float o[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; j++) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+#pragma unroll
+    for (int nj = 0; nj < 8; nj += 2) {
+      uint32_t b0, b1, b2, b3;
+      const int r = (lane & 7) + 8 * ((lane >> 3) & 1), c = nj + (lane >> 4);
+      ldsm_x4_t(sv + r * 128 + ((c ^ (r & 7)) << 4), b0, b1, b2, b3);
+      mma16816(o[nj], pa0, pa1, pa2, pa3, b0, b1);
+      mma16816(o[nj + 1], pa0, pa1, pa2, pa3, b2, b3);
+    }
+    const float iA = 1.f / lA, iB = 1.f / lB;
+    // ---- stage O (fp16) in the Q tile, then 128-bit coalesced stores
+    __syncwarp();
+    {
+      const int g = lane >> 2, t = lane & 3;
+      uint8_t* so = wbase + buf * (3 * TA_TILE);
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        *reinterpret_cast<uint32_t*>(so + g * 128 + ((j ^ (g & 7)) << 4) + t * 4) = pack_half2(o[j][0] * iA, o[j][1] * iA);
+        *reinterpret_cast<uint32_t*>(so + (g + 8) * 128 + ((j ^ ((g + 8) & 7)) << 4) + t * 4) = pack_half2(o[j][2] * iB, o[j][3] * iB);
+      }
+    }
+    __syncwarp();
+    {
+      const int head = pr % heads;
+      const int64_t bp = pr / heads;
+      const int px = bp % HW;
+      const int b = bp / HW;
+      __half* ob = out + ((int64_t)b * 16 * HW + px) * inner + head * 64;
+      const uint8_t* so = wbase + buf * (3 * TA_TILE);
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int piece = lane + 32 * i;
+        const int r = piece >> 3, c = piece & 7;
+        const uint4 val = *reinterpret_cast<const uint4*>(so + r * 128 + ((c ^ (r & 7)) << 4));
+        *reinterpret_cast<uint4*>(ob + (int64_t)r * HW * inner + c * 8) = val;
+      }
+    }
+    __syncwarp();     // the tile is reused by the prefetch issued two iterations from now
+  }
+}
+
 const CUtensorMap* rows_map(const __half* base, int width, int pitch, int rows, int batches) {
   const uint64_t dims[5] = {(uint64_t)width, (uint64_t)rows, (uint64_t)batches, 1, 1};
   const uint64_t pb = (uint64_t)pitch * 2;
@@ -722,6 +869,23 @@ void flash_attention(const FlashArgs& a, cudaStream_t st) {
 
 void temporal_attention(const __half* qkv, __half* out, int B, int T, int HW, int heads, float scale, cudaStream_t st) {
   MUDG_REQUIRE(T >= 1 && T <= 64, "temporal attention supports T <= 64 (T=%d)", T);
+  static const bool generic_only = [] {
+    const char* e = getenv("MUDG_TATTN_GENERIC");
+    return e && e[0] == '1';
+  }();
+  if (T == 16 && !generic_only) {
+    static bool attr16 = false;
+    if (!attr16) {
+      MUDG_CUDA(cudaFuncSetAttribute(temporal_attn16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
+      attr16 = true;
+    }
+    const int64_t np = (int64_t)B * HW * heads;
+    const int64_t want = (np + TA_WARPS - 1) / TA_WARPS;
+    const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count() * 4);
+    temporal_attn16_kernel<<<grid, TA_WARPS * 32, TA_SMEM, st>>>(qkv, out, B, HW, heads, scale * 1.4426950408889634f);
+    MUDG_CUDA(cudaGetLastError());
+    return;
+  }
   int group = 1;
   while (group < T && group < 32) group *= 2;
   const int ppw = group < 32 ? 32 / group : 1;
