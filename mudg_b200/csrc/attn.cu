@@ -244,16 +244,17 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // ================================================================ flash attention v2 (FA4-style schedule)
 // One CTA per SM, 256 queries (two 128-row tiles) of one (frame, head):
 //   warp 0      TMA producer: Q0,Q1 once; K/V 128-token blocks through a 3-stage ring (shared by both tiles)
-//   warp 1      tcgen05 issuer: per kv block S_i = Q_i K^T (N128 K64) and O_i += P_i V (N64 K128, V MN-major)
-//               plus l_i += P_i 1 (N16: the row sums come from the tensor core, consistent with the fp16 P)
+//   warp 1      tcgen05 issuer: per kv block S_i = Q_i K^T (N128 K64) and O_i += P_i V (N64 K128): P is read from
+//               TMEM (A-in-TMEM MMA), V MN-major from its row-major TMA tile -- P never touches shared memory
 //   warps 2-5   softmax group 0 (tile 0);  warps 6-9 softmax group 1 (tile 1): thread == row == TMEM lane.
 //               While group 0 works on S_0 the tensor core runs the other tile's GEMMs (ping-pong).
-//   O and l stay in TMEM across kv blocks; the running max is only raised when it grows by > 2^8 (lazy
-//   rescale: P <= 256 fits fp16), in which case the warp rescales its O/l rows in place (tcgen05.ld/st).
-//   exp2 is evaluated two-at-a-time (ex2.approx.ftz.f16x2) directly into the fp16 P operand.
+//   The S row is pulled into registers in one TMEM round trip (the issuer then already computes the next S),
+//   P = 2^(s - m) is written back to TMEM as packed fp16, O stays in TMEM across kv blocks; the running max is only
+//   raised when it grows by > 2^8 (lazy rescale: P <= 256 fits fp16), in which case the warp rescales its O rows
+//   in place (tcgen05.ld/st); the row sum l is a register.
 constexpr int F2_THREADS = 320;
 constexpr int F2_KV_STAGES = 3;
-constexpr int F2_SMEM = 2 * TILE /*Q0,Q1*/ + F2_KV_STAGES * 2 * TILE + 2 * 2 * TILE /*P0,P1*/ + 4096 /*ones*/ + 1024 + 256;
+constexpr int F2_SMEM = 2 * TILE /*Q0,Q1*/ + F2_KV_STAGES * 2 * TILE + 2 * TILE /*output staging*/ + 1024 + 256;
 constexpr float F2_LAZY = 8.0f;
 
 template <int NSEG>
@@ -265,16 +266,16 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                  // 2 tiles
   uint8_t* sKV = smem + 2 * TILE;                      // stage s: K at + s*2*TILE, V at + TILE
-  uint8_t* sP = sKV + F2_KV_STAGES * 2 * TILE;         // tile i: 2 atoms (32 KB) at + i*2*TILE
-  uint8_t* sOnes = sP + 4 * TILE;                      // 4 KB of fp16 1.0
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + 4096);
+  uint8_t* sOut = sKV + F2_KV_STAGES * 2 * TILE;       // tile i: 16 KB output staging at + i*TILE
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + 2 * TILE);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;                        // [3]
   uint64_t* kv_empty = bars + 4;                       // [3]
   uint64_t* s_full = bars + 7;                         // [2]
   uint64_t* p_ready = bars + 9;                        // [2]
   uint64_t* o_done = bars + 11;                        // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* s_free = bars + 13;                        // [2]  S tile copied to registers -> TMEM tile reusable
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 256, head = blockIdx.y, f = blockIdx.z;
@@ -282,17 +283,17 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < F2_KV_STAGES; i++) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); mbar_init(&o_done[i], 1); }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); mbar_init(&o_done[i], 1); mbar_init(&s_free[i], 128);
+    }
     fence_mbar_init();
   }
-  for (int i = threadIdx.x; i < 4096 / 4; i += F2_THREADS) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3C003C00u;
-  fence_proxy_async_smem();
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: S0 [0,128) S1 [128,256) | O0 [256,320) l0 [320,336) | O1 [384,448) l1 [448,464)
+  // TMEM columns: S0 [0,128) S1 [128,256) | O0 [256,320) O1 [320,384) | P0 [384,448) P1 [448,512) (fp16 pairs)
 
   int nblk[2];
   nblk[0] = (p.len[0] + 127) >> 7;
@@ -324,8 +325,6 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_f16(128, 128, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_f16(128, 64, 0, 1);     // V MN-major
-      constexpr uint32_t idesc_l = umma_idesc_f16(128, 16, 0, 0);     // ones, K-major
-      const uint64_t d_ones = umma_desc_sw128(smem_u32(sOnes), 16, 1024);
       mbar_wait(q_full, 0);
       auto issue_s = [&](int i, int it) {
         const int s = it % F2_KV_STAGES;
@@ -343,26 +342,27 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       for (int it = 0; it < nb; it++) {
         if (NSEG > 1 && it == nblk[0]) seg_first = nblk[0];
         const int s = it % F2_KV_STAGES;
-        const bool next = it + 1 < nb;
-        if (next) {
+        // S of the next block as soon as the softmax groups hold the current S in registers: the tensor core works
+        // on S(it+1) while the groups exponentiate block it
+        if (it + 1 < nb) {
           mbar_wait(&kv_full[(it + 1) % F2_KV_STAGES], ((it + 1) / F2_KV_STAGES) & 1);
-          tc_fence_after();
+          for (int i = 0; i < 2; i++) {
+            mbar_wait(&s_free[i], it & 1);
+            tc_fence_after();
+            issue_s(i, it + 1);
+          }
         }
         const uint64_t dv = umma_desc_sw128(smem_u32(sKV + s * 2 * TILE + TILE), 1024, 1024);
         for (int i = 0; i < 2; i++) {
           mbar_wait(&p_ready[i], it & 1);
           tc_fence_after();
-          const uint64_t dp = umma_desc_sw128(smem_u32(sP + i * 2 * TILE), 16, 1024);
-          const uint32_t tO = tmem_base + 256 + i * 128;
+          const uint32_t tO = tmem_base + 256 + i * 64;
+          const uint32_t tP = tmem_base + 384 + i * 64;
           const uint32_t acc0 = it != seg_first ? 1u : 0u;
 #pragma unroll
-          for (int k = 0; k < 8; k++) {
-            const uint64_t dpk = dp + (uint64_t)((k >> 2) * (TILE >> 4) + (k & 3) * 2);
-            umma_f16(tO, dpk, dv + (uint64_t)(k * (2048 >> 4)), idesc_o, (k != 0) ? 1u : acc0);
-            umma_f16(tO + 64, dpk, d_ones, idesc_l, (k != 0) ? 1u : acc0);
-          }
+          for (int k = 0; k < 8; k++)     // K = 16 kv tokens = 8 TMEM columns of P, 16 smem rows of V
+            umma_f16_ts(tO, tP + k * 8, dv + (uint64_t)(k * (2048 >> 4)), idesc_o, (k != 0) ? 1u : acc0);
           umma_commit(&o_done[i]);
-          if (next) issue_s(i, it + 1);
         }
         umma_commit(&kv_empty[s]);
       }
@@ -374,8 +374,9 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const int row = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t tS = tmem_base + grp * 128 + lane_off;
-    const uint32_t tO = tmem_base + 256 + grp * 128 + lane_off;
-    uint8_t* myP = sP + grp * 2 * TILE;
+    const uint32_t tO = tmem_base + 256 + grp * 64 + lane_off;
+    const uint32_t tP = tmem_base + 384 + grp * 64 + lane_off;
+    uint8_t* myOut = sOut + grp * TILE;
     uint32_t acc[NSEG > 1 ? 32 : 1];
     if (NSEG > 1) {
 #pragma unroll
@@ -385,45 +386,70 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     int it = 0;
 #pragma unroll 1
     for (int sg = 0; sg < NSEG; sg++) {
-      float m_used = -INFINITY;
+      float m_used = -INFINITY, l_run = 0.f;
 #pragma unroll 1
       for (int j = 0; j < nblk[sg]; j++, it++) {
         const int valid = p.len[sg] - j * 128;
         mbar_wait(&s_full[grp], it & 1);
         __syncwarp();
         tc_fence_after();
-        // ---- pass 1: row max (scaled to the log2 domain)
-        float mx = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < 4; c++) {
-          uint32_t v[32];
-          tmem_ld32(tS + c * 32, v);
-          tmem_ld_wait();
-          if (valid >= 128) {
+        // ---- the whole 128-column S row goes to registers in one TMEM round trip; the TMEM tile is then free
+        uint32_t sr[4][32];
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-          } else {
+        for (int c = 0; c < 4; c++) tmem_ld32(tS + c * 32, sr[c]);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&s_free[grp]);
+        float mx = -INFINITY;
+        if (valid >= 128) {
+#pragma unroll
+          for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; c++)
 #pragma unroll
             for (int i = 0; i < 32; i++)
-              if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-          }
+              if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(sr[c][i]));
         }
         mx *= p.scale_log2;
+        const bool grow = (j > 0) && (mx > m_used + F2_LAZY);
+        const float m_old = m_used;
+        if (j == 0 || grow) m_used = mx;
+        // ---- P = 2^(s*scale - m_used): fp32 exp2, row sum in a register, packed to fp16 in place over the S registers
+        float lsum = 0.f;
+        if (valid >= 128) {
+#pragma unroll
+          for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c][i]), p.scale_log2, -m_used));
+              const float p1 = ex2_approx(fmaf(__uint_as_float(sr[c][i + 1]), p.scale_log2, -m_used));
+              lsum += p0 + p1;
+              sr[c][i >> 1] = pack_half2(p0, p1);
+            }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float p0 = (c * 32 + i < valid) ? ex2_approx(fmaf(__uint_as_float(sr[c][i]), p.scale_log2, -m_used)) : 0.f;
+              const float p1 = (c * 32 + i + 1 < valid) ? ex2_approx(fmaf(__uint_as_float(sr[c][i + 1]), p.scale_log2, -m_used)) : 0.f;
+              lsum += p0 + p1;
+              sr[c][i >> 1] = pack_half2(p0, p1);
+            }
+        }
         // the previous P V of this tile must have retired before P (and possibly O) are overwritten
         if (j > 0) {
           mbar_wait(&o_done[grp], (it - 1) & 1);
           __syncwarp();
           tc_fence_after();
-        }
-        if (j == 0) {
-          m_used = mx;
-        } else {
-          const bool grow = mx > m_used + F2_LAZY;
           if (__any_sync(0xffffffffu, grow)) {       // warp-uniform: tcgen05.ld/st are warp-collective
-            const float m_new = grow ? mx : m_used;
-            const float factor = exp2f(m_used - m_new);
+            const float factor = ex2_approx(m_old - m_used);   // 1 for the lanes whose max did not move
+            l_run *= factor;
 #pragma unroll 1
-            for (int c = 0; c < 3; c++) {            // 64 O columns + the l columns
+            for (int c = 0; c < 2; c++) {
               uint32_t v[32];
               tmem_ld32(tO + c * 32, v);
               tmem_ld_wait();
@@ -431,39 +457,20 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
               for (int i = 0; i < 32; i++) v[i] = __float_as_uint(__uint_as_float(v[i]) * factor);
               tmem_st32(tO + c * 32, v);
             }
-            tmem_st_wait();
-            m_used = m_new;
           }
         }
-        // ---- pass 2: P = 2^(s*scale - m_used) as fp16, into the swizzled K-major smem operand
-#pragma unroll 1
-        for (int c = 0; c < 4; c++) {
-          uint32_t v[32];
-          tmem_ld32(tS + c * 32, v);
-          tmem_ld_wait();
-          uint32_t pk[16];
-          if (valid >= 128) {
+        l_run += lsum;
+        // P -> TMEM: 128 fp16 = 64 columns; chunk c of the S row became 16 packed words sr[c][0..15]
+        {
+          uint32_t w[32];
 #pragma unroll
-            for (int i = 0; i < 32; i += 2)
-              pk[i >> 1] = ex2_f16x2(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_used),
-                                     fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_used));
-          } else {
+          for (int i = 0; i < 16; i++) { w[i] = sr[0][i]; w[16 + i] = sr[1][i]; }
+          tmem_st32(tP, w);
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float a = (c * 32 + i < valid) ? fmaf(__uint_as_float(v[i]), p.scale_log2, -m_used) : -INFINITY;
-              const float b = (c * 32 + i + 1 < valid) ? fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_used) : -INFINITY;
-              pk[i >> 1] = ex2_f16x2(a, b);
-            }
-          }
-          uint8_t* atom = myP + (c >> 1) * TILE + row * 128;
-#pragma unroll
-          for (int jj = 0; jj < 4; jj++) {
-            const int chunk = (c & 1) * 4 + jj;
-            *reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) =
-                make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
-          }
+          for (int i = 0; i < 16; i++) { w[i] = sr[2][i]; w[16 + i] = sr[3][i]; }
+          tmem_st32(tP + 32, w);
         }
-        fence_proxy_async_smem();
+        tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_ready[grp]);
       }
@@ -471,13 +478,7 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       mbar_wait(&o_done[grp], (it - 1) & 1);
       __syncwarp();
       tc_fence_after();
-      float inv;
-      {
-        uint32_t v[32];
-        tmem_ld32(tO + 64, v);
-        tmem_ld_wait();
-        inv = 1.f / __uint_as_float(v[0]);
-      }
+      const float inv = 1.f / l_run;
 #pragma unroll
       for (int c = 0; c < 2; c++) {
         uint32_t v[32];
@@ -495,8 +496,8 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       }
       tc_fence_before();
     }
-    // ---- epilogue: this group's P buffer is free (its last P V has retired)
-    uint8_t* stg = myP + row * 128;
+    // ---- epilogue: fp16 tile -> swizzled staging smem -> TMA store
+    uint8_t* stg = myOut + row * 128;
 #pragma unroll
     for (int jj = 0; jj < 8; jj++) {
       uint4 val;
@@ -509,7 +510,7 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
     else asm volatile("bar.sync 2, 128;" ::: "memory");
     if (q == 2 && lane == 0) {       // warps 2 and 6 (first warp of each group)
-      tma_store_5d(&tmO, myP, head * 64, q0 + grp * 128, f, 0, 0);
+      tma_store_5d(&tmO, myOut, head * 64, q0 + grp * 128, f, 0, 0);
       tma_store_commit();
       tma_store_wait_read0();
     }
