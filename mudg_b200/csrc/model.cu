@@ -1,6 +1,7 @@
 #include "model.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace mudg {
@@ -138,6 +139,13 @@ Model::Model(int device, const MudgUNetConfig& u, const MudgVaeConfig& v) : ucfg
   build_plan();
 }
 Model::~Model() {
+  drop_graphs();
+  if (own_stream_) cudaStreamDestroy(own_stream_);
+  for (auto& kv : graphs_) {
+    cudaFree(kv.second.in_x);
+    cudaFree(kv.second.in_idx);
+    cudaFree(kv.second.out);
+  }
   for (auto& kv : kv_) {
     cudaFree(kv.second.text);
     cudaFree(kv.second.img);
@@ -289,6 +297,7 @@ void Model::finalize(int which, cudaStream_t st) {
 void Model::ensure_arena(size_t bytes) {
   if (arena_.capacity() < bytes) {
     MUDG_CUDA(cudaDeviceSynchronize());
+    drop_graphs();                     // the slab moves: pointers captured in CUDA graphs are stale
     arena_.reserve(bytes + (bytes >> 4));
   }
 }
@@ -666,6 +675,7 @@ void Model::set_context(const void* ctx, int dtype, int N, int L, int T, cudaStr
   MUDG_REQUIRE(L > tl, "context needs image tokens after the %d text tokens (L=%d)", tl, L);
   const int Limg = L - tl;
   const bool per_frame = (L == tl + 16 * T);     // openaimodel3d.py:581 hard-coded split
+  bool realloc = (N != ctx_N_ || L != ctx_L_ || T != ctx_T_);
   __half *text = nullptr, *img = nullptr;
   MUDG_CUDA(cudaMalloc(&text, sizeof(__half) * (size_t)N * tl * D));
   MUDG_CUDA(cudaMalloc(&img, sizeof(__half) * (size_t)N * Limg * D));
@@ -676,8 +686,8 @@ void Model::set_context(const void* ctx, int dtype, int N, int L, int T, cudaStr
     const int C = l.ch;
     KvCache& kc = kv_[l.prefix];
     const size_t tb = sizeof(__half) * (size_t)N * tl * 2 * C, ib = sizeof(__half) * (size_t)N * Limg * 2 * C;
-    if (kc.text_bytes < tb) { cudaFree(kc.text); MUDG_CUDA(cudaMalloc(&kc.text, tb)); kc.text_bytes = tb; }
-    if (kc.img_bytes < ib) { cudaFree(kc.img); MUDG_CUDA(cudaMalloc(&kc.img, ib)); kc.img_bytes = ib; }
+    if (kc.text_bytes < tb) { cudaFree(kc.text); MUDG_CUDA(cudaMalloc(&kc.text, tb)); kc.text_bytes = tb; realloc = true; }
+    if (kc.img_bytes < ib) { cudaFree(kc.img); MUDG_CUDA(cudaMalloc(&kc.img, ib)); kc.img_bytes = ib; realloc = true; }
     const std::string tbp = l.prefix + ".transformer_blocks.0.attn2.";
     for (int k = 0; k < 2; k++) {
       const Weight& w = unet_w.W(tbp + (k ? "kv_img.weight" : "kv_text.weight"));
@@ -696,6 +706,7 @@ void Model::set_context(const void* ctx, int dtype, int N, int L, int T, cudaStr
   cudaFree(text);
   cudaFree(img);
   ctx_N_ = N; ctx_L_ = L; ctx_T_ = T; ctx_Limg_ = Limg; ctx_per_frame_ = per_frame;
+  ctx_version_ += realloc ? 1 : 0;     // K/V buffers moved (or the token layout changed): graphs must be re-captured
 }
 
 // ================================================================ entry points
@@ -712,6 +723,8 @@ size_t Model::plan_unet(int N, int T, int h, int w) {
   return need;
 }
 
+// The ~1300 launches of one forward are captured once per shape into a CUDA graph (inputs/outputs go through fixed
+// staging buffers so the captured pointers stay valid); later steps replay it.  MUDG_GRAPH=0 disables the capture.
 void Model::unet_forward(const void* x, const int64_t* t, const int64_t* label, const int64_t* fs, int N, int T, int h, int w,
                          void* out, cudaStream_t st) {
   MUDG_REQUIRE(unet_ready_, "weights not finalized");
@@ -720,7 +733,71 @@ void Model::unet_forward(const void* x, const int64_t* t, const int64_t* label, 
   if (it == unet_plans_.end()) it = unet_plans_.emplace(key, plan_unet(N, T, h, w)).first;
   ensure_arena(it->second);
   st_ = st;
-  unet_body(x, t, label, fs, N, T, h, w, out);
+  static const bool graphs_on = [] {
+    const char* e = getenv("MUDG_GRAPH");
+    return !(e && e[0] == '0');
+  }();
+  if (!graphs_on || gemm_profile_active()) {
+    unet_body(x, t, label, fs, N, T, h, w, out);
+    return;
+  }
+  // Capture is illegal on the legacy default stream (what PyTorch uses unless told otherwise): run on an own
+  // *blocking* stream there, which the legacy stream implicitly orders against on both sides.
+  if (st == nullptr || st == cudaStreamLegacy) {
+    if (!own_stream_) MUDG_CUDA(cudaStreamCreate(&own_stream_));
+    st = own_stream_;
+    st_ = st;
+  }
+  GraphSlot& g = graphs_[key];
+  const size_t xin = sizeof(float) * (size_t)N * ucfg_.in_channels * T * h * w;
+  const size_t xout = sizeof(__half) * (size_t)N * ucfg_.out_channels * T * h * w;
+  if (g.ctx_version != ctx_version_) {                     // set_context may have re-allocated the K/V caches
+    if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    g.runs = 0;
+    g.ctx_version = ctx_version_;
+  }
+  if (!g.in_x) {
+    MUDG_CUDA(cudaMalloc(&g.in_x, xin));
+    MUDG_CUDA(cudaMalloc(&g.in_idx, sizeof(int64_t) * 3 * N));
+    MUDG_CUDA(cudaMalloc(&g.out, xout));
+  }
+  MUDG_CUDA(cudaMemcpyAsync(g.in_x, x, xin, cudaMemcpyDeviceToDevice, st));
+  MUDG_CUDA(cudaMemcpyAsync(g.in_idx, t, sizeof(int64_t) * N, cudaMemcpyDeviceToDevice, st));
+  MUDG_CUDA(cudaMemcpyAsync(g.in_idx + N, label, sizeof(int64_t) * N, cudaMemcpyDeviceToDevice, st));
+  MUDG_CUDA(cudaMemcpyAsync(g.in_idx + 2 * N, fs, sizeof(int64_t) * N, cudaMemcpyDeviceToDevice, st));
+  if (g.exec) {
+    MUDG_CUDA(cudaGraphLaunch(g.exec, st));
+    launches += g.launches;
+  } else if (g.runs == 0) {
+    // first call: eager (sets kernel attributes, fills the tensor-map cache)
+    const int64_t l0 = launches;
+    unet_body(g.in_x, g.in_idx, g.in_idx + N, g.in_idx + 2 * N, N, T, h, w, g.out);
+    g.launches = launches - l0;
+  } else {
+    cudaGraph_t graph = nullptr;
+    MUDG_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    try {
+      unet_body(g.in_x, g.in_idx, g.in_idx + N, g.in_idx + 2 * N, N, T, h, w, g.out);
+    } catch (...) {
+      cudaStreamEndCapture(st, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    MUDG_CUDA(cudaStreamEndCapture(st, &graph));
+    MUDG_CUDA(cudaGraphInstantiate(&g.exec, graph, 0));
+    cudaGraphDestroy(graph);
+    MUDG_CUDA(cudaGraphLaunch(g.exec, st));
+  }
+  g.runs++;
+  MUDG_CUDA(cudaMemcpyAsync(out, g.out, xout, cudaMemcpyDeviceToDevice, st));
+}
+
+void Model::drop_graphs() {
+  for (auto& kv : graphs_) {
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    kv.second.exec = nullptr;
+    kv.second.runs = 0;
+  }
 }
 
 // ================================================================ VAE decoder (ae_modules.py:466-578)

@@ -100,6 +100,19 @@ class Model {
   std::vector<float*> emb_out_;   // per ResBlock [N][Cout]
   int T_real_ = 1;                // frames per sample of the current forward
   int N_ = 1;
+  struct GraphSlot {
+    cudaGraphExec_t exec = nullptr;
+    float* in_x = nullptr;
+    int64_t* in_idx = nullptr;
+    __half* out = nullptr;
+    int runs = 0;
+    int64_t launches = 0;
+    int64_t ctx_version = -1;
+  };
+  std::map<std::array<int, 4>, GraphSlot> graphs_;
+  int64_t ctx_version_ = 0;
+  cudaStream_t own_stream_ = nullptr;
+  void drop_graphs();
   std::map<std::array<int, 4>, size_t> unet_plans_;
   std::map<std::array<int, 2>, size_t> vae_plans_;
 

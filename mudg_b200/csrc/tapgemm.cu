@@ -800,6 +800,8 @@ struct GemmProfiler {
 } g_prof;
 }  // namespace
 
+bool gemm_profile_active() { return g_prof.on; }
+
 void gemm_profile_enable(bool on) {
   g_prof.on = on;
   g_prof.used = 0;
