@@ -254,21 +254,29 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 //                             prefetched from global one 32-column slice ahead; 64-column chunks go through a 16 KB
 //                             swizzled staging tile and are written with TMA (clips partial tiles).
 // TMEM alloc, barrier init and descriptor prefetch are paid once per CTA instead of once per tile.
-constexpr int G2_STAGES = 3;
+// SUB = M sub-tiles (128 pixels each) a CTA computes per tile against ONE shared weight tile:
+//   SUB 1: 192 threads, 3 stages x 32 KB, 2 CTAs/SM                (small problems, short K)
+//   SUB 2: 320 threads, 4 stages x 48 KB, 1 CTA/SM, 8 epilogue warps: 25 % less L2->SM operand traffic per MAC
 constexpr int G2_BN_MAX = 128;
-constexpr int G2_A_BYTES = BM * BK * 2;                 // 16 KB
+constexpr int G2_A_BYTES = BM * BK * 2;                 // 16 KB per sub-tile
 constexpr int G2_B_BYTES = G2_BN_MAX * BK * 2;          // 16 KB
-constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES; // 32 KB
-constexpr int G2_STG_BYTES = 16384;
-// 2 CTAs/SM: 2 * (G2_SMEM + 1 KB reserved) must fit in 228 KB -> no alignment slack; the base is declared 1024-aligned
-constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + G2_STG_BYTES + 128;
-static_assert(2 * (G2_SMEM + 1024) <= 233472, "two CTAs of the persistent GEMM must fit one SM");
-constexpr int G2_THREADS = 192;
+template <int SUB> struct G2Cfg {
+  static constexpr int STAGES = SUB == 1 ? 3 : 4;
+  static constexpr int STAGE_BYTES = SUB * G2_A_BYTES + G2_B_BYTES;
+  static constexpr int STG_BYTES = SUB * 16384;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + STG_BYTES + 128;   // no alignment slack: base declared 1024-aligned
+  static constexpr int THREADS = 64 + SUB * 128;
+  static constexpr int TMEM_COLS = SUB * 256;            // 2 accumulator buffers x SUB x 128 columns
+  static constexpr int CTAS_PER_SM = SUB == 1 ? 2 : 1;
+};
+static_assert(2 * (G2Cfg<1>::SMEM + 1024) <= 233472, "two CTAs of the SUB=1 persistent GEMM must fit one SM");
+static_assert(G2Cfg<2>::SMEM + 1024 <= 233472, "SUB=2 persistent GEMM must fit one SM");
 
 struct G2Params {
   TcParams b;            // shared fields (taps, bias, ...)
   int nt;                // number of N tiles (all 128 wide except possibly the last)
-  int total_tiles;
+  int total_tiles;       // N tiles x ceil(M tiles / SUB)
+  int m_tiles;
   int tiles_b;
   int dimW, dimH, dimB;  // extents for the residual bounds check
   const __half* R;       // residual (read straight from global / L2)
@@ -290,10 +298,13 @@ __device__ __forceinline__ float gelu_fast(float x) { return 0.5f * x * (1.f + e
 struct G2Tile {
   int n0, bn, w0, h0, t0, b0;
 };
-__device__ __forceinline__ G2Tile g2_decode(const G2Params& p, int tile) {
+// tile = n-tile + nt * m-super-tile; sub-tile `sub` of a super tile is M tile (msuper*SUB + sub).  An M tile index past
+// the end decodes to a batch coordinate outside the tensor: its loads are zero-filled and its stores clipped away.
+template <int SUB>
+__device__ __forceinline__ G2Tile g2_decode(const G2Params& p, int tile, int sub) {
   G2Tile t;
   const int nt_i = tile % p.nt;
-  int m = tile / p.nt;
+  int m = (tile / p.nt) * SUB + sub;
   t.n0 = nt_i * G2_BN_MAX;
   t.bn = min(G2_BN_MAX, p.b.N - t.n0);
   const int tw = m % p.b.tiles_w; m /= p.b.tiles_w;
@@ -304,16 +315,19 @@ __device__ __forceinline__ G2Tile g2_decode(const G2Params& p, int tile) {
   return t;
 }
 
-__global__ void __launch_bounds__(G2_THREADS, 2)
+template <int SUB>
+__global__ void __launch_bounds__(G2Cfg<SUB>::THREADS, G2Cfg<SUB>::CTAS_PER_SM)
 tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmD, const G2Params p) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   uint8_t* smem = smem_dyn;
   if ((smem_u32(smem) & 1023u) != 0) __trap();          // SWIZZLE_128B tiles need a 1024 B aligned base
-  uint8_t* stg = smem + G2_STAGES * G2_STAGE_BYTES;     // 16 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + G2_STG_BYTES);
-  uint64_t* full = bars;                        // [3]
-  uint64_t* empty = bars + G2_STAGES;           // [3]
+  using Cfg = G2Cfg<SUB>;
+  constexpr int G2_STAGES = Cfg::STAGES, G2_STAGE_BYTES = Cfg::STAGE_BYTES;
+  uint8_t* stg_all = smem + G2_STAGES * G2_STAGE_BYTES;  // 16 KB per epilogue group
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_all + Cfg::STG_BYTES);
+  uint64_t* full = bars;                        // [STAGES]
+  uint64_t* empty = bars + G2_STAGES;           // [STAGES]
   uint64_t* tmem_full = bars + 2 * G2_STAGES;   // [2]
   uint64_t* tmem_empty = bars + 2 * G2_STAGES + 2;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G2_STAGES + 4);
@@ -321,7 +335,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < G2_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
+    for (int i = 0; i < 2; i++) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], SUB * 128); }
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -329,7 +343,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmD);
   }
-  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -340,17 +354,21 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const G2Tile tl = g2_decode(p, tile);
+        G2Tile tl[SUB];
+#pragma unroll
+        for (int u = 0; u < SUB; u++) tl[u] = g2_decode<SUB>(p, tile, u);
         for (int k = 0; k < ktotal; k++, it++) {
           const int s = it % G2_STAGES;
           mbar_wait(&empty[s], ((it / G2_STAGES) & 1) ^ 1);
           mbar_expect_tx(&full[s], G2_STAGE_BYTES);
           const int tap = k / p.b.kchunks, kc = k - tap * p.b.kchunks;
           uint8_t* a_s = smem + s * G2_STAGE_BYTES;
-          tma_load_5d(a_s, &tmA, &full[s], kc * BK, tl.w0 + p.b.taps[tap][0], tl.h0 + p.b.taps[tap][1],
-                      tl.t0 + p.b.taps[tap][2], tl.b0);
-          // rows past N (last tile of N = 64 mod 128) are zero-filled and never multiplied (MMA N = tl.bn)
-          tma_load_5d(a_s + G2_A_BYTES, &tmB, &full[s], tap * p.b.cin + kc * BK, tl.n0, 0, 0, 0);
+#pragma unroll
+          for (int u = 0; u < SUB; u++)
+            tma_load_5d(a_s + u * G2_A_BYTES, &tmA, &full[s], kc * BK, tl[u].w0 + p.b.taps[tap][0],
+                        tl[u].h0 + p.b.taps[tap][1], tl[u].t0 + p.b.taps[tap][2], tl[u].b0);
+          // rows past N (last tile of N = 64 mod 128) are zero-filled and never multiplied (MMA N = bn)
+          tma_load_5d(a_s + SUB * G2_A_BYTES, &tmB, &full[s], tap * p.b.cin + kc * BK, tl[0].n0, 0, 0, 0);
         }
       }
     }
@@ -359,22 +377,25 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (lane == 0) {
       uint32_t it = 0, lt = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, lt++) {
-        const G2Tile tl = g2_decode(p, tile);
+        const G2Tile tl = g2_decode<SUB>(p, tile, 0);
         const uint32_t acc = lt & 1;
         mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t idesc = umma_idesc_f16(BM, tl.bn, 0, 0);
-        const uint32_t d_tmem = tmem_base + acc * G2_BN_MAX;
+        const uint32_t d_tmem = tmem_base + acc * (SUB * G2_BN_MAX);
         for (int k = 0; k < ktotal; k++, it++) {
           const int s = it % G2_STAGES;
           mbar_wait(&full[s], (it / G2_STAGES) & 1);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * G2_STAGE_BYTES);
-          const uint64_t da = umma_desc_sw128(a_addr, 16, 1024);
-          const uint64_t db = umma_desc_sw128(a_addr + G2_A_BYTES, 16, 1024);
+          const uint64_t db = umma_desc_sw128(a_addr + SUB * G2_A_BYTES, 16, 1024);
 #pragma unroll
-          for (int kk = 0; kk < BK / 16; kk++)
-            umma_f16(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+          for (int u = 0; u < SUB; u++) {
+            const uint64_t da = umma_desc_sw128(a_addr + u * G2_A_BYTES, 16, 1024);
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; kk++)
+              umma_f16(d_tmem + u * G2_BN_MAX, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+          }
           umma_commit(&empty[s]);
         }
         umma_commit(&tmem_full[acc]);
@@ -382,11 +403,17 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     __syncwarp();
   } else {
+    const int grp = (warp - 2) >> 2;        // which M sub-tile this epilogue group drains
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const bool issuer = (warp == 2 && lane == 0);
+    const bool issuer = (((warp - 2) & 3) == 0 && lane == 0);
+    uint8_t* stg = stg_all + grp * 16384;
     uint8_t* srow = stg + row * 128;
+    auto group_sync = [&]() {               // 128 threads of this group only
+      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+    };
     // row -> (iw, ih, it, ib) inside the pixel box
     int r = row;
     const int iw = r % p.b.bw; r /= p.b.bw;
@@ -395,9 +422,9 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int ib_ = r / p.b.bt;
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, lt++) {
-      const G2Tile tl = g2_decode(p, tile);
+      const G2Tile tl = g2_decode<SUB>(p, tile, grp);
       const uint32_t acc = lt & 1;
-      const uint32_t t_row = tmem_base + acc * G2_BN_MAX + lane_off;
+      const uint32_t t_row = tmem_base + acc * (SUB * G2_BN_MAX) + grp * G2_BN_MAX + lane_off;
       const int pw = tl.w0 + iw, ph = tl.h0 + ih, pt = tl.t0 + it_, pb = tl.b0 + ib_;
       const bool row_ok = pw < p.dimW && ph < p.dimH && pt < p.b.dimT && pb < p.dimB;
       const int64_t pix = (((int64_t)pb * p.b.dimT + pt) * p.dimH + ph) * p.dimW + pw;
@@ -408,7 +435,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // weight rows interleaved 64 value / 64 gate: TMEM columns [0,64) value, [64,128) gate -> 64 output columns
         if (issuer) tma_store_wait_read0();
         __syncwarp();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        group_sync();
 #pragma unroll 1
         for (int c = 0; c < 2; c++) {
           uint32_t v[32], g[32];
@@ -439,7 +466,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
         }
         fence_proxy_async_smem();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        group_sync();
         if (issuer) {
           tma_store_5d(&tmD, stg, tl.n0 / 2, tl.w0, tl.h0, tl.t0, tl.b0);
           tma_store_commit();
@@ -478,7 +505,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if ((hf & 1) == 0) {                 // staging tile must be free: previous TMA store has read it
           if (issuer) tma_store_wait_read0();
           __syncwarp();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          group_sync();
         }
         tmem_ld_wait();
         if (hf == nh - 1) {                  // all TMEM reads of this accumulator are done
@@ -525,7 +552,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                          pack_half2(f[8 * j + 4], f[8 * j + 5]), pack_half2(f[8 * j + 6], f[8 * j + 7]));
         if (hf & 1) {                        // a 64-column chunk is complete
           fence_proxy_async_smem();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          group_sync();
           if (issuer) {
             tma_store_5d(&tmD, stg, tl.n0 + (hf >> 1) * 64, tl.w0, tl.h0, tl.t0, tl.b0);
             tma_store_commit();
@@ -542,7 +569,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc<256>(tmem_base);
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -734,8 +761,18 @@ void tapgemm_tc2(const TapGemm& g, cudaStream_t st) {
   p.tiles_b = (g.B + p.b.bb - 1) / p.b.bb;
   p.nt = (g.N + G2_BN_MAX - 1) / G2_BN_MAX;
   p.b.tiles_n = p.nt;
-  const int64_t total = (int64_t)p.nt * p.b.tiles_w * p.b.tiles_h * p.b.tiles_t * p.tiles_b;
-  MUDG_REQUIRE(total > 0 && total < (int64_t(1) << 31), "grid too large");
+  const int64_t m_tiles = (int64_t)p.b.tiles_w * p.b.tiles_h * p.b.tiles_t * p.tiles_b;
+  MUDG_REQUIRE(m_tiles * p.nt < (int64_t(1) << 30), "grid too large");
+  p.m_tiles = (int)m_tiles;
+  // 256-row super tiles when there is enough work to fill the machine several times over (MUDG_GEMM_SUB=1|2 forces)
+  static const int force_sub = [] {
+    const char* e = getenv("MUDG_GEMM_SUB");
+    return e ? atoi(e) : 0;
+  }();
+  const int ktot_steps = g.ntaps * ((g.Cin + BK - 1) / BK);
+  int sub = (m_tiles * p.nt >= 8 * (int64_t)sm_count() && ktot_steps >= 8) ? 2 : 1;
+  if (force_sub == 1 || force_sub == 2) sub = force_sub;
+  const int64_t total = (int64_t)p.nt * ((m_tiles + sub - 1) / sub);
   p.total_tiles = (int)total;
   p.dimW = g.W; p.dimH = g.H; p.dimB = g.B;
   p.R = g.R;
@@ -755,11 +792,17 @@ void tapgemm_tc2(const TapGemm& g, cudaStream_t st) {
   const CUtensorMap* md = get_tmap(g.D, ddims, dstr, abox);
   static bool attr_set = false;
   if (!attr_set) {
-    MUDG_CUDA(cudaFuncSetAttribute(tapgemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
+    MUDG_CUDA(cudaFuncSetAttribute(tapgemm_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<1>::SMEM));
+    MUDG_CUDA(cudaFuncSetAttribute(tapgemm_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<2>::SMEM));
     attr_set = true;
   }
-  const int grid = (int)std::min<int64_t>(total, 2 * sm_count());
-  tapgemm_tc2_kernel<<<grid, G2_THREADS, G2_SMEM, st>>>(*ma, *mb, *md, p);
+  if (sub == 1) {
+    const int grid = (int)std::min<int64_t>(total, 2 * sm_count());
+    tapgemm_tc2_kernel<1><<<grid, G2Cfg<1>::THREADS, G2Cfg<1>::SMEM, st>>>(*ma, *mb, *md, p);
+  } else {
+    const int grid = (int)std::min<int64_t>(total, sm_count());
+    tapgemm_tc2_kernel<2><<<grid, G2Cfg<2>::THREADS, G2Cfg<2>::SMEM, st>>>(*ma, *mb, *md, p);
+  }
   MUDG_CUDA(cudaGetLastError());
 }
 
