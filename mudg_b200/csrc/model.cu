@@ -248,6 +248,7 @@ void Model::finalize(int which, cudaStream_t st) {
       if (lvl != 0) vae_w.W("decoder.up." + std::to_string(lvl) + ".upsample.conv.weight");
     }
     vae_w.V("decoder.norm_out.weight"); vae_w.W("decoder.conv_out.weight");
+    vae_w.pad_rows("decoder.conv_out.weight", "decoder.conv_out.bias", 64, st);
     vae_ready_ = true;
     return;
   }
@@ -896,19 +897,20 @@ void Model::vae_body(const void* z, int h, int w, void* out) {
   }
   Act o = group_norm(cur, "decoder.norm_out", 1e-6f, true, false);
   release(cur);
+  // 3 output channels: tensor-core path with the weight zero-padded to 64 rows, then keep 3 columns as NCHW
+  Act y64 = alloc(1, 1, o.H, o.W, 64);
   if (live()) {
-    const Weight& wt = ws_->W("decoder.conv_out.weight");
-    const int H = o.H, W = o.W;
-    TapGemmGeneric g;
-    g.A = o.p; g.B = 1; g.T = 1; g.H = H; g.W = W; g.Cin = o.C;
-    g.a_sc = 1; g.a_sw = o.C; g.a_sh = (int64_t)W * o.C;
+    const Weight& wt = ws_->W("decoder.conv_out.weight.pad");
+    TapGemm g;
+    g.A = o.p; g.B = 1; g.T = 1; g.H = o.H; g.W = o.W; g.Cin = o.C;
     g.ntaps = 9; set_taps_3x3(g.taps);
-    g.Wt = wt.w; g.CinW = wt.Ipad; g.N = wt.O;
-    g.D = out; g.d_sw = 1; g.d_sh = W; g.d_sn = (int64_t)H * W;
-    g.bias = ws_->V("decoder.conv_out.bias").p;
-    tapgemm_generic(g, st_);
-    launches++;
+    g.Wt = wt.w; g.N = wt.O; g.D = y64.p;
+    g.bias = ws_->V("decoder.conv_out.bias.pad").p;
+    tapgemm(g, st_);
+    from_channels_last(y64.p, static_cast<__half*>(out), 1, vcfg_.out_ch, (int64_t)o.H * o.W, 64, st_);
+    launches += 2;
   }
+  release(y64);
   release(o);
 }
 

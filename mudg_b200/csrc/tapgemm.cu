@@ -480,6 +480,17 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (sample >= p.b.nb2) sample = p.b.nb2 - 1;
       }
       const uint4* rp = (p.R != nullptr && row_ok) ? reinterpret_cast<const uint4*>(p.R + pix * p.b.n_out + tl.n0) : nullptr;
+      if (p.R != nullptr && tile + (int)gridDim.x < p.total_tiles) {
+        // residual rows of this CTA's NEXT tile: pull them from HBM into L2 now, a whole mainloop ahead of their use
+        const G2Tile nx = g2_decode<SUB>(p, tile + gridDim.x, grp);
+        const int nw = nx.w0 + iw, nh_ = nx.h0 + ih, nt_ = nx.t0 + it_, nb_ = nx.b0 + ib_;
+        if (nw < p.dimW && nh_ < p.dimH && nt_ < p.b.dimT && nb_ < p.dimB) {
+          const int64_t npix = (((int64_t)nb_ * p.b.dimT + nt_) * p.dimH + nh_) * p.dimW + nw;
+          const __half* np_ = p.R + npix * p.b.n_out + nx.n0;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(np_));
+          if (nx.bn > 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(np_ + 64));
+        }
+      }
       uint4 res_nxt[4];
       if (rp != nullptr) {
 #pragma unroll

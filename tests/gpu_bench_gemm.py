@@ -38,9 +38,12 @@ SHAPES = [
 def main():
     dev = "cuda"
     L = lib()
-    backends = [(2, "v1"), (0, "v2")]
+    backends = [(0, "v2")] if os.environ.get("BENCH_V2_ONLY") else [(2, "v1"), (0, "v2")]
     print(f"{'shape':28s} " + " ".join(f"{n:>8s}us {n:>6s}TF" for _, n in backends))
+    only = sys.argv[1] if len(sys.argv) > 1 else None
     for name, B, T, H, W, Cin, N, mode, res, geglu in SHAPES:
+        if only and only not in name:
+            continue
         ntaps = {0: 1, 1: 9, 2: 3}[mode]
         A = torch.randn(B, T, H, W, Cin, device=dev).half()
         Wt = (torch.randn(N, ntaps * Cin, device=dev) / (ntaps * Cin) ** 0.5).half()
