@@ -82,6 +82,11 @@ MUDG_EXPORT int mudg_ddim_step(const void* x, const void* v_cond, const void* v_
  * out [F, out_ch, 8h, 8w] fp16. */
 MUDG_EXPORT int mudg_vae_decode(MudgCtx* ctx, const void* z, int F, int h, int w, void* out, void* stream);
 
+/* "Next" row: AutoencoderKL.encode (autoencoder.py:97-102) + Encoder.forward (ae_modules.py:432-463), the
+ * get_latent_z step before the sampler (virtual_pose_render.py:54-59).  x [F, 3, H, W] fp32 in [-1,1]; moments
+ * [F, 2*z_channels, H/8, W/8] fp32 (mean | logvar) -- sampling the posterior stays on the host side (CPU RNG parity). */
+MUDG_EXPORT int mudg_vae_encode(MudgCtx* ctx, const void* x, int F, int H, int W, void* moments, void* stream);
+
 /* Workspace the library needs (and will allocate on first use) for a forward of this shape. */
 MUDG_EXPORT size_t mudg_workspace_bytes(MudgCtx* ctx, int N, int T, int h, int w);
 /* Kernels launched by this context since creation (bench.py's gpu_launches). */

@@ -108,6 +108,13 @@ MUDG_EXPORT int mudg_vae_decode(MudgCtx* ctx, const void* z, int F, int h, int w
   MUDG_API_END
 }
 
+MUDG_EXPORT int mudg_vae_encode(MudgCtx* ctx, const void* x, int F, int H, int W, void* moments, void* stream) {
+  MUDG_API_BEGIN
+  MUDG_REQUIRE(ctx && x && moments, "null argument");
+  ctx->model.vae_encode(x, F, H, W, moments, S(stream));
+  MUDG_API_END
+}
+
 MUDG_EXPORT size_t mudg_workspace_bytes(MudgCtx* ctx, int N, int T, int h, int w) {
   try {
     return ctx->model.plan_unet(N, T, h, w);

@@ -201,9 +201,10 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict
   }
 }
 
-// 3x3 stride-2 pad-1 patches: out[f, ho, wo, (kh*3+kw)*C + c] = x[f, 2ho+kh-1, 2wo+kw-1, c] (0 outside)
+// 3x3 stride-2 patches: out[f, ho, wo, (kh*3+kw)*C + c] = x[f, 2ho+kh-pad, 2wo+kw-pad, c] (0 outside).
+// pad = 1: symmetric padding (UNet Downsample); pad = 0: zeros only at the bottom/right (VAE Downsample's (0,1,0,1) pad)
 __global__ void im2col_s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int F, int H, int W, int Ho, int Wo,
-                                 int vecs) {
+                                 int vecs, int pad) {
   const int64_t total = (int64_t)F * Ho * Wo * 9 * vecs;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t t = i;
@@ -212,7 +213,7 @@ __global__ void im2col_s2_kernel(const uint4* __restrict__ x, uint4* __restrict_
     const int wo = t % Wo; t /= Wo;
     const int ho = t % Ho;
     const int f = t / Ho;
-    const int h = 2 * ho + tap / 3 - 1, w = 2 * wo + tap % 3 - 1;
+    const int h = 2 * ho + tap / 3 - pad, w = 2 * wo + tap % 3 - pad;
     uint4 val = make_uint4(0, 0, 0, 0);
     if (h >= 0 && h < H && w >= 0 && w < W) val = __ldg(x + (((int64_t)f * H + h) * W + w) * vecs + v);
     y[i] = val;
@@ -417,11 +418,11 @@ void upsample2x(const __half* x, __half* y, int F, int H, int W, int C, cudaStre
   MUDG_CUDA(cudaGetLastError());
 }
 
-void im2col_s2(const __half* x, __half* y, int F, int H, int W, int C, cudaStream_t st) {
-  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+void im2col_s2(const __half* x, __half* y, int F, int H, int W, int C, int pad, cudaStream_t st) {
+  const int Ho = (H + pad - 2) / 2 + 1, Wo = (W + pad - 2) / 2 + 1;
   const int64_t total = (int64_t)F * Ho * Wo * 9 * (C / 8);
   im2col_s2_kernel<<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), F,
-                                                         H, W, Ho, Wo, C / 8);
+                                                         H, W, Ho, Wo, C / 8, pad);
   MUDG_CUDA(cudaGetLastError());
 }
 

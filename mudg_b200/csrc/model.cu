@@ -250,6 +250,24 @@ void Model::finalize(int which, cudaStream_t st) {
     vae_w.V("decoder.norm_out.weight"); vae_w.W("decoder.conv_out.weight");
     vae_w.pad_rows("decoder.conv_out.weight", "decoder.conv_out.bias", 64, st);
     vae_ready_ = true;
+    if (vae_w.hasW("encoder.conv_in.weight")) {       // the encoder is optional (decode-only deployments)
+      int bi = v.ch;
+      vae_w.W("encoder.conv_in.weight");
+      for (int lvl = 0; lvl < v.n_ch_mult; lvl++) {
+        const int bo = v.ch * v.ch_mult[lvl];
+        for (int ib = 0; ib < v.num_res_blocks; ib++) {
+          need_res("encoder.down." + std::to_string(lvl) + ".block." + std::to_string(ib), bi, bo);
+          bi = bo;
+        }
+        if (lvl != v.n_ch_mult - 1) vae_w.W("encoder.down." + std::to_string(lvl) + ".downsample.conv.weight");
+      }
+      need_res("encoder.mid.block_1", bi, bi);
+      for (const char* n : {"q", "k", "v", "proj_out"}) vae_w.W(std::string("encoder.mid.attn_1.") + n + ".weight");
+      need_res("encoder.mid.block_2", bi, bi);
+      vae_w.V("encoder.norm_out.weight"); vae_w.W("encoder.conv_out.weight"); vae_w.W("quant_conv.weight");
+      vae_w.pad_rows("encoder.conv_out.weight", "encoder.conv_out.bias", 64, st);
+      vae_enc_ready_ = true;
+    }
     return;
   }
   WeightStore& w = unet_w;
@@ -421,14 +439,16 @@ Act Model::upsample(const Act& x) {
   return y;
 }
 
-Act Model::downsample(const Act& x, const std::string& p) {   // Conv2d 3x3 stride 2 pad 1 (openaimodel3d.py:66-70)
-  const int Ho = (x.H - 1) / 2 + 1, Wo = (x.W - 1) / 2 + 1;
+Act Model::downsample(const Act& x, const std::string& p, int pad) {
+  // pad 1: Conv2d 3x3 stride 2 padding 1 (UNet Downsample, openaimodel3d.py:66-70)
+  // pad 0: F.pad (0,1,0,1) + Conv2d 3x3 stride 2 padding 0 (VAE Downsample, ae_modules.py:103-106)
+  const int Ho = (x.H + pad - 2) / 2 + 1, Wo = (x.W + pad - 2) / 2 + 1;
   Act col = alloc(x.B, x.T, Ho, Wo, 9 * x.C);
   if (live()) {
-    im2col_s2(x.p, col.p, x.B * x.T, x.H, x.W, x.C, st_);
+    im2col_s2(x.p, col.p, x.B * x.T, x.H, x.W, x.C, pad, st_);
     launches++;
   }
-  Act y = linear(col, p + ".op.weight", p + ".op.bias", nullptr);
+  Act y = linear(col, p + ".weight", p + ".bias", nullptr);
   release(col);
   return y;
 }
@@ -567,7 +587,7 @@ Act Model::run_block(Act h, const Block& b, bool owns_input) {
     if (l.kind == "res") y = res_block(h, l);
     else if (l.kind == "spatial") y = spatial_transformer(h, l);
     else if (l.kind == "temporal") y = temporal_transformer(h, l);
-    else if (l.kind == "down") y = downsample(h, l.prefix);
+    else if (l.kind == "down") y = downsample(h, l.prefix + ".op", 1);
     else if (l.kind == "up") { Act u = upsample(h); y = conv3x3(u, l.prefix + ".conv", nullptr, nullptr); release(u); }
     else if (l.kind == "conv") y = conv3x3(h, l.prefix, nullptr, nullptr);
     else throw Error("unknown layer kind " + l.kind);
@@ -938,6 +958,75 @@ void Model::vae_decode(const void* z, int F, int h, int w, void* out, cudaStream
   for (int f = 0; f < F; f++)   // perframe_ae loop (ddpm3d.py:659-664)
     vae_body(static_cast<const float*>(z) + (size_t)f * v.z_channels * h * w, h, w,
              static_cast<__half*>(out) + (size_t)f * v.out_ch * 64 * h * w);
+}
+
+// ================================================================ VAE encoder (ae_modules.py:364-463) -- "next" row (f)1
+void Model::vae_encode_body(const void* x, int H, int W, void* moments) {
+  ws_ = &vae_w;
+  N_ = 1; T_real_ = 1;
+  arena_.reset();
+  const MudgVaeConfig& v = vcfg_;
+  Act xin = alloc(1, 1, H, W, 8);
+  if (live()) {
+    to_channels_last(x, true, xin.p, 1, 3, (int64_t)H * W, 8, st_);
+    launches++;
+  }
+  Act cur = conv3x3(xin, "encoder.conv_in", nullptr, nullptr);
+  release(xin);
+  auto step = [&](Act y) { release(cur); cur = y; };
+  for (int lvl = 0; lvl < v.n_ch_mult; lvl++) {
+    for (int ib = 0; ib < v.num_res_blocks; ib++)
+      step(vae_res(cur, "encoder.down." + std::to_string(lvl) + ".block." + std::to_string(ib)));
+    if (lvl != v.n_ch_mult - 1) step(downsample(cur, "encoder.down." + std::to_string(lvl) + ".downsample.conv", 0));
+  }
+  step(vae_res(cur, "encoder.mid.block_1"));
+  step(vae_attn(cur, "encoder.mid.attn_1"));
+  step(vae_res(cur, "encoder.mid.block_2"));
+  Act o = group_norm(cur, "encoder.norm_out", 1e-6f, true, false);
+  release(cur);
+  // conv_out (-> 2z = 8 channels) on the tensor cores with the weight zero-padded to 64 rows, then quant_conv 1x1
+  Act y64 = alloc(1, 1, o.H, o.W, 64);
+  if (live()) {
+    const Weight& wt = ws_->W("encoder.conv_out.weight.pad");
+    TapGemm g;
+    g.A = o.p; g.B = 1; g.T = 1; g.H = o.H; g.W = o.W; g.Cin = o.C;
+    g.ntaps = 9; set_taps_3x3(g.taps);
+    g.Wt = wt.w; g.N = wt.O; g.D = y64.p;
+    g.bias = ws_->V("encoder.conv_out.bias.pad").p;
+    tapgemm(g, st_);
+    const Weight& wq = ws_->W("quant_conv.weight");
+    const int h = o.H, w = o.W;
+    TapGemmGeneric q;
+    q.A = y64.p; q.B = 1; q.T = 1; q.H = h; q.W = w; q.Cin = wq.I;
+    q.a_sc = 1; q.a_sw = 64; q.a_sh = (int64_t)w * 64;
+    q.ntaps = 1; q.Wt = wq.w; q.CinW = wq.Ipad; q.N = wq.O;
+    q.D = moments; q.d_fp32 = true; q.d_sw = 1; q.d_sh = w; q.d_sn = (int64_t)h * w;
+    q.bias = ws_->V("quant_conv.bias").p;
+    tapgemm_generic(q, st_);
+    launches += 2;
+  }
+  release(y64);
+  release(o);
+}
+
+void Model::vae_encode(const void* x, int F, int H, int W, void* moments, cudaStream_t st) {
+  MUDG_REQUIRE(vae_enc_ready_, "VAE encoder weights not loaded");
+  MUDG_REQUIRE(H % 8 == 0 && W % 8 == 0, "image size must be a multiple of 8");
+  std::array<int, 2> key{-H, -W};
+  auto it = vae_plans_.find(key);
+  if (it == vae_plans_.end()) {
+    arena_.planning = true; planning_ = true; arena_.reset_high();
+    vae_encode_body(nullptr, H, W, nullptr);
+    const size_t need = arena_.high_water();
+    arena_.planning = false; planning_ = false; arena_.reset();
+    it = vae_plans_.emplace(key, need).first;
+  }
+  ensure_arena(it->second);
+  st_ = st;
+  const MudgVaeConfig& v = vcfg_;
+  for (int f = 0; f < F; f++)
+    vae_encode_body(static_cast<const float*>(x) + (size_t)f * 3 * H * W, H, W,
+                    static_cast<float*>(moments) + (size_t)f * 2 * v.z_channels * (H / 8) * (W / 8));
 }
 
 }  // namespace mudg

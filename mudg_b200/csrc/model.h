@@ -74,6 +74,7 @@ class Model {
   void unet_forward(const void* x, const int64_t* t, const int64_t* label, const int64_t* fs, int N, int T, int h, int w,
                     void* out, cudaStream_t st);
   void vae_decode(const void* z, int F, int h, int w, void* out, cudaStream_t st);
+  void vae_encode(const void* x, int F, int H, int W, void* moments, cudaStream_t st);
   size_t plan_unet(int N, int T, int h, int w);
   size_t plan_vae(int h, int w);
   int64_t launches = 0;
@@ -87,7 +88,7 @@ class Model {
   std::vector<Block> in_blocks_, out_blocks_;
   Block mid_;
   int n_res_ = 0;
-  bool unet_ready_ = false, vae_ready_ = false;
+  bool unet_ready_ = false, vae_ready_ = false, vae_enc_ready_ = false;
 
   // ---- per-call state
   Arena arena_;
@@ -133,7 +134,7 @@ class Model {
   Act gemm_raw(const __half* A, int M, int K, const __half* Wt, int N, const float* bias, const Act* residual, float alpha);
   Act concat(const Act& a, const Act& b);
   Act upsample(const Act& x);
-  Act downsample(const Act& x, const std::string& p);
+  Act downsample(const Act& x, const std::string& p, int pad);
 
   Act res_block(const Act& x, const Layer& l);
   Act transformer_block_tail(Act x, const std::string& p);   // LN3 + GEGLU FF + residual (consumes x)
@@ -146,6 +147,7 @@ class Model {
   Act vae_res(const Act& x, const std::string& p);
   Act vae_attn(const Act& x, const std::string& p);
   void vae_body(const void* z, int h, int w, void* out);
+  void vae_encode_body(const void* x, int H, int W, void* moments);
 };
 
 }  // namespace mudg

@@ -144,6 +144,15 @@ class Engine:
         check(lib().mudg_vae_decode(self._h, ptr(z), F_, h, w, ptr(out), cur_stream()))
         return out
 
+    def vae_encode_moments(self, x: torch.Tensor) -> torch.Tensor:
+        """x [F, 3, H, W] in [-1,1] -> posterior moments [F, 2*zc, H/8, W/8] fp32 (mean | logvar)."""
+        F_, C, H, W = x.shape
+        assert C == 3
+        x = x.detach().float().contiguous()
+        out = torch.empty((F_, 2 * self.z_channels, H // 8, W // 8), device=x.device, dtype=torch.float32)
+        check(lib().mudg_vae_encode(self._h, ptr(x), F_, H, W, ptr(out), cur_stream()))
+        return out
+
     def ddim_step(self, x, v_cond, v_uncond, noise, *, cfg_scale, guidance_rescale, sqrt_ac, sqrt_1mac, rescale,
                   a_prev, sigma):
         B = x.shape[0]

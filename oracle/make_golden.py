@@ -156,6 +156,11 @@ def main():
     dec_mine = O.vae_decode(vsd, vsmall, z)
     print("vae small: ref vs oracle max|d| =", float((dec - dec_mine).abs().max()), "ref absmax", float(dec.abs().max()))
     np.savez_compressed(os.path.join(OUT, "vae_small.npz"), z=z.numpy(), dec=dec.numpy())
+    ximg = torch.rand(2, 3, 64, 96, generator=g) * 2 - 1
+    mom = ae.encode(ximg).parameters
+    mom_mine = O.vae_encode_moments(vsd, vsmall, ximg)
+    print("vae encode small: ref vs oracle max|d| =", float((mom - mom_mine).abs().max()), "ref absmax", float(mom.abs().max()))
+    np.savez_compressed(os.path.join(OUT, "vae_enc_small.npz"), x=ximg.numpy(), moments=mom.numpy())
     meta["vae_small"] = dict(cfg=dict(ch=64), weight_seed=2)
 
     # ---- schedules (full config constants, infer yaml) ----

@@ -558,6 +558,25 @@ def vae_decode(sd: SD, cfg: VaeCfg, z: Tensor) -> Tensor:
 
 
 @torch.no_grad()
+def vae_encode_moments(sd: SD, cfg: VaeCfg, x: Tensor) -> Tensor:
+    """Encoder.forward (ae_modules.py:432-463) + quant_conv (autoencoder.py:97-102): x [F,3,H,W] -> moments
+    [F, 2*z, H/8, W/8] (mean | logvar).  Downsample = pad (0,1,0,1) then 3x3 stride-2 conv (ae_modules.py:103-106)."""
+    h = F.conv2d(x, sd["encoder.conv_in.weight"], sd["encoder.conv_in.bias"], padding=1)
+    n = len(cfg.ch_mult)
+    for lvl in range(n):
+        for ib in range(cfg.num_res_blocks):
+            h = _vae_res(sd, f"encoder.down.{lvl}.block.{ib}", h)
+        if lvl != n - 1:
+            h = F.conv2d(F.pad(h, (0, 1, 0, 1)), sd[f"encoder.down.{lvl}.downsample.conv.weight"],
+                         sd[f"encoder.down.{lvl}.downsample.conv.bias"], stride=2)
+    h = _vae_res(sd, "encoder.mid.block_1", h)
+    h = _vae_attn(sd, "encoder.mid.attn_1", h)
+    h = _vae_res(sd, "encoder.mid.block_2", h)
+    h = F.conv2d(_swish(_gn(sd, "encoder.norm_out", h, 1e-6)), sd["encoder.conv_out.weight"], sd["encoder.conv_out.bias"], padding=1)
+    return F.conv2d(h, sd["quant_conv.weight"], sd["quant_conv.bias"])
+
+
+@torch.no_grad()
 def decode_first_stage(sd: SD, cfg: VaeCfg, z: Tensor, scale_factor: float = 0.18215) -> Tensor:
     """LatentDiffusion.decode_core, perframe_ae=True (ddpm3d.py:646-667): z [B,4,T,h,w] -> [B,3,T,8h,8w]."""
     b, c, t, h, w = z.shape

@@ -80,6 +80,14 @@ def test_vae_decode_vs_reference_golden(engine, golden_dir):
     assert float(err.max()) < 0.03, float(err.max())
 
 
+def test_vae_encode_vs_reference_golden(engine, golden_dir):
+    g = np.load(os.path.join(golden_dir, "vae_enc_small.npz"))
+    mom = engine.vae_encode_moments(torch.from_numpy(g["x"]).cuda())
+    torch.cuda.synchronize()
+    err = (mom.cpu() - torch.from_numpy(g["moments"])).abs()
+    assert float(err.max()) < 0.03, float(err.max())
+
+
 def test_ddim_step_vs_oracle(engine):
     from oracle import mudg_oracle as O
     tab = O.make_tables(base_scale=0.3)

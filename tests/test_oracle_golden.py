@@ -58,6 +58,15 @@ def test_vae_decode_matches_reference(golden_dir):
     assert float((dec - torch.from_numpy(g["dec"])).abs().max()) < 1e-5
 
 
+def test_vae_encode_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "vae_enc_small.npz"))
+    cfg = O.VaeCfg(ch=64)
+    sd = O.seeded_state_dict(O.vae_param_shapes(cfg), seed=2)
+    mom = O.vae_encode_moments(sd, cfg, torch.from_numpy(g["x"]))
+    assert mom.shape == (2, 8, 8, 12)
+    assert float((mom - torch.from_numpy(g["moments"])).abs().max()) < 1e-5
+
+
 def test_schedule_tables(golden_dir):
     g = np.load(os.path.join(golden_dir, "tables.npz"))
     tab = O.make_tables(base_scale=0.3)
