@@ -257,7 +257,7 @@ constexpr int F2_KV_STAGES = 3;
 constexpr int F2_SMEM = 2 * TILE /*Q0,Q1*/ + F2_KV_STAGES * 2 * TILE + 2 * TILE /*output staging*/ + 1024 + 256;
 constexpr float F2_LAZY = 8.0f;
 
-template <int NSEG>
+template <int NSEG, bool F2_POLY>
 __global__ void __launch_bounds__(F2_THREADS, 1)
 flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmO,
               const __grid_constant__ CUtensorMap tmK0, const __grid_constant__ CUtensorMap tmV0,
@@ -402,10 +402,13 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         mbar_arrive(&s_free[grp]);
         float mx = -INFINITY;
         if (valid >= 128) {
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // independent chains: the max is latency-bound
 #pragma unroll
           for (int c = 0; c < 4; c++)
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])));
+            for (int i = 0; i < 32; i += 2)
+              m4[(i >> 1) & 3] = fmaxf(m4[(i >> 1) & 3], fmaxf(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])));
+          mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         } else {
 #pragma unroll
           for (int c = 0; c < 4; c++)
@@ -420,15 +423,19 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         // ---- P = 2^(s*scale - m_used): fp32 exp2, row sum in a register, packed to fp16 in place over the S registers
         float lsum = 0.f;
         if (valid >= 128) {
+          float l4[4] = {0.f, 0.f, 0.f, 0.f};                            // independent chains for the row sum too
 #pragma unroll
           for (int c = 0; c < 4; c++)
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
+              // (optional) every 4th exponential on the FMA pipe (polynomial), the rest on the MUFU unit
               const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c][i]), p.scale_log2, -m_used));
-              const float p1 = ex2_approx(fmaf(__uint_as_float(sr[c][i + 1]), p.scale_log2, -m_used));
-              lsum += p0 + p1;
+              const float a1 = fmaf(__uint_as_float(sr[c][i + 1]), p.scale_log2, -m_used);
+              const float p1 = ((i & 2) && F2_POLY) ? ex2_poly(a1) : ex2_approx(a1);
+              l4[(i >> 1) & 3] += p0 + p1;
               sr[c][i >> 1] = pack_half2(p0, p1);
             }
+          lsum = (l4[0] + l4[1]) + (l4[2] + l4[3]);
         } else {
 #pragma unroll
           for (int c = 0; c < 4; c++)
@@ -852,18 +859,26 @@ void flash_attention(const FlashArgs& a, cudaStream_t st) {
   if (!attr) {
     MUDG_CUDA(cudaFuncSetAttribute(flash_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
     MUDG_CUDA(cudaFuncSetAttribute(flash_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-    MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
-    MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
+    MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
+    MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
+    MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
     attr = true;
   }
+  // Polynomial exp2 offload (FA4 trick).  Measured on B200 (tests/gpu_bench_flash.py): 5.49 ms vs 4.99 ms without it at
+  // 9216 tokens -- the kernel is not MUFU-bound at this occupancy, so it stays off unless MUDG_FLASH_POLY=1.
+  static const bool poly = [] {
+    const char* e = getenv("MUDG_FLASH_POLY");
+    return e && e[0] == '1';
+  }();
   if (use_v1) {
     dim3 grid((a.Nq + 127) / 128, a.heads, a.F);
     if (a.nseg == 1) flash_tc_kernel<1><<<grid, FA_THREADS, FA_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
     else flash_tc_kernel<2><<<grid, FA_THREADS, FA_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
   } else {
     dim3 grid((a.Nq + 255) / 256, a.heads, a.F);
-    if (a.nseg == 1) flash2_kernel<1><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
-    else flash2_kernel<2><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
+    if (a.nseg == 1 && poly) flash2_kernel<1, true><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
+    else if (a.nseg == 1) flash2_kernel<1, false><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
+    else flash2_kernel<2, false><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
   }
   MUDG_CUDA(cudaGetLastError());
 }

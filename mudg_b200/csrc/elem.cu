@@ -46,7 +46,23 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, double* __restrict
   for (int i = 0; i < 8; i++) sm[i] = sq[i] = 0.f;
   const __half* base = x + ((int64_t)s * R) * C + v * 8;
   if (r0 < rstep) {
-    for (int64_t r = row_begin + r0; r < row_end; r += rstep) {
+    int64_t r = row_begin + r0;
+    for (; r + 3 * (int64_t)rstep < row_end; r += 4 * (int64_t)rstep) {   // 4 independent 128-bit loads in flight
+      uint4 raw[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) raw[u] = __ldg(reinterpret_cast<const uint4*>(base + (r + u * (int64_t)rstep) * C));
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        float f[8];
+        unpack8(raw[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          sm[i] += f[i];
+          sq[i] += f[i] * f[i];
+        }
+      }
+    }
+    for (; r < row_end; r += rstep) {
       const uint4 raw = __ldg(reinterpret_cast<const uint4*>(base + r * C));
       float f[8];
       unpack8(raw, f);

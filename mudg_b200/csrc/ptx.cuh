@@ -192,6 +192,18 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA/ALU pipes (no MUFU): Cody-Waite split x = n + f, f in [-0.5, 0.5], degree-3 minimax polynomial for
+// 2^f (max rel. error 7.6e-5, below fp16 resolution), exponent patched in with an integer add.  Used for a fraction of
+// the softmax exponentials so the MUFU unit (16 ex2/clk/SM) stops being the limiter of d=64 attention.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;          // 1.5 * 2^23: the low mantissa bits now hold round(x)
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(0.05520550534f, f, 0.24261397123f);
+  p = fmaf(p, f, 0.69325476885f);
+  p = fmaf(p, f, 0.99992769957f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 // Arrive on an mbarrier once all previously issued tcgen05 async ops of this thread complete
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {

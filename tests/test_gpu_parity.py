@@ -160,3 +160,42 @@ def test_sampler_public_api_vs_reference_golden(golden_dir):
     assert set(inter) == {"x_inter", "pred_x0"}
     ferr = (frames.float().cpu() - torch.from_numpy(d["frames"]).float()).abs()
     assert frames.shape == (2, 3, 4, 128, 128) and float(ferr.max()) < 0.25, float(ferr.max())
+
+
+def test_window_pipeline_three_modalities():
+    """The driver's per-window flow (embedders -> VAE encode -> CFG DDIM -> VAE decode) with the three modalities
+    stacked on the batch dim (colour 0, depth 500, semantic 1), as virtual_pose_render.py:206-233 does."""
+    from mudg_b200 import compat
+    compat.install()
+    from omegaconf import OmegaConf
+    from utils.utils import instantiate_from_config
+    from mudg_b200.pipeline import image_guided_synthesis
+    cfg = OmegaConf.load(os.path.join(ROOT, "configs", "stage2-1024_mdm_waymo_infer_synthetic.yaml")).model
+    p = cfg.params
+    p.unet_config.params.model_channels = 64
+    p.unet_config.params.temporal_length = 4
+    p.first_stage_config.params.ddconfig.ch = 64
+    p.image_proj_stage_config.params.video_length = 4
+    p.image_size = [8, 16]
+    torch.manual_seed(0)
+    model = instantiate_from_config(cfg)
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        for name, q in model.named_parameters():        # undo the zero-inits so the output is non-trivial
+            if q.dim() > 1 and float(q.abs().sum()) == 0.0:
+                q.copy_(torch.randn(q.shape, generator=g) / q[0].numel() ** 0.5)
+    model = model.cuda().eval()
+    T, H, W = 4, 64, 128
+    sparse_x = (torch.rand(3, 3, T, H, W, generator=g) * 2 - 1).cuda()
+    sparse_d = (torch.rand(3, 3, T, H, W, generator=g) * 2 - 1).cuda()
+    labels = torch.tensor([[0], [500], [1]], dtype=torch.long).cuda()
+    torch.manual_seed(123)
+    with torch.autocast("cuda", dtype=torch.float16):
+        out = image_guided_synthesis(model, ["a street"] * 3, sparse_x, sparse_d, labels, [1, 4, T, H // 8, W // 8],
+                                     ddim_steps=4, ddim_eta=1.0, unconditional_guidance_scale=7.5, fs=10, text_input=True,
+                                     timestep_spacing="uniform_trailing", guidance_rescale=0.7)
+    torch.cuda.synchronize()
+    assert out.shape == (3, 1, 3, T, H, W)
+    assert bool(torch.isfinite(out.float()).all()) and float(out.float().abs().max()) > 1e-3
+    # modalities differ (different class labels / contexts)
+    assert float((out[0].float() - out[1].float()).abs().max()) > 1e-3
