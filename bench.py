@@ -71,13 +71,18 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+_CPU_SD = {}
+
+
 def cpu_forward_sample(threads, reps=1):
     """Bounded CPU sample: the oracle's UNet forward (fp32, full-size weights) on a [1,12,16,24,32] latent."""
     import torch
     from oracle import mudg_oracle as O
     torch.set_num_threads(threads)
     cfg = O.UNetCfg()
-    sd = O.seeded_state_dict(O.unet_param_shapes(cfg), seed=0)
+    if "sd" not in _CPU_SD:        # 1.44 B seeded parameters: build once, outside the timed part
+        _CPU_SD["sd"] = O.seeded_state_dict(O.unet_param_shapes(cfg), seed=0)
+    sd = _CPU_SD["sd"]
     g = torch.Generator().manual_seed(1)
     T, h, w = 16, 24, 32
     x = torch.randn(1, 12, T, h, w, generator=g)
@@ -293,7 +298,9 @@ def main():
                          "launches_timed": int(gn.value), "kernel_ms_per_step": gms.value,
                          "kernel_share_of_step": gms.value / ms_prof, "instrumented_step_ms": ms_prof,
                          "how": "CUDA-event pair around each launch, one extra (eager) clip after the timed region",
-                         "traffic": None,
+                         # dram__bytes_read+write of ONE launch of this kernel from the committed ncu --set full capture
+                         # (profiles/r1_tapgemm_tc2_conv_l0.md: level-0 3x3 conv 320->320, 0.544 TFLOP, 380 MB algorithmic)
+                         "traffic": 341.4e6, "traffic_unit": "bytes/launch (level-0 conv capture)",
                          "path": {"achieved": path_tf, "frac": path_tf / sus, "algorithmic_tflop_per_clip": flops_clip / 1e12}},
         }
         if not args.no_cpu_baseline:
