@@ -372,6 +372,70 @@ __global__ void from_channels_last_kernel(const __half* __restrict__ y, __half* 
   }
 }
 
+// LayerNorm statistics only (the normalisation itself is folded into the consuming GEMM): warp per row -> (mean, rstd)
+template <int MAXV>
+__global__ void ln_stats_kernel(const __half* __restrict__ x, float2* __restrict__ out, int64_t rows, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int vecs = C >> 3;
+  float f[MAXV][8];
+  float sum = 0.f;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * C);
+#pragma unroll
+  for (int k = 0; k < MAXV; k++) {
+    const int v = lane + 32 * k;
+    if (v < vecs) {
+      unpack8(__ldg(xr + v), f[k]);
+#pragma unroll
+      for (int i = 0; i < 8; i++) sum += f[k][i];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / C;
+  float var = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; k++) {
+    const int v = lane + 32 * k;
+    if (v < vecs) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const float d = f[k][i] - mean;
+        var += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  if (lane == 0) out[row] = make_float2(mean, rsqrtf(var / C + eps));
+}
+
+// Fold a LayerNorm's affine part into the Linear that consumes it: W[n][k] *= gamma[k] (re-rounded to fp16, in place),
+// c1[n] = sum_k fp16(W gamma), c2[n] = sum_k W[n][k] beta[k] + bias[n].  Warp per output row.
+__global__ void ln_fold_kernel(__half* __restrict__ W, const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ bias, float* __restrict__ c1, float* __restrict__ c2, int N, int K) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  __half* wr = W + (int64_t)warp * K;
+  float a = 0.f, b = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = __half2float(wr[k]);
+    const __half wf = __float2half_rn(w * gamma[k]);
+    wr[k] = wf;
+    a += __half2float(wf);
+    b += w * beta[k];
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (lane == 0) {
+    c1[warp] = a;
+    c2[warp] = b + (bias ? bias[warp] : 0.f);
+  }
+}
+
 inline int grid_for(int64_t work, int threads) {
   int64_t b = (work + threads - 1) / threads;
   return (int)std::max<int64_t>(1, std::min<int64_t>(b, (int64_t)sm_count() * 16));
@@ -511,6 +575,23 @@ void gather_rows_f16(const void* src, bool src_fp32, __half* dst, int B, int src
 void from_channels_last(const __half* y, __half* out, int B, int C, int64_t R, int Cp, cudaStream_t st) {
   const int64_t total = (int64_t)B * C * R;
   from_channels_last_kernel<<<grid_for(total, 256), 256, 0, st>>>(y, out, B, C, R, Cp);
+  MUDG_CUDA(cudaGetLastError());
+}
+
+void ln_stats(const __half* x, float2* out, int64_t rows, int C, float eps, cudaStream_t st) {
+  MUDG_REQUIRE(C % 8 == 0 && C <= 2560, "LayerNorm width %d unsupported", C);
+  const int wpb = 8;
+  const int64_t blocks = (rows + wpb - 1) / wpb;
+  const int vecs = C / 8;
+  if (vecs <= 64) ln_stats_kernel<2><<<(unsigned)blocks, wpb * 32, 0, st>>>(x, out, rows, C, eps);
+  else if (vecs <= 160) ln_stats_kernel<5><<<(unsigned)blocks, wpb * 32, 0, st>>>(x, out, rows, C, eps);
+  else ln_stats_kernel<10><<<(unsigned)blocks, wpb * 32, 0, st>>>(x, out, rows, C, eps);
+  MUDG_CUDA(cudaGetLastError());
+}
+
+void ln_fold(__half* W, const float* gamma, const float* beta, const float* bias, float* c1, float* c2, int N, int K,
+             cudaStream_t st) {
+  ln_fold_kernel<<<(N * 32 + 255) / 256, 256, 0, st>>>(W, gamma, beta, bias, c1, c2, N, K);
   MUDG_CUDA(cudaGetLastError());
 }
 

@@ -27,6 +27,10 @@ struct TapGemm {
   int bias2_div = 1, nb2 = 0;
   float alpha = 1.f;
   bool geglu = false;
+  // LayerNorm folded into the GEMM (A is the RAW activation, Wt already carries gamma):
+  //   D = rstd[m] * (acc - mean[m] * ln_c1[n]) + bias[n]      with bias = W beta (+ the layer's own bias)
+  const float2* ln_stats = nullptr;   // [rows] (mean, rstd)
+  const float* ln_c1 = nullptr;       // [N] row sums of the gamma-scaled fp16 weight
 };
 
 // generic-stride variant for the irregular layers (tiny Cin / tiny N, fp32 NCTHW in/out)

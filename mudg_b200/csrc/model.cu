@@ -112,6 +112,25 @@ void WeightStore::pad_rows(const std::string& wkey, const std::string& bkey, int
   bytes_ += nb + sizeof(float) * O_new;
 }
 
+// Fold LayerNorm `ln` (gamma, beta) into Linear `wkey` (+ optional bias `bkey`): the weight is scaled in place and two
+// vectors are added: "<wkey>.ln_c1" (row sums) and "<wkey>.ln_c2" (W beta + bias), consumed by the GEMM epilogue.
+void WeightStore::fold_ln(const std::string& wkey, const std::string& bkey, const std::string& ln, cudaStream_t st) {
+  if (hasV(wkey + ".ln_c1")) return;
+  const Weight& w = W(wkey);
+  MUDG_REQUIRE(w.taps == 1 && w.Ipad == w.I, "fold_ln: %s is not a plain Linear", wkey.c_str());
+  const Vec& g = V(ln + ".weight");
+  const Vec& b = V(ln + ".bias");
+  MUDG_REQUIRE(g.n == w.I, "fold_ln: LayerNorm width %d vs Linear K %d", g.n, w.I);
+  Vec c1, c2;
+  c1.n = c2.n = w.O;
+  MUDG_CUDA(cudaMalloc(&c1.p, sizeof(float) * w.O));
+  MUDG_CUDA(cudaMalloc(&c2.p, sizeof(float) * w.O));
+  ln_fold(w.w, g.p, b.p, bkey.empty() ? nullptr : V(bkey).p, c1.p, c2.p, w.O, w.I, st);
+  v_[wkey + ".ln_c1"] = c1;
+  v_[wkey + ".ln_c2"] = c2;
+  bytes_ += 2 * sizeof(float) * w.O;
+}
+
 void WeightStore::make_geglu(const std::string& p, cudaStream_t st) {
   if (hasW(p + ".geglu.weight")) return;
   const Weight& w = W(p + ".weight");
@@ -281,6 +300,10 @@ void Model::finalize(int which, cudaStream_t st) {
       w.stack_rows(tb + ".attn2.qkv.weight", {tb + ".attn2.to_q.weight", tb + ".attn2.to_k.weight", tb + ".attn2.to_v.weight"}, st);
     }
     w.make_geglu(tb + ".ff.net.0.proj", st);
+    // LayerNorms are folded into the Linear they feed (raw activations go straight into the GEMM)
+    w.fold_ln(tb + ".attn1.qkv.weight", "", tb + ".norm1", st);
+    w.fold_ln(tb + (cross ? ".attn2.to_q.weight" : ".attn2.qkv.weight"), "", tb + ".norm2", st);
+    w.fold_ln(tb + ".ff.net.0.proj.geglu.weight", tb + ".ff.net.0.proj.geglu.bias", tb + ".norm3", st);
     for (const char* n : {".attn1.to_out.0", ".attn2.to_out.0", ".ff.net.2"}) { w.W(tb + n + ".weight"); w.V(tb + n + ".bias"); }
     for (const char* n : {".norm1", ".norm2", ".norm3"}) { w.V(tb + n + ".weight"); w.V(tb + n + ".bias"); }
   };
@@ -361,8 +384,18 @@ Act Model::layer_norm(const Act& x, const std::string& p) {
   return y;
 }
 
+// (mean, rstd) per row for a LayerNorm that has been folded into its consumer GEMM
+float2* Model::layer_norm_stats(const Act& x) {
+  float2* st = static_cast<float2*>(alloc_bytes(sizeof(float2) * (size_t)x.rows()));
+  if (live()) {
+    ln_stats(x.p, st, x.rows(), x.C, 1e-5f, st_);
+    launches++;
+  }
+  return st;
+}
+
 Act Model::linear(const Act& x, const std::string& wkey, const std::string& bkey, const Act* residual, bool geglu,
-                  float alpha) {
+                  float alpha, const float2* ln) {
   const Weight& w0 = ws_->W(wkey);
   MUDG_REQUIRE(w0.K() == x.C, "linear %s: K %d vs activation width %d", wkey.c_str(), w0.K(), x.C);
   const int n_out = geglu ? w0.O / 2 : w0.O;
@@ -378,6 +411,11 @@ Act Model::linear(const Act& x, const std::string& wkey, const std::string& bkey
     g.R = residual ? residual->p : nullptr;
     g.bias = bkey.empty() ? nullptr : ws_->V(bkey).p;
     g.alpha = alpha; g.geglu = geglu;
+    if (ln) {                                  // folded LayerNorm: the weight already carries gamma
+      g.ln_stats = ln;
+      g.ln_c1 = ws_->V(wkey + ".ln_c1").p;
+      g.bias = ws_->V(wkey + ".ln_c2").p;
+    }
     if (residual) MUDG_REQUIRE(residual->C == n_out && residual->rows() == x.rows(), "linear %s: residual shape", wkey.c_str());
     tapgemm(g, st_);
     launches++;
@@ -482,9 +520,9 @@ Act Model::res_block(const Act& x, const Layer& l) {   // ResBlock._forward (ope
 
 // LN3 -> GEGLU FF -> +x   (BasicTransformerBlock._forward last line, attention.py:399); consumes x
 Act Model::transformer_block_tail(Act x, const std::string& tb) {
-  Act n3 = layer_norm(x, tb + ".norm3");
-  Act hid = linear(n3, tb + ".ff.net.0.proj.geglu.weight", tb + ".ff.net.0.proj.geglu.bias", nullptr, true);
-  release(n3);
+  float2* s3 = layer_norm_stats(x);
+  Act hid = linear(x, tb + ".ff.net.0.proj.geglu.weight", tb + ".ff.net.0.proj.geglu.bias", nullptr, true, 1.f, s3);
+  release_bytes(s3);
   Act y = linear(hid, tb + ".ff.net.2.weight", tb + ".ff.net.2.bias", &x);
   release(hid);
   release(x);
@@ -499,9 +537,9 @@ Act Model::spatial_transformer(const Act& xin, const Layer& l) {   // attention.
   Act x = linear(g, p + ".proj_in.weight", p + ".proj_in.bias", nullptr);
   release(g);
   // attn1: self-attention over the H*W tokens of each frame
-  Act n1 = layer_norm(x, tb + ".norm1");
-  Act qkv = linear(n1, tb + ".attn1.qkv.weight", "", nullptr);
-  release(n1);
+  float2* s1 = layer_norm_stats(x);
+  Act qkv = linear(x, tb + ".attn1.qkv.weight", "", nullptr, false, 1.f, s1);
+  release_bytes(s1);
   Act a1 = alloc(xin.B, xin.T, xin.H, xin.W, C);
   if (live()) {
     FlashArgs fa;
@@ -518,9 +556,9 @@ Act Model::spatial_transformer(const Act& xin, const Layer& l) {   // attention.
   release(a1);
   release(x);
   // attn2: text (77 tokens, shared by the frames of a sample) + image tokens, separate softmaxes summed
-  Act n2 = layer_norm(x1, tb + ".norm2");
-  Act q = linear(n2, tb + ".attn2.to_q.weight", "", nullptr);
-  release(n2);
+  float2* s2 = layer_norm_stats(x1);
+  Act q = linear(x1, tb + ".attn2.to_q.weight", "", nullptr, false, 1.f, s2);
+  release_bytes(s2);
   Act a2 = alloc(xin.B, xin.T, xin.H, xin.W, C);
   if (live()) {
     auto it = kv_.find(p);
@@ -558,9 +596,9 @@ Act Model::temporal_transformer(const Act& xin, const Layer& l) {   // attention
   release(g);
   for (int k = 1; k <= 2; k++) {   // attn1 and attn2 are both self-attention over T (only_self_att)
     const std::string an = tb + ".attn" + std::to_string(k);
-    Act n = layer_norm(x, tb + ".norm" + std::to_string(k));
-    Act qkv = linear(n, an + ".qkv.weight", "", nullptr);
-    release(n);
+    float2* sk = layer_norm_stats(x);
+    Act qkv = linear(x, an + ".qkv.weight", "", nullptr, false, 1.f, sk);
+    release_bytes(sk);
     Act a = alloc(xin.B, xin.T, xin.H, xin.W, l.inner);
     if (live()) {
       temporal_attention(qkv.p, a.p, xin.B, xin.T, HW, l.heads, 0.125f, st_);

@@ -47,7 +47,8 @@ class WeightStore {
   // out = rows of keys stacked ([sum O][K]); sources are released
   void stack_rows(const std::string& out_key, const std::vector<std::string>& keys, cudaStream_t st);
   void pad_rows(const std::string& wkey, const std::string& bkey, int O_new, cudaStream_t st);
-  void make_geglu(const std::string& proj_prefix, cudaStream_t st);   // "<p>.weight"/".bias" -> "<p>.geglu.weight"/".bias"
+  void make_geglu(const std::string& proj_prefix, cudaStream_t st);
+  void fold_ln(const std::string& wkey, const std::string& bkey, const std::string& ln, cudaStream_t st);   // "<p>.weight"/".bias" -> "<p>.geglu.weight"/".bias"
   void drop(const std::string& key);
   size_t bytes() const { return bytes_; }
 
@@ -128,7 +129,8 @@ class Model {
   Act group_norm(const Act& x, const std::string& p, float eps, bool silu, bool over_time);
   Act layer_norm(const Act& x, const std::string& p);
   Act linear(const Act& x, const std::string& wkey, const std::string& bkey, const Act* residual, bool geglu = false,
-             float alpha = 1.f);
+             float alpha = 1.f, const float2* ln = nullptr);
+  float2* layer_norm_stats(const Act& x);
   Act conv3x3(const Act& x, const std::string& p, const Act* residual, const float* bias2);
   Act conv_t3(const Act& x, const std::string& p, const Act* residual);
   Act gemm_raw(const __half* A, int M, int K, const __half* Wt, int N, const float* bias, const Act* residual, float alpha);

@@ -11,6 +11,9 @@ void gn_apply(const __half* x, __half* y, const float* scale, const float* shift
               int64_t rows_per_sample, bool silu_act, cudaStream_t st);
 void layernorm(const __half* x, __half* y, const float* gamma, const float* beta, int64_t rows, int C, float eps,
                cudaStream_t st);
+void ln_stats(const __half* x, float2* out, int64_t rows, int C, float eps, cudaStream_t st);
+void ln_fold(__half* W, const float* gamma, const float* beta, const float* bias, float* c1, float* c2, int N, int K,
+             cudaStream_t st);
 void concat_channels(const __half* a, int Ca, const __half* b, int Cb, __half* out, int64_t rows, cudaStream_t st);
 void upsample2x(const __half* x, __half* y, int F, int H, int W, int C, cudaStream_t st);
 void im2col_s2(const __half* x, __half* y, int F, int H, int W, int C, int pad, cudaStream_t st);   // Ho = (H + pad - 2) / 2 + 1

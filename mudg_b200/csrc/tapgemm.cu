@@ -33,6 +33,8 @@ struct TcParams {
   const float* bias;
   const float* bias2;
   int bias2_div, nb2, dimT;
+  const float2* ln_stats;   // folded LayerNorm: per-row (mean, rstd), or null
+  const float* ln_c1;       // [N]
   int8_t taps[9][4];
 };
 
@@ -428,6 +430,8 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int pw = tl.w0 + iw, ph = tl.h0 + ih, pt = tl.t0 + it_, pb = tl.b0 + ib_;
       const bool row_ok = pw < p.dimW && ph < p.dimH && pt < p.b.dimT && pb < p.dimB;
       const int64_t pix = (((int64_t)pb * p.b.dimT + pt) * p.dimH + ph) * p.dimW + pw;
+      float2 ln_ms = make_float2(0.f, 1.f);
+      if (p.b.ln_stats != nullptr && row_ok) ln_ms = __ldg(p.b.ln_stats + pix);
       if (p.b.geglu) {
         mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
         __syncwarp();
@@ -447,16 +451,26 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             mbar_arrive(&tmem_empty[acc]);
           }
           const float4* bv = reinterpret_cast<const float4*>(p.b.bias + tl.n0 + c * 32);
+          const float4* cv = reinterpret_cast<const float4*>(p.b.ln_c1 + tl.n0 + c * 32);
           uint32_t o[16];
 #pragma unroll
           for (int i4 = 0; i4 < 8; i4++) {
             float4 b_v = make_float4(0.f, 0.f, 0.f, 0.f), b_g = b_v;
             if (p.b.bias != nullptr) { b_v = __ldg(bv + i4); b_g = __ldg(bv + 16 + i4); }
-            const float al = p.b.alpha;
-            const float v0 = fmaf(__uint_as_float(v[4 * i4]), al, b_v.x), v1 = fmaf(__uint_as_float(v[4 * i4 + 1]), al, b_v.y);
-            const float v2 = fmaf(__uint_as_float(v[4 * i4 + 2]), al, b_v.z), v3 = fmaf(__uint_as_float(v[4 * i4 + 3]), al, b_v.w);
-            const float g0 = fmaf(__uint_as_float(g[4 * i4]), al, b_g.x), g1 = fmaf(__uint_as_float(g[4 * i4 + 1]), al, b_g.y);
-            const float g2 = fmaf(__uint_as_float(g[4 * i4 + 2]), al, b_g.z), g3 = fmaf(__uint_as_float(g[4 * i4 + 3]), al, b_g.w);
+            // alpha (plain scale) or the folded LayerNorm: rstd * (acc - mean * c1[n]) + c2[n]
+            float al = p.b.alpha;
+            float4 s_v = make_float4(0.f, 0.f, 0.f, 0.f), s_g = s_v;
+            if (p.b.ln_stats != nullptr) {
+              al = ln_ms.y;
+              const float4 c_v = __ldg(cv + i4), c_g = __ldg(cv + 16 + i4);
+              const float k = -ln_ms.x * ln_ms.y;
+              s_v = make_float4(k * c_v.x, k * c_v.y, k * c_v.z, k * c_v.w);
+              s_g = make_float4(k * c_g.x, k * c_g.y, k * c_g.z, k * c_g.w);
+            }
+            const float v0 = fmaf(__uint_as_float(v[4 * i4]), al, b_v.x + s_v.x), v1 = fmaf(__uint_as_float(v[4 * i4 + 1]), al, b_v.y + s_v.y);
+            const float v2 = fmaf(__uint_as_float(v[4 * i4 + 2]), al, b_v.z + s_v.z), v3 = fmaf(__uint_as_float(v[4 * i4 + 3]), al, b_v.w + s_v.w);
+            const float g0 = fmaf(__uint_as_float(g[4 * i4]), al, b_g.x + s_g.x), g1 = fmaf(__uint_as_float(g[4 * i4 + 1]), al, b_g.y + s_g.y);
+            const float g2 = fmaf(__uint_as_float(g[4 * i4 + 2]), al, b_g.z + s_g.z), g3 = fmaf(__uint_as_float(g[4 * i4 + 3]), al, b_g.w + s_g.w);
             o[2 * i4] = pack_half2(v0 * gelu_fast(g0), v1 * gelu_fast(g1));
             o[2 * i4 + 1] = pack_half2(v2 * gelu_fast(g2), v3 * gelu_fast(g3));
           }
@@ -530,6 +544,16 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (!p.alpha_is_one) {
 #pragma unroll
           for (int i = 0; i < 32; i++) f[i] *= p.b.alpha;
+        }
+        if (p.b.ln_stats != nullptr) {      // folded LayerNorm: rstd * (acc - mean * c1[n]); c2 arrives as the bias
+          const float4* cp = reinterpret_cast<const float4*>(p.b.ln_c1 + col0);
+          const float k = -ln_ms.x * ln_ms.y;
+#pragma unroll
+          for (int i4 = 0; i4 < 8; i4++) {
+            const float4 c4 = __ldg(cp + i4);
+            f[4 * i4] = fmaf(f[4 * i4], ln_ms.y, k * c4.x); f[4 * i4 + 1] = fmaf(f[4 * i4 + 1], ln_ms.y, k * c4.y);
+            f[4 * i4 + 2] = fmaf(f[4 * i4 + 2], ln_ms.y, k * c4.z); f[4 * i4 + 3] = fmaf(f[4 * i4 + 3], ln_ms.y, k * c4.w);
+          }
         }
         if (p.b.bias != nullptr) {
           const float4* bp = reinterpret_cast<const float4*>(p.b.bias + col0);
@@ -615,6 +639,11 @@ __global__ void tapgemm_simt_kernel(const __half* __restrict__ A, const __half* 
         if (p.geglu) accg += av * __half2float(wg[c]);
       }
     }
+    if (p.ln_stats != nullptr) {           // folded LayerNorm (rows == pixels here: linear layers only)
+      const float2 ms = p.ln_stats[idx / n_out];
+      acc = ms.y * (acc - ms.x * p.ln_c1[nv]);
+      accg = ms.y * (accg - ms.x * p.ln_c1[ng < p.N ? ng : nv]);
+    }
     float out;
     if (p.geglu) {
       float v = acc * p.alpha, g = accg * p.alpha;
@@ -685,6 +714,8 @@ TcParams make_params(const TapGemm& g) {
   p.bias2_div = g.bias2_div > 0 ? g.bias2_div : 1;
   p.nb2 = g.nb2;
   p.dimT = g.T;
+  p.ln_stats = g.ln_stats;
+  p.ln_c1 = g.ln_c1;
   for (int i = 0; i < g.ntaps; i++)
     for (int j = 0; j < 3; j++) p.taps[i][j] = g.taps[i][j];
   return p;
@@ -719,6 +750,7 @@ bool tapgemm_tc_eligible(const TapGemm& g) {
 
 void tapgemm_tc(const TapGemm& g, cudaStream_t st) {
   MUDG_REQUIRE(tapgemm_tc_eligible(g), "layer not eligible for the tcgen05 path (Cin=%d N=%d)", g.Cin, g.N);
+  MUDG_REQUIRE(g.ln_stats == nullptr, "the v1 GEMM kernel has no folded-LayerNorm epilogue");
   TcParams p = make_params(g);
   // box: 128 pixels = bw*bh*bt*bb
   int budget = BM;
