@@ -23,7 +23,33 @@ constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTE
 constexpr int TC_THREADS = 192;
 constexpr int TC_SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
+// Division by a runtime constant without the ~40-instruction IDIV sequence (Granlund-Montgomery, dividends < 2^31):
+// the tile decode runs once per tile in EVERY role of the persistent kernels, on their critical path.
+struct FastDiv {
+  uint32_t mul, shr;
+  int d;
+};
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f{0u, 0u, d < 1 ? 1 : d};
+  if (f.d > 1) {
+    int lg = 0;
+    while ((int64_t(1) << lg) < f.d) lg++;
+    const int pw = 31 + lg;
+    f.mul = (uint32_t)(((uint64_t(1) << pw) + (uint64_t)f.d - 1) / (uint64_t)f.d);
+    f.shr = (uint32_t)(pw - 32);
+  }
+  return f;
+}
+__device__ __forceinline__ int fd_div(const FastDiv& f, int n) {
+  return f.d == 1 ? n : (int)(__umulhi((uint32_t)n, f.mul) >> f.shr);
+}
+__device__ __forceinline__ void fd_divmod(const FastDiv& f, int n, int& q, int& r) {
+  q = fd_div(f, n);
+  r = n - q * f.d;
+}
+
 struct TcParams {
+  FastDiv fd_tw, fd_th, fd_tt, fd_nt, fd_b2;   // tiles_w, tiles_h, tiles_t, N tiles, bias2_div
   int ntaps, kchunks, cin;
   int tiles_n, tiles_w, tiles_h, tiles_t;
   int bw, bh, bt, bb;
@@ -297,6 +323,20 @@ __device__ __forceinline__ float erf_fast(float x) {   // Abramowitz-Stegun 7.1.
 }
 __device__ __forceinline__ float gelu_fast(float x) { return 0.5f * x * (1.f + erf_fast(x * 0.70710678118654752f)); }
 
+// gelu(g) = 0.5 g (1 + erf(g / sqrt 2)) with erf from Abramowitz-Stegun 7.1.25 (|err| <= 2.5e-5, far below the fp16
+// resolution of the output):  erf(x) = 1 - (a1 t + a2 t^2 + a3 t^3) exp(-x^2),  t = 1 / (1 + 0.47047 x),  x >= 0, so
+// gelu(g) = max(g, 0) - |g| * (0.5 P(t)) * exp(-g^2 / 2):  2 MUFU + 9 FMA-pipe instructions per element.
+__device__ __forceinline__ float gelu_as25(float g) {
+  const float ag = fabsf(g);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(ag, 0.47047f * 0.70710678118654752f, 1.f)));
+  float poly = fmaf(0.5f * 0.7478556f, t, 0.5f * -0.0958798f);
+  poly = fmaf(poly, t, 0.5f * 0.3480242f);
+  poly *= t;
+  const float e = ex2_approx(g * g * -0.72134752044448170f);     // exp(-g^2 / 2)
+  return fmaf(-ag * poly, e, fmaxf(g, 0.f));
+}
+
 struct G2Tile {
   int n0, bn, w0, h0, t0, b0;
 };
@@ -305,14 +345,14 @@ struct G2Tile {
 template <int SUB>
 __device__ __forceinline__ G2Tile g2_decode(const G2Params& p, int tile, int sub) {
   G2Tile t;
-  const int nt_i = tile % p.nt;
-  int m = (tile / p.nt) * SUB + sub;
+  int nt_i, m, tw, th, tt, tb;
+  fd_divmod(p.b.fd_nt, tile, m, nt_i);
+  m = m * SUB + sub;
   t.n0 = nt_i * G2_BN_MAX;
   t.bn = min(G2_BN_MAX, p.b.N - t.n0);
-  const int tw = m % p.b.tiles_w; m /= p.b.tiles_w;
-  const int th = m % p.b.tiles_h; m /= p.b.tiles_h;
-  const int tt = m % p.b.tiles_t;
-  const int tb = m / p.b.tiles_t;
+  fd_divmod(p.b.fd_tw, m, m, tw);
+  fd_divmod(p.b.fd_th, m, m, th);
+  fd_divmod(p.b.fd_tt, m, tb, tt);
   t.w0 = tw * p.b.bw; t.h0 = th * p.b.bh; t.t0 = tt * p.b.bt; t.b0 = tb * p.b.bb;
   return t;
 }
@@ -353,31 +393,37 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int ktotal = p.b.ntaps * p.b.kchunks;
 
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        G2Tile tl[SUB];
+    // whole warp runs the loop (uniform registers), one elected lane issues; no divisions / modulo per k-step
+    uint32_t s = 0, ph = 1;
+    const int ntaps = p.b.ntaps, kchunks = p.b.kchunks;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      G2Tile tl[SUB];
 #pragma unroll
-        for (int u = 0; u < SUB; u++) tl[u] = g2_decode<SUB>(p, tile, u);
-        for (int k = 0; k < ktotal; k++, it++) {
-          const int s = it % G2_STAGES;
-          mbar_wait(&empty[s], ((it / G2_STAGES) & 1) ^ 1);
-          mbar_expect_tx(&full[s], G2_STAGE_BYTES);
-          const int tap = k / p.b.kchunks, kc = k - tap * p.b.kchunks;
-          uint8_t* a_s = smem + s * G2_STAGE_BYTES;
+      for (int u = 0; u < SUB; u++) tl[u] = g2_decode<SUB>(p, tile, u);
+      for (int tap = 0; tap < ntaps; tap++) {
+        const int dw = p.b.taps[tap][0], dh = p.b.taps[tap][1], dt = p.b.taps[tap][2];
+        int kb = tap * p.b.cin;
+        for (int kc = 0; kc < kchunks; kc++, kb += BK) {
+          mbar_wait(&empty[s], ph);
+          if (elect_one()) {
+            mbar_expect_tx(&full[s], G2_STAGE_BYTES);
+            uint8_t* a_s = smem + s * G2_STAGE_BYTES;
 #pragma unroll
-          for (int u = 0; u < SUB; u++)
-            tma_load_5d(a_s + u * G2_A_BYTES, &tmA, &full[s], kc * BK, tl[u].w0 + p.b.taps[tap][0],
-                        tl[u].h0 + p.b.taps[tap][1], tl[u].t0 + p.b.taps[tap][2], tl[u].b0);
-          // rows past N (last tile of N = 64 mod 128) are zero-filled and never multiplied (MMA N = bn)
-          tma_load_5d(a_s + SUB * G2_A_BYTES, &tmB, &full[s], tap * p.b.cin + kc * BK, tl[0].n0, 0, 0, 0);
+            for (int u = 0; u < SUB; u++)
+              tma_load_5d(a_s + u * G2_A_BYTES, &tmA, &full[s], kc * BK, tl[u].w0 + dw, tl[u].h0 + dh, tl[u].t0 + dt,
+                          tl[u].b0);
+            // rows past N (last tile of N = 64 mod 128) are zero-filled and never multiplied (MMA N = bn)
+            tma_load_5d(a_s + SUB * G2_A_BYTES, &tmB, &full[s], kb, tl[0].n0, 0, 0, 0);
+          }
+          __syncwarp();
+          if (++s == G2_STAGES) { s = 0; ph ^= 1u; }
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      uint32_t it = 0, lt = 0;
+    {
+      uint32_t s = 0, ph = 0, lt = 0;
+      const uint64_t da0 = umma_desc_sw128(smem_u32(smem), 16, 1024);
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, lt++) {
         const G2Tile tl = g2_decode<SUB>(p, tile, 0);
         const uint32_t acc = lt & 1;
@@ -385,25 +431,27 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         tc_fence_after();
         const uint32_t idesc = umma_idesc_f16(BM, tl.bn, 0, 0);
         const uint32_t d_tmem = tmem_base + acc * (SUB * G2_BN_MAX);
-        for (int k = 0; k < ktotal; k++, it++) {
-          const int s = it % G2_STAGES;
-          mbar_wait(&full[s], (it / G2_STAGES) & 1);
+        for (int k = 0; k < ktotal; k++) {
+          mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * G2_STAGE_BYTES);
-          const uint64_t db = umma_desc_sw128(a_addr + SUB * G2_A_BYTES, 16, 1024);
+          if (elect_one()) {
+            const uint64_t da_s = da0 + (uint64_t)(s * (G2_STAGE_BYTES >> 4));   // start address field: 16 B units
+            const uint64_t db = da_s + (uint64_t)((SUB * G2_A_BYTES) >> 4);
 #pragma unroll
-          for (int u = 0; u < SUB; u++) {
-            const uint64_t da = umma_desc_sw128(a_addr + u * G2_A_BYTES, 16, 1024);
+            for (int u = 0; u < SUB; u++) {
+              const uint64_t da = da_s + (uint64_t)((u * G2_A_BYTES) >> 4);
 #pragma unroll
-            for (int kk = 0; kk < BK / 16; kk++)
-              umma_f16(d_tmem + u * G2_BN_MAX, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+              for (int kk = 0; kk < BK / 16; kk++)
+                umma_f16(d_tmem + u * G2_BN_MAX, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty[s]);
+            if (k == ktotal - 1) umma_commit(&tmem_full[acc]);
           }
-          umma_commit(&empty[s]);
+          __syncwarp();
+          if (++s == G2_STAGES) { s = 0; ph ^= 1u; }
         }
-        umma_commit(&tmem_full[acc]);
       }
     }
-    __syncwarp();
   } else {
     const int grp = (warp - 2) >> 2;        // which M sub-tile this epilogue group drains
     const int q = warp & 3;
@@ -490,7 +538,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
       int sample = 0;
       if (p.b.bias2 != nullptr) {
-        sample = (pb * p.b.dimT + pt) / p.b.bias2_div;
+        sample = fd_div(p.b.fd_b2, pb * p.b.dimT + pt);
         if (sample >= p.b.nb2) sample = p.b.nb2 - 1;
       }
       const uint4* rp = (p.R != nullptr && row_ok) ? reinterpret_cast<const uint4*>(p.R + pix * p.b.n_out + tl.n0) : nullptr;
@@ -608,6 +656,383 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 }
 
+// ================================================================ tap GEMM v3: CTA pair, 256 x (<=256) tiles
+// A cluster of two CTAs (one TPC) works on one output tile with tcgen05.mma.cta_group::2 (M = 256):
+//   CTA r owns M sub-tile r (128 pixels): it TMA-loads its A box and HALF of the weight tile (bn/2 rows) per k-step,
+//   so the pair moves 16 KB of operands per 1M MACs from L2 -- 2/3 of the 256x128 single-CTA tile, half of 128x128;
+//   the leader's elected thread issues the MMAs for both SMs; each CTA's 128 x bn fp32 accumulator lives in its own TMEM
+//   (2 buffers x 256 columns); commits are multicast to both CTAs' barriers.
+//   warp 0 producer (both CTAs; bytes are signalled on the LEADER's full barrier), warp 1 MMA issuer (leader only),
+//   warps 2-5 / 6-9: epilogue groups draining columns [0,128) / [128,256) of the CTA's rows (same fused epilogue as v2).
+// N is split into balanced tiles of whole 64-column units (128 for GEGLU): 320 -> 192+128, 640 -> 256+192+192.
+constexpr int G3_STAGES = 5;
+constexpr int G3_A_BYTES = BM * BK * 2;                   // 16 KB: this CTA's 128 pixels x 64 channels
+constexpr int G3_B_BYTES = 128 * BK * 2;                  // 16 KB: up to 128 weight rows (half of the N tile)
+constexpr int G3_STAGE_BYTES = G3_A_BYTES + G3_B_BYTES;
+constexpr int G3_STG_BYTES = 2 * 2 * 16384;              // per epilogue group: two 16 KB staging tiles (ping-pong)
+constexpr int G3_SMEM = G3_STAGES * G3_STAGE_BYTES + G3_STG_BYTES + 256;
+constexpr int G3_THREADS = 64 + 2 * 128;
+static_assert(G3_SMEM <= 232448, "pair GEMM must fit one SM");
+
+struct G3Params {
+  TcParams b;
+  int nt;                       // N tiles
+  int n_unit, n_q, n_rem;       // tile i spans (n_q + (i < n_rem)) units of n_unit columns
+  FastDiv rot_div;              // d = cluster count when it is a multiple of nt (N-tile rotation), else d = 0
+  int bn_first;                 // width of tile 0 (tmB0's box is bn_first/2 rows; narrower tiles use tmB1)
+  int total_tiles;              // nt x ceil(M tiles / 2)
+  int tiles_b;
+  int dimW, dimH, dimB;
+  const __half* R;
+  int alpha_is_one;
+};
+
+__device__ __forceinline__ G2Tile g3_decode(const G3Params& p, int tile, int rank) {
+  G2Tile t;
+  int nt_i, m, tw, th, tt, tb;
+  fd_divmod(p.b.fd_nt, tile, m, nt_i);
+  if (p.rot_div.d > 0) {           // cluster count is a multiple of nt: rotate so a cluster does not keep one N tile width
+    nt_i += fd_div(p.rot_div, tile);
+    nt_i -= fd_div(p.b.fd_nt, nt_i) * p.nt;
+  }
+  m = m * 2 + rank;
+  t.bn = (p.n_q + (nt_i < p.n_rem ? 1 : 0)) * p.n_unit;
+  t.n0 = (nt_i * p.n_q + min(nt_i, p.n_rem)) * p.n_unit;
+  fd_divmod(p.b.fd_tw, m, m, tw);
+  fd_divmod(p.b.fd_th, m, m, th);
+  fd_divmod(p.b.fd_tt, m, tb, tt);
+  t.w0 = tw * p.b.bw; t.h0 = th * p.b.bh; t.t0 = tt * p.b.bt; t.b0 = tb * p.b.bb;
+  return t;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G3_THREADS, 1)
+tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
+                   const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmD,
+                   const G3Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_dyn[];
+  uint8_t* smem = smem_dyn;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* stg_all = smem + G3_STAGES * G3_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_all + G3_STG_BYTES);
+  uint64_t* full = bars;                        // [STAGES]  used in the leader CTA only
+  uint64_t* empty = bars + G3_STAGES;           // [STAGES]  one per CTA, signalled by the multicast commit
+  uint64_t* tmem_full = bars + 2 * G3_STAGES;   // [2]       one per CTA, multicast commit
+  uint64_t* tmem_empty = bars + 2 * G3_STAGES + 2;   // [2]  leader only: 2 CTAs x 2 epilogue groups arrive
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G3_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < G3_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB0);
+    tma_prefetch_desc(&tmB1);
+    tma_prefetch_desc(&tmD);
+  }
+  if (warp == 1) tmem_alloc_pair<512>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int ktotal = p.b.ntaps * p.b.kchunks;
+
+  if (warp == 0) {
+    // The whole warp runs the loop so that addresses and coordinates stay in uniform registers; one elected lane
+    // issues.  The body runs once per k-step (every 256-512 tensor clocks): no divisions, no modulo.
+    uint32_t s = 0, ph = 1;                 // stage, parity to wait for on its "empty" barrier
+    const uint32_t full0 = mapa_u32(&full[0], 0);
+    const int ntaps = p.b.ntaps, kchunks = p.b.kchunks;
+    for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters) {
+      const G2Tile tl = g3_decode(p, tile, (int)rank);
+      const CUtensorMap* mb = (tl.bn == p.bn_first) ? &tmB0 : &tmB1;
+      const int brow = tl.n0 + (int)rank * (tl.bn >> 1);
+      const uint32_t stage_tx = 2u * (uint32_t)(G3_A_BYTES + (tl.bn >> 1) * (BK * 2));
+      for (int tap = 0; tap < ntaps; tap++) {
+        const int cw = tl.w0 + p.b.taps[tap][0], ch = tl.h0 + p.b.taps[tap][1], ct = tl.t0 + p.b.taps[tap][2];
+        int kb = tap * p.b.cin;
+        for (int kc = 0; kc < kchunks; kc++, kb += BK) {
+          mbar_wait(&empty[s], ph);
+          if (elect_one()) {
+            if (rank == 0) mbar_expect_tx(&full[s], stage_tx);     // bytes of BOTH CTAs' boxes
+            uint8_t* a_s = smem + s * G3_STAGE_BYTES;
+            tma_load_5d_pair(a_s, &tmA, full0 + 8u * s, kc * BK, cw, ch, ct, tl.b0);
+            tma_load_5d_pair(a_s + G3_A_BYTES, mb, full0 + 8u * s, kb, brow, 0, 0, 0);
+          }
+          __syncwarp();
+          if (++s == G3_STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {                         // whole warp loops (uniform registers), one elected lane issues
+      uint32_t s = 0, ph = 0, lt = 0;
+      const uint64_t da0 = umma_desc_sw128(smem_u32(smem), 16, 1024);
+      const uint64_t db0 = umma_desc_sw128(smem_u32(smem) + G3_A_BYTES, 16, 1024);
+      for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters, lt++) {
+        const G2Tile tl = g3_decode(p, tile, 0);
+        const uint32_t acc = lt & 1;
+        mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);      // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t idesc = umma_idesc_f16(256, tl.bn, 0, 0);
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int k = 0; k < ktotal; k++) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t so = (uint64_t)(s * (G3_STAGE_BYTES >> 4));     // descriptor start address: 16 B units
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; kk++)
+              umma_f16_pair(d_tmem, da0 + so + 2 * kk, db0 + so + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+            umma_commit_pair(&empty[s], 3);
+            if (k == ktotal - 1) umma_commit_pair(&tmem_full[acc], 3);
+          }
+          __syncwarp();
+          if (++s == G3_STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // Two epilogue groups of 4 warps (a warp may only touch TMEM lanes 32*(warp%4)..+32, so each group spans all 128
+    // rows).  The tile's 64-column output chunks are dealt round-robin to the groups across tiles (a running chunk
+    // counter), so odd chunk counts (bn = 192) do not leave one group with twice the work.
+    const int grp = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const bool issuer = (((warp - 2) & 3) == 0 && lane == 0);
+    uint8_t* stg_grp = stg_all + grp * 32768;   // two staging tiles: this group's n-th chunk uses tile n & 1
+    uint32_t chunk_no = 0;                      // chunks this group has stored
+    uint32_t cc = 0;                            // chunks of all tiles so far (both groups)
+    auto group_sync = [&]() {
+      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+    };
+    int r = row;
+    const int iw = r % p.b.bw; r /= p.b.bw;
+    const int ih = r % p.b.bh; r /= p.b.bh;
+    const int it_ = r % p.b.bt;
+    const int ib_ = r / p.b.bt;
+    const int csh = p.b.geglu ? 7 : 6;          // accumulator columns per chunk: 64, or 128 (64 value + 64 gate)
+    uint32_t lt = 0;
+    for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters, lt++) {
+      const G2Tile tl = g3_decode(p, tile, (int)rank);
+      const uint32_t acc = lt & 1;
+      const uint32_t empty_bar = mapa_u32(&tmem_empty[acc], 0);
+      const int nchunks = tl.bn >> csh;
+      const int first = (int)((grp - cc) & 1u);                // my chunks: first, first + 2, ...
+      const int mine = first < nchunks ? (nchunks - first + 1) >> 1 : 0;
+      cc += (uint32_t)nchunks;
+      if (mine == 0) {
+        mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
+        if (issuer) mbar_arrive_cluster(empty_bar);
+        __syncwarp();
+        continue;
+      }
+      const uint32_t t_row = tmem_base + acc * 256 + lane_off;
+      const int pw = tl.w0 + iw, ph = tl.h0 + ih, pt = tl.t0 + it_, pb = tl.b0 + ib_;
+      const bool row_ok = pw < p.dimW && ph < p.dimH && pt < p.b.dimT && pb < p.dimB;
+      const int64_t pix = (((int64_t)pb * p.b.dimT + pt) * p.dimH + ph) * p.dimW + pw;
+      float2 ln_ms = make_float2(0.f, 1.f);
+      if (p.b.ln_stats != nullptr && row_ok) ln_ms = __ldg(p.b.ln_stats + pix);
+      if (p.b.geglu) {
+        mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
+        __syncwarp();
+        tc_fence_after();
+#pragma unroll 1
+        for (int ci = 0; ci < mine; ci++) {
+          const int ch = first + 2 * ci;                       // chunk: accumulator columns [128 ch, 128 ch + 128)
+          const int nbase = tl.n0 + ch * 128;
+          uint8_t* stg = stg_grp + (chunk_no & 1) * 16384;
+          uint8_t* srow = stg + row * 128;
+          chunk_no++;
+#pragma unroll 1
+          for (int c = 0; c < 2; c++) {
+            uint32_t v[32], g[32];
+            tmem_ld32(t_row + ch * 128 + c * 32, v);
+            tmem_ld32(t_row + ch * 128 + 64 + c * 32, g);
+            tmem_ld_wait();
+            if (c == 1 && ci == mine - 1) tc_fence_before();
+            const float4* bv = reinterpret_cast<const float4*>(p.b.bias + nbase + c * 32);
+            const float4* cv = reinterpret_cast<const float4*>(p.b.ln_c1 + nbase + c * 32);
+            uint32_t o[16];
+            if (p.b.ln_stats != nullptr) {     // folded LayerNorm: rstd * acc + (k * c1[n] + c2[n]),  k = -mean * rstd
+              const float al = ln_ms.y, k = -ln_ms.x * ln_ms.y;
+#pragma unroll
+              for (int i4 = 0; i4 < 8; i4++) {
+                const float4 b_v = __ldg(bv + i4), b_g = __ldg(bv + 16 + i4);
+                const float4 c_v = __ldg(cv + i4), c_g = __ldg(cv + 16 + i4);
+                const float v0 = fmaf(__uint_as_float(v[4 * i4]), al, fmaf(k, c_v.x, b_v.x));
+                const float v1 = fmaf(__uint_as_float(v[4 * i4 + 1]), al, fmaf(k, c_v.y, b_v.y));
+                const float v2 = fmaf(__uint_as_float(v[4 * i4 + 2]), al, fmaf(k, c_v.z, b_v.z));
+                const float v3 = fmaf(__uint_as_float(v[4 * i4 + 3]), al, fmaf(k, c_v.w, b_v.w));
+                const float g0 = fmaf(__uint_as_float(g[4 * i4]), al, fmaf(k, c_g.x, b_g.x));
+                const float g1 = fmaf(__uint_as_float(g[4 * i4 + 1]), al, fmaf(k, c_g.y, b_g.y));
+                const float g2 = fmaf(__uint_as_float(g[4 * i4 + 2]), al, fmaf(k, c_g.z, b_g.z));
+                const float g3 = fmaf(__uint_as_float(g[4 * i4 + 3]), al, fmaf(k, c_g.w, b_g.w));
+                o[2 * i4] = pack_half2(v0 * gelu_as25(g0), v1 * gelu_as25(g1));
+                o[2 * i4 + 1] = pack_half2(v2 * gelu_as25(g2), v3 * gelu_as25(g3));
+              }
+            } else {
+              const float al = p.b.alpha;
+#pragma unroll
+              for (int i4 = 0; i4 < 8; i4++) {
+                float4 b_v = make_float4(0.f, 0.f, 0.f, 0.f), b_g = b_v;
+                if (p.b.bias != nullptr) { b_v = __ldg(bv + i4); b_g = __ldg(bv + 16 + i4); }
+                const float v0 = fmaf(__uint_as_float(v[4 * i4]), al, b_v.x), v1 = fmaf(__uint_as_float(v[4 * i4 + 1]), al, b_v.y);
+                const float v2 = fmaf(__uint_as_float(v[4 * i4 + 2]), al, b_v.z), v3 = fmaf(__uint_as_float(v[4 * i4 + 3]), al, b_v.w);
+                const float g0 = fmaf(__uint_as_float(g[4 * i4]), al, b_g.x), g1 = fmaf(__uint_as_float(g[4 * i4 + 1]), al, b_g.y);
+                const float g2 = fmaf(__uint_as_float(g[4 * i4 + 2]), al, b_g.z), g3 = fmaf(__uint_as_float(g[4 * i4 + 3]), al, b_g.w);
+                o[2 * i4] = pack_half2(v0 * gelu_as25(g0), v1 * gelu_as25(g1));
+                o[2 * i4 + 1] = pack_half2(v2 * gelu_as25(g2), v3 * gelu_as25(g3));
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+              *reinterpret_cast<uint4*>(srow + (((c * 4 + j) ^ (row & 7)) << 4)) =
+                  make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          }
+          fence_proxy_async_smem();
+          if (issuer) tma_store_wait_read0();   // my previous chunk's store has read the OTHER staging tile
+          __syncwarp();
+          group_sync();                         // every thread of the group is past its TMEM reads and smem writes
+          if (issuer) {
+            if (ci == mine - 1) mbar_arrive_cluster(empty_bar);
+            tma_store_5d(&tmD, stg, nbase / 2, tl.w0, tl.h0, tl.t0, tl.b0);
+            tma_store_commit();
+          }
+          __syncwarp();
+        }
+        continue;
+      }
+      int sample = 0;
+      if (p.b.bias2 != nullptr) {
+        sample = fd_div(p.b.fd_b2, pb * p.b.dimT + pt);
+        if (sample >= p.b.nb2) sample = p.b.nb2 - 1;
+      }
+      // residual row of this thread: chunk ch covers 8 uint4 (64 columns) starting at rp + 8 ch
+      const uint4* rp = (p.R != nullptr && row_ok) ? reinterpret_cast<const uint4*>(p.R + pix * p.b.n_out + tl.n0) : nullptr;
+      if (p.R != nullptr && tile + n_clusters < p.total_tiles) {
+        // residual rows of this CTA's NEXT tile: pull them from HBM into L2 a whole mainloop ahead of their use
+        // (128 B line = one chunk; the two groups take alternate lines)
+        const G2Tile nx = g3_decode(p, tile + n_clusters, (int)rank);
+        const int nw = nx.w0 + iw, nh_ = nx.h0 + ih, nt_ = nx.t0 + it_, nb_ = nx.b0 + ib_;
+        if (nw < p.dimW && nh_ < p.dimH && nt_ < p.b.dimT && nb_ < p.dimB) {
+          const int64_t npix = (((int64_t)nb_ * p.b.dimT + nt_) * p.dimH + nh_) * p.dimW + nw;
+          const __half* np_ = p.R + npix * p.b.n_out + nx.n0;
+          for (int c = grp; c < (nx.bn >> 6); c += 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(np_ + c * 64));
+        }
+      }
+      uint4 res_nxt[4];
+      if (rp != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) res_nxt[j] = __ldg(rp + first * 8 + j);
+      }
+      mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
+      __syncwarp();
+      tc_fence_after();
+      const int nslices = mine * 2;          // my 32-column slices, two per chunk
+#pragma unroll 1
+      for (int sl = 0; sl < nslices; sl++) {
+        const int hf = sl & 1;
+        const int ch = first + (sl >> 1) * 2;                  // chunk: accumulator / output columns [64 ch, 64 ch + 64)
+        const int coff = ch * 64 + hf * 32;
+        uint4 res[4];
+        if (rp != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) res[j] = res_nxt[j];
+          if (sl + 1 < nslices) {
+            const int nch = first + ((sl + 1) >> 1) * 2;
+            const uint4* np4 = rp + nch * 8 + ((sl + 1) & 1) * 4;
+#pragma unroll
+            for (int j = 0; j < 4; j++) res_nxt[j] = __ldg(np4 + j);
+          }
+        }
+        uint32_t v[32];
+        tmem_ld32(t_row + coff, v);
+        uint8_t* stg = stg_grp + (chunk_no & 1) * 16384;
+        uint8_t* srow = stg + row * 128;
+        tmem_ld_wait();
+        if (sl == nslices - 1) tc_fence_before();   // last TMEM read of this accumulator (released at the next group_sync)
+        const int col0 = tl.n0 + coff;
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) f[i] = __uint_as_float(v[i]);
+        if (!p.alpha_is_one) {
+#pragma unroll
+          for (int i = 0; i < 32; i++) f[i] *= p.b.alpha;
+        }
+        if (p.b.ln_stats != nullptr) {
+          const float4* cp = reinterpret_cast<const float4*>(p.b.ln_c1 + col0);
+          const float k = -ln_ms.x * ln_ms.y;
+#pragma unroll
+          for (int i4 = 0; i4 < 8; i4++) {
+            const float4 c4 = __ldg(cp + i4);
+            f[4 * i4] = fmaf(f[4 * i4], ln_ms.y, k * c4.x); f[4 * i4 + 1] = fmaf(f[4 * i4 + 1], ln_ms.y, k * c4.y);
+            f[4 * i4 + 2] = fmaf(f[4 * i4 + 2], ln_ms.y, k * c4.z); f[4 * i4 + 3] = fmaf(f[4 * i4 + 3], ln_ms.y, k * c4.w);
+          }
+        }
+        if (p.b.bias != nullptr) {
+          const float4* bp = reinterpret_cast<const float4*>(p.b.bias + col0);
+#pragma unroll
+          for (int i4 = 0; i4 < 8; i4++) {
+            const float4 b4 = __ldg(bp + i4);
+            f[4 * i4] += b4.x; f[4 * i4 + 1] += b4.y; f[4 * i4 + 2] += b4.z; f[4 * i4 + 3] += b4.w;
+          }
+        }
+        if (p.b.bias2 != nullptr) {
+          const float4* bp = reinterpret_cast<const float4*>(p.b.bias2 + (size_t)sample * p.b.N + col0);
+#pragma unroll
+          for (int i4 = 0; i4 < 8; i4++) {
+            const float4 b4 = __ldg(bp + i4);
+            f[4 * i4] += b4.x; f[4 * i4 + 1] += b4.y; f[4 * i4 + 2] += b4.z; f[4 * i4 + 3] += b4.w;
+          }
+        }
+        if (rp != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const float2 r0 = unpack_half2(res[j].x), r1 = unpack_half2(res[j].y), r2 = unpack_half2(res[j].z),
+                         r3 = unpack_half2(res[j].w);
+            f[8 * j + 0] += r0.x; f[8 * j + 1] += r0.y; f[8 * j + 2] += r1.x; f[8 * j + 3] += r1.y;
+            f[8 * j + 4] += r2.x; f[8 * j + 5] += r2.y; f[8 * j + 6] += r3.x; f[8 * j + 7] += r3.y;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          *reinterpret_cast<uint4*>(srow + (((hf * 4 + j) ^ (row & 7)) << 4)) =
+              make_uint4(pack_half2(f[8 * j + 0], f[8 * j + 1]), pack_half2(f[8 * j + 2], f[8 * j + 3]),
+                         pack_half2(f[8 * j + 4], f[8 * j + 5]), pack_half2(f[8 * j + 6], f[8 * j + 7]));
+        if (hf) {                            // a 64-column chunk is complete
+          fence_proxy_async_smem();
+          if (issuer) tma_store_wait_read0();  // my previous chunk's store has read the OTHER staging tile
+          __syncwarp();
+          group_sync();
+          if (issuer) {
+            if (sl == nslices - 1) mbar_arrive_cluster(empty_bar);   // the whole group is past its TMEM reads
+            tma_store_5d(&tmD, stg, tl.n0 + ch * 64, tl.w0, tl.h0, tl.t0, tl.b0);
+            tma_store_commit();
+          }
+          __syncwarp();
+          chunk_no++;
+        }
+      }
+    }
+    if (issuer) tma_store_wait_read0();
+    __syncwarp();
+    tc_fence_before();
+  }
+  cluster_sync_all();      // the peer's smem / barriers / TMEM stay alive until both CTAs are done
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc_pair<512>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // SIMT checker of the same contract: one thread per output element, fp32 accumulate.
 __global__ void tapgemm_simt_kernel(const __half* __restrict__ A, const __half* __restrict__ Wt, __half* __restrict__ D,
@@ -712,6 +1137,7 @@ TcParams make_params(const TapGemm& g) {
   p.bias = g.bias;
   p.bias2 = g.bias2;
   p.bias2_div = g.bias2_div > 0 ? g.bias2_div : 1;
+  p.fd_b2 = make_fastdiv(p.bias2_div);
   p.nb2 = g.nb2;
   p.dimT = g.T;
   p.ln_stats = g.ln_stats;
@@ -789,8 +1215,88 @@ void tapgemm_tc(const TapGemm& g, cudaStream_t st) {
   MUDG_CUDA(cudaGetLastError());
 }
 
+// CTA-pair kernel (tapgemm_tc3_kernel): large problems only (several waves of 256 x 256 tiles over the 74 TPCs)
+bool tapgemm_pair_wanted(const TapGemm& g, int64_t m_tiles, int nt128) {
+  static const int mode = [] {
+    const char* e = getenv("MUDG_GEMM_PAIR");
+    return e ? atoi(e) : -1;
+  }();
+  if (mode == 0) return false;
+  if (mode == 1) return true;
+  const int ktot_steps = g.ntaps * ((g.Cin + BK - 1) / BK);
+  return m_tiles * nt128 >= 8 * (int64_t)sm_count() && ktot_steps >= 4;
+}
+
+void tapgemm_tc3(const TapGemm& g, cudaStream_t st) {
+  G3Params p{};
+  p.b = make_params(g);
+  int budget = BM;
+  p.b.bw = pick_box(g.W, budget); budget /= p.b.bw;
+  p.b.bh = pick_box(g.H, budget); budget /= p.b.bh;
+  p.b.bt = pick_box(g.T, budget); budget /= p.b.bt;
+  p.b.bb = budget;
+  p.b.tiles_w = (g.W + p.b.bw - 1) / p.b.bw;
+  p.b.tiles_h = (g.H + p.b.bh - 1) / p.b.bh;
+  p.b.tiles_t = (g.T + p.b.bt - 1) / p.b.bt;
+  p.tiles_b = (g.B + p.b.bb - 1) / p.b.bb;
+  const int64_t m_tiles = (int64_t)p.b.tiles_w * p.b.tiles_h * p.b.tiles_t * p.tiles_b;
+  // balanced N tiles of whole units (64 columns; 128 for GEGLU so value/gate pairs stay inside one epilogue group)
+  p.n_unit = g.geglu ? 128 : 64;
+  const int units = g.N / p.n_unit, max_units = 256 / p.n_unit;
+  p.nt = (units + max_units - 1) / max_units;
+  p.n_q = units / p.nt;
+  p.n_rem = units % p.nt;
+  p.bn_first = (p.n_q + (p.n_rem > 0 ? 1 : 0)) * p.n_unit;
+  const int bn_last = p.n_q * p.n_unit;
+  p.b.tiles_n = p.nt;
+  p.b.fd_nt = make_fastdiv(p.nt);
+  p.b.fd_tw = make_fastdiv(p.b.tiles_w);
+  p.b.fd_th = make_fastdiv(p.b.tiles_h);
+  p.b.fd_tt = make_fastdiv(p.b.tiles_t);
+  const int64_t total = (int64_t)p.nt * ((m_tiles + 1) / 2);
+  MUDG_REQUIRE(total < (int64_t(1) << 30), "grid too large");
+  p.total_tiles = (int)total;
+  p.dimW = g.W; p.dimH = g.H; p.dimB = g.B;
+  p.R = g.R;
+  p.alpha_is_one = g.alpha == 1.f ? 1 : 0;
+
+  const uint64_t C = g.Cin, No = p.b.n_out, Ktot = (uint64_t)g.ntaps * g.Cin;
+  const uint64_t adims[5] = {C, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.T, (uint64_t)g.B};
+  const uint64_t astr[4] = {C * 2, C * 2 * g.W, C * 2 * g.W * g.H, C * 2 * g.W * g.H * g.T};
+  const uint32_t abox[5] = {BK, (uint32_t)p.b.bw, (uint32_t)p.b.bh, (uint32_t)p.b.bt, (uint32_t)p.b.bb};
+  const uint64_t ddims[5] = {No, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.T, (uint64_t)g.B};
+  const uint64_t dstr[4] = {No * 2, No * 2 * g.W, No * 2 * g.W * g.H, No * 2 * g.W * g.H * g.T};
+  const uint64_t bdims[5] = {Ktot, (uint64_t)g.N, 1, 1, 1};
+  const uint64_t bstr[4] = {Ktot * 2, Ktot * 2 * g.N, Ktot * 2 * g.N, Ktot * 2 * g.N};
+  const uint32_t bbox0[5] = {BK, (uint32_t)(p.bn_first / 2), 1, 1, 1};
+  const uint32_t bbox1[5] = {BK, (uint32_t)(bn_last / 2), 1, 1, 1};
+  const CUtensorMap* ma = get_tmap(g.A, adims, astr, abox);
+  const CUtensorMap* mb0 = get_tmap(g.Wt, bdims, bstr, bbox0);
+  const CUtensorMap* mb1 = get_tmap(g.Wt, bdims, bstr, bbox1);
+  const CUtensorMap* md = get_tmap(g.D, ddims, dstr, abox);
+  static bool attr_set = false;
+  if (!attr_set) {
+    MUDG_CUDA(cudaFuncSetAttribute(tapgemm_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM));
+    attr_set = true;
+  }
+  const int clusters = (int)std::min<int64_t>(total, sm_count() / 2);
+  p.rot_div = FastDiv{0u, 0u, 0};
+  if (p.nt > 1 && clusters % p.nt == 0) p.rot_div = make_fastdiv(clusters);
+  tapgemm_tc3_kernel<<<2 * clusters, G3_THREADS, G3_SMEM, st>>>(*ma, *mb0, *mb1, *md, p);
+  MUDG_CUDA(cudaGetLastError());
+}
+
 void tapgemm_tc2(const TapGemm& g, cudaStream_t st) {
   MUDG_REQUIRE(tapgemm_tc_eligible(g), "layer not eligible for the tcgen05 path (Cin=%d N=%d)", g.Cin, g.N);
+  {
+    int budget = BM;
+    const int bw = pick_box(g.W, budget); budget /= bw;
+    const int bh = pick_box(g.H, budget); budget /= bh;
+    const int bt = pick_box(g.T, budget); budget /= bt;
+    const int64_t m_tiles = (int64_t)((g.W + bw - 1) / bw) * ((g.H + bh - 1) / bh) * ((g.T + bt - 1) / bt) *
+                            ((g.B + budget - 1) / budget);
+    if (tapgemm_pair_wanted(g, m_tiles, (g.N + G2_BN_MAX - 1) / G2_BN_MAX)) return tapgemm_tc3(g, st);
+  }
   G2Params p{};
   p.b = make_params(g);
   int budget = BM;
@@ -804,6 +1310,10 @@ void tapgemm_tc2(const TapGemm& g, cudaStream_t st) {
   p.tiles_b = (g.B + p.b.bb - 1) / p.b.bb;
   p.nt = (g.N + G2_BN_MAX - 1) / G2_BN_MAX;
   p.b.tiles_n = p.nt;
+  p.b.fd_nt = make_fastdiv(p.nt);
+  p.b.fd_tw = make_fastdiv(p.b.tiles_w);
+  p.b.fd_th = make_fastdiv(p.b.tiles_h);
+  p.b.fd_tt = make_fastdiv(p.b.tiles_t);
   const int64_t m_tiles = (int64_t)p.b.tiles_w * p.b.tiles_h * p.b.tiles_t * p.tiles_b;
   MUDG_REQUIRE(m_tiles * p.nt < (int64_t(1) << 30), "grid too large");
   p.m_tiles = (int)m_tiles;
