@@ -25,7 +25,7 @@ extern "C" {
 
 typedef struct MudgCtx MudgCtx;
 
-enum { MUDG_F32 = 0, MUDG_F16 = 1 };
+enum { MUDG_F32 = 0, MUDG_F16 = 1, MUDG_U8 = 2 /* mudg_postdecode input only */ };
 enum { MUDG_UNET = 0, MUDG_VAE = 1 };
 
 /* unet_config.params of configs/stage{1,2}-*_infer.yaml:26-56 (only the keys that shape the graph) */
@@ -86,6 +86,21 @@ MUDG_EXPORT int mudg_vae_decode(MudgCtx* ctx, const void* z, int F, int h, int w
  * get_latent_z step before the sampler (virtual_pose_render.py:54-59).  x [F, 3, H, W] fp32 in [-1,1]; moments
  * [F, 2*z_channels, H/8, W/8] fp32 (mean | logvar) -- sampling the posterior stays on the host side (CPU RNG parity). */
 MUDG_EXPORT int mudg_vae_encode(MudgCtx* ctx, const void* x, int F, int H, int W, void* moments, void* stream);
+
+/* "Next" row: the per-frame CPU code the driver runs on the decoded clip before writing files
+ * (virtual_pose_render.py:243 clamp; eval_tools.py:22-27 uint8 conversion; :70-74 + colormap :205-236 depth mean and
+ * Spectral colouring; visualize_semantic :297-347 nearest-of-19-palette class + colour).  frames [B, 3, T, H, W]
+ * (decode_first_stage layout, dtype MUDG_F16 | MUDG_F32, or MUDG_U8 for frames that are already uint8); modes: HOST array [B] of MUDG_POST_{COLOR,DEPTH,SEMANTIC}
+ * (class labels 0 / 500 / 1 of the driver).  rgb_u8 [B, T, 3, H, W] uint8 (the frame, or its depth / semantic
+ * visualisation); depth_f32 [B, T, H, W] fp32 in [0,1] and class_u8 [B, T, H, W] uint8 are written for the samples of
+ * that mode only and may be NULL.  Bit-exact against the reference's CPU arithmetic. */
+enum { MUDG_POST_COLOR = 0, MUDG_POST_DEPTH = 1, MUDG_POST_SEMANTIC = 2 };
+MUDG_EXPORT int mudg_postdecode(const void* frames, int dtype, int B, int T, int H, int W, const int* modes,
+                                void* rgb_u8, void* depth_f32, void* class_u8, void* stream);
+
+/* colormap(image, cmap="Spectral", bytes=True) of the reference (eval_tools.py:137-250, method_custom): map fp32 [n] in
+ * [0,1] (clamped) -> out_u8 [n, 3] (HWC).  Used for the ground-truth depth visualisation (eval_tools.py:82). */
+MUDG_EXPORT int mudg_colormap_spectral(const void* map_f32, int64_t n, void* out_u8, void* stream);
 
 /* Workspace the library needs (and will allocate on first use) for a forward of this shape. */
 MUDG_EXPORT size_t mudg_workspace_bytes(MudgCtx* ctx, int N, int T, int h, int w);

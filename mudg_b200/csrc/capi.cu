@@ -115,6 +115,24 @@ MUDG_EXPORT int mudg_vae_encode(MudgCtx* ctx, const void* x, int F, int H, int W
   MUDG_API_END
 }
 
+MUDG_EXPORT int mudg_postdecode(const void* frames, int dtype, int B, int T, int H, int W, const int* modes,
+                                void* rgb_u8, void* depth_f32, void* class_u8, void* stream) {
+  MUDG_API_BEGIN
+  MUDG_REQUIRE(frames && modes && rgb_u8, "null argument");
+  MUDG_REQUIRE(dtype == MUDG_F32 || dtype == MUDG_F16 || dtype == MUDG_U8, "postdecode: dtype %d", dtype);
+  MUDG_REQUIRE(H >= 1 && W >= 1, "postdecode: empty frame");
+  postdecode(frames, dtype, static_cast<uint8_t*>(rgb_u8), static_cast<float*>(depth_f32),
+             static_cast<uint8_t*>(class_u8), B, T, (int64_t)H * W, modes, S(stream));
+  MUDG_API_END
+}
+
+MUDG_EXPORT int mudg_colormap_spectral(const void* map_f32, int64_t n, void* out_u8, void* stream) {
+  MUDG_API_BEGIN
+  MUDG_REQUIRE(map_f32 && out_u8, "null argument");
+  spectral_colormap(static_cast<const float*>(map_f32), static_cast<uint8_t*>(out_u8), n, S(stream));
+  MUDG_API_END
+}
+
 MUDG_EXPORT size_t mudg_workspace_bytes(MudgCtx* ctx, int N, int T, int h, int w) {
   try {
     return ctx->model.plan_unet(N, T, h, w);

@@ -73,4 +73,12 @@ struct DdimStepArgs {
 };
 void ddim_step(const DdimStepArgs& a, cudaStream_t st);
 
+// ---- post-decode frame pipeline (post.cu): decoded clip -> uint8 RGB (+ fp32 depth / class index), bit-exact against
+// the reference's CPU code (eval_tools.py).  frames [B][3][T][HW]; modes_host[b]: 0 colour, 1 depth, 2 semantic.
+constexpr int POSTDECODE_MAX_SAMPLES = 64;
+void postdecode(const void* frames, int dtype /*0 fp32, 1 fp16, 2 uint8*/, uint8_t* rgb /*[B][T][3][HW]*/, float* depth /*[B][T][HW] or null*/,
+                uint8_t* cls /*[B][T][HW] or null*/, int B, int T, int64_t HW, const int* modes_host, cudaStream_t st);
+// Spectral colour map of a [0,1] fp32 map -> [n][3] uint8 (HWC), colormap(..., "Spectral", bytes=True) of the reference
+void spectral_colormap(const float* map, uint8_t* out_hwc, int64_t n, cudaStream_t st);
+
 }  // namespace mudg

@@ -11,7 +11,11 @@
 #include "gemm.h"
 #include "ptx.cuh"
 
+#include <array>
+#include <cstdio>
 #include <cstdlib>
+#include <map>
+#include <string>
 #include <vector>
 
 namespace mudg {
@@ -1392,6 +1396,7 @@ struct GemmProfiler {
   bool on = false;
   std::vector<cudaEvent_t> ev;      // pairs
   std::vector<double> flops;
+  std::vector<std::string> shape;   // "rows,N,taps,Cin,geglu,res,ln" of each timed launch (per-shape dump)
   size_t used = 0;
 } g_prof;
 }  // namespace
@@ -1402,22 +1407,40 @@ void gemm_profile_enable(bool on) {
   g_prof.on = on;
   g_prof.used = 0;
   g_prof.flops.clear();
+  g_prof.shape.clear();
 }
 
 void gemm_profile_read(double* ms_total, double* flops_total, int64_t* launches) {
   MUDG_CUDA(cudaDeviceSynchronize());
   double ms = 0, fl = 0;
+  // MUDG_GEMM_PROFILE_DUMP=<file>: per-shape table (launches, total ms, total FLOP) of the timed launches
+  const char* dump = getenv("MUDG_GEMM_PROFILE_DUMP");
+  std::map<std::string, std::array<double, 3>> by_shape;
   for (size_t i = 0; i < g_prof.used; i++) {
     float t = 0.f;
     MUDG_CUDA(cudaEventElapsedTime(&t, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]));
     ms += t;
     fl += g_prof.flops[i];
+    if (dump) {
+      auto& a = by_shape[g_prof.shape[i]];
+      a[0] += 1; a[1] += t; a[2] += g_prof.flops[i];
+    }
+  }
+  if (dump && !by_shape.empty()) {
+    if (FILE* f = fopen(dump, "w")) {
+      fprintf(f, "rows,N,taps,Cin,geglu,res,ln,launches,ms_total,tflop_total,tflops\n");
+      for (auto& kv : by_shape)
+        fprintf(f, "%s,%.0f,%.4f,%.4f,%.1f\n", kv.first.c_str(), kv.second[0], kv.second[1], kv.second[2] / 1e12,
+                kv.second[1] > 0 ? kv.second[2] / 1e9 / kv.second[1] : 0.0);
+      fclose(f);
+    }
   }
   *ms_total = ms;
   *flops_total = fl;
   *launches = (int64_t)g_prof.used;
   g_prof.used = 0;
   g_prof.flops.clear();
+  g_prof.shape.clear();
 }
 
 void tapgemm(const TapGemm& g, cudaStream_t st) {
@@ -1439,6 +1462,12 @@ void tapgemm(const TapGemm& g, cudaStream_t st) {
       MUDG_CUDA(cudaEventRecord(g_prof.ev[2 * g_prof.used + 1], st));
       // algorithmic work of the layer: 2 * rows * N * (taps * Cin), padding and tile overhang not counted
       g_prof.flops.push_back(2.0 * (double)g.B * g.T * g.H * g.W * (double)g.N * (double)g.ntaps * g.Cin);
+      {
+        char buf[96];
+        snprintf(buf, sizeof buf, "%lld,%d,%d,%d,%d,%d,%d", (long long)g.B * g.T * g.H * g.W, g.N, g.ntaps, g.Cin,
+                 g.geglu ? 1 : 0, g.R ? 1 : 0, g.ln_stats ? 1 : 0);
+        g_prof.shape.push_back(buf);
+      }
       g_prof.used++;
     } else {
       tapgemm_tc_auto(g, st);

@@ -13,8 +13,47 @@ import torch
 
 from ._lib import MudgError, check, cur_stream, lib, ptr
 
-MUDG_F32, MUDG_F16 = 0, 1
+MUDG_F32, MUDG_F16, MUDG_U8 = 0, 1, 2
 MUDG_UNET, MUDG_VAE = 0, 1
+MUDG_POST_COLOR, MUDG_POST_DEPTH, MUDG_POST_SEMANTIC = 0, 1, 2
+# class labels the driver gives the three modalities (virtual_pose_render.py:247-318)
+LABEL_TO_POST_MODE = {0: MUDG_POST_COLOR, 500: MUDG_POST_DEPTH, 1: MUDG_POST_SEMANTIC}
+
+
+def postdecode(frames: torch.Tensor, modes: Sequence[int]):
+    """Post-decode frame pipeline on the GPU (mudg_postdecode): frames [B, 3, T, H, W] (fp16 / fp32 in [-1,1], or uint8)
+    and one mode per sample -> (rgb uint8 [B,T,3,H,W], depth fp32 [B,T,H,W], cls uint8 [B,T,H,W]).  depth / cls rows of
+    samples in another mode are left zero.  Bit-exact against the reference's CPU code (eval_tools.py)."""
+    if not frames.is_cuda:
+        raise MudgError("postdecode needs a CUDA tensor; there is no CPU fallback")
+    if frames.dim() != 5 or frames.shape[1] != 3:
+        raise MudgError(f"postdecode expects [B, 3, T, H, W], got {tuple(frames.shape)}")
+    dt = {torch.float32: MUDG_F32, torch.float16: MUDG_F16, torch.uint8: MUDG_U8}.get(frames.dtype)
+    if dt is None:
+        frames, dt = frames.float(), MUDG_F32
+    frames = frames.detach().contiguous()
+    B, _, T, H, W = frames.shape
+    modes = [int(m) for m in modes]
+    if len(modes) != B:
+        raise MudgError(f"postdecode: {len(modes)} modes for {B} samples")
+    rgb = torch.empty((B, T, 3, H, W), device=frames.device, dtype=torch.uint8)
+    depth = torch.zeros((B, T, H, W), device=frames.device, dtype=torch.float32) if MUDG_POST_DEPTH in modes else None
+    cls = torch.zeros((B, T, H, W), device=frames.device, dtype=torch.uint8) if MUDG_POST_SEMANTIC in modes else None
+    marr = (ctypes.c_int * B)(*modes)
+    with torch.cuda.device(frames.device):
+        check(lib().mudg_postdecode(ptr(frames), dt, B, T, H, W, marr, ptr(rgb), ptr(depth), ptr(cls), cur_stream()))
+    return rgb, depth, cls
+
+
+def colormap_spectral(depth01: torch.Tensor) -> torch.Tensor:
+    """[...] fp32 map in [0,1] on the device -> [..., 3] uint8 (the reference's colormap(..., 'Spectral', bytes=True))."""
+    if not depth01.is_cuda:
+        raise MudgError("colormap_spectral needs a CUDA tensor; there is no CPU fallback")
+    m = depth01.detach().float().contiguous()
+    out = torch.empty(tuple(m.shape) + (3,), device=m.device, dtype=torch.uint8)
+    with torch.cuda.device(m.device):
+        check(lib().mudg_colormap_spectral(ptr(m), ctypes.c_int64(m.numel()), ptr(out), cur_stream()))
+    return out
 
 
 class _UNetConfig(ctypes.Structure):

@@ -68,6 +68,17 @@ def main():
         ms = e0.elapsed_time(e1) / reps
         fl = FLOPS.get((T, h, w), 0) * N
         print(f"  unet forward: {ms:.2f} ms  -> {fl / ms / 1e9:.1f} TFLOP/s algorithmic", flush=True)
+        if os.environ.get("MUDG_GEMM_PROFILE_DUMP"):      # per-shape table of the tcgen05 GEMM launches (one eager forward)
+            import ctypes
+            from mudg_b200._lib import lib
+            L = lib()
+            L.mudg_profile_gemm(1)
+            eng.unet_forward(x, ts, lab, fs)
+            gms, gfl, gn = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+            L.mudg_profile_gemm_read(ctypes.byref(gms), ctypes.byref(gfl), ctypes.byref(gn))
+            L.mudg_profile_gemm(0)
+            print(f"  gemm launches {gn.value}: {gms.value:.2f} ms, {gfl.value / 1e12:.2f} TFLOP -> "
+                  f"{gfl.value / gms.value / 1e9:.1f} TFLOP/s", flush=True)
         if os.environ.get("PROBE_VAE", "1") == "1":
             z = torch.randn(2, 4, h, w, device="cuda")
             eng.vae_decode(z)

@@ -199,3 +199,93 @@ def test_window_pipeline_three_modalities():
     assert bool(torch.isfinite(out.float()).all()) and float(out.float().abs().max()) > 1e-3
     # modalities differ (different class labels / contexts)
     assert float((out[0].float() - out[1].float()).abs().max()) > 1e-3
+
+
+# ---------------------------------------------------------------- post-decode frame pipeline (section 8f row 2): bit-exact
+def _post(frames, modes):
+    from mudg_b200.engine import postdecode
+    rgb, depth, cls = postdecode(frames, modes)
+    torch.cuda.synchronize()
+    return rgb.cpu().numpy(), None if depth is None else depth.cpu().numpy(), None if cls is None else cls.cpu().numpy()
+
+
+def test_postdecode_vs_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "post_small.npz"))
+    for dt in (torch.float16, torch.float32):
+        rgb, depth, cls = _post(torch.from_numpy(g["frames"]).cuda().to(dt), [0, 1, 2])
+        assert np.array_equal(rgb, np.stack([g["u8"][0], g["depth_vis"], g["sem_vis"]]))
+        assert depth[1].tobytes() == g["depth_pred"].tobytes()
+        assert np.array_equal(cls[2].astype(np.int64), g["sem_cls"])
+        assert not depth[0].any() and not depth[2].any() and not cls[0].any() and not cls[1].any()
+
+
+@pytest.mark.parametrize("shape", [(1, 3, 1, 1, 1), (2, 3, 2, 5, 7), (3, 3, 2, 16, 24), (1, 3, 1, 3, 8)])
+def test_postdecode_ragged_vs_oracle(shape):
+    """Odd / tiny frame sizes (scalar path when H*W is not a multiple of 8) and every mode for every sample."""
+    from oracle import post_oracle as P
+    g = torch.Generator().manual_seed(sum(shape))
+    frames = (0.9 * torch.randn(shape, generator=g)).half()
+    for modes in ([0] * shape[0], [1] * shape[0], [2] * shape[0]):
+        ref_rgb, ref_d, ref_c = P.postdecode(frames.numpy(), modes)
+        rgb, depth, cls = _post(frames.cuda(), modes)
+        assert np.array_equal(rgb, ref_rgb)
+        if modes[0] == 1:
+            assert depth.tobytes() == ref_d.tobytes()
+        if modes[0] == 2:
+            assert np.array_equal(cls, ref_c)
+
+
+def test_postdecode_full_size_properties():
+    """BASELINE full size (3 modalities x 16 frames x 576 x 1024): two frames against the oracle bit for bit, plus
+    size-independent properties on the whole clip: the colour output fed back as uint8 is a fixed point, the semantic
+    visualisation is idempotent, class indices and palette colours agree, depth in [0,1] is the RGB mean."""
+    from oracle import post_oracle as P
+    g = torch.Generator(device="cuda").manual_seed(7)
+    frames = (0.7 * torch.randn(3, 3, 16, 576, 1024, generator=g, device="cuda")).half()
+    from mudg_b200.engine import postdecode
+    rgb, depth, cls = postdecode(frames, [0, 1, 2])
+    torch.cuda.synchronize()
+    for t in (0, 15):
+        sub = frames[:, :, t:t + 1].cpu().numpy()
+        r_rgb, r_d, r_c = P.postdecode(sub, [0, 1, 2])
+        assert np.array_equal(rgb[:, t].cpu().numpy(), r_rgb[:, 0])
+        assert depth[1, t].cpu().numpy().tobytes() == r_d[1, 0].tobytes()
+        assert np.array_equal(cls[2, t].cpu().numpy(), r_c[2, 0])
+    u8 = rgb.permute(0, 2, 1, 3, 4).contiguous()                      # [B, 3, T, H, W] uint8
+    rgb2, depth2, cls2 = postdecode(u8, [0, 0, 2])
+    assert torch.equal(rgb2[0], rgb[0])                               # colour: uint8 in == uint8 out
+    assert torch.equal(rgb2[2], rgb[2]) and torch.equal(cls2[2], cls[2])   # semantic: idempotent
+    pal = torch.tensor(P.PALETTE, dtype=torch.uint8, device="cuda")
+    assert torch.equal(pal[cls[2].long()].permute(0, 3, 1, 2), rgb[2])
+    col_u8 = postdecode(frames[1:2], [0])[0][0].float()               # depth == mean of the colour conversion / 255
+    assert torch.equal(depth[1], col_u8.sum(1) / 3 / 255)
+    assert float(depth[1].min()) >= 0.0 and float(depth[1].max()) <= 1.0
+
+
+def test_eval_tools_dropin(tmp_path):
+    """virtual_render.eval_tools keeps the reference's function surface and writes the same files."""
+    from virtual_render import eval_tools as E
+    from oracle import post_oracle as P
+    g = torch.Generator().manual_seed(1)
+    samples = (0.8 * torch.randn(1, 3, 3, 16, 24, generator=g)).half().cuda()
+    gts = torch.rand(1, 3, 3, 16, 24, generator=g) * 2 - 1
+    sparses = torch.rand(1, 3, 3, 16, 24, generator=g) * 2 - 1
+    fakedir = str(tmp_path / "samples")
+    E.save_virtual_color_results("p", samples, 0, fakedir, gts, sparses, base_index=5, dir_name="virtual_color")
+    E.save_virtual_depth_results("p", samples, 0, fakedir, gts, sparses, base_index=5, is_virtual=True, dir_name="virtual_depth")
+    E.save_virtual_semantic_results("p", samples, 0, fakedir, gts, sparses, base_index=5, dir_name="virtual_semantic")
+    assert sorted(os.listdir(tmp_path / "virtual_color")) == sorted(
+        f"color_{k}_{i}.png" for k in ("re", "gt", "sp", "all") for i in (6, 7))
+    ref_rgb, ref_d, ref_c = P.postdecode(samples.cpu().numpy().repeat(3, 0), [0, 1, 2])
+    d = np.load(tmp_path / "depth" / "depth_re_6.npy")
+    assert d.shape == (1, 16, 24) and d.tobytes() == ref_d[1, 1].tobytes()
+    s = np.load(tmp_path / "semantic" / "semantic_re_7.npy")
+    assert s.dtype == np.int64 and np.array_equal(s, ref_c[2, 2].astype(np.int64))
+    import torchvision
+    png = torchvision.io.read_image(str(tmp_path / "virtual_color" / "color_re_6.png")).numpy()
+    assert np.array_equal(png, ref_rgb[0, 1])
+    vis, idx = E.visualize_semantic(torch.from_numpy(ref_rgb[0, 0]), return_pt=True)
+    rv, rc = P.semantic_from_uint8(ref_rgb[0, 0])
+    assert np.array_equal(vis.numpy(), rv) and np.array_equal(idx.numpy(), rc)
+    dv = np.array(E.visualize_depth(ref_d[1, 0][None])[0])
+    assert np.array_equal(dv.transpose(2, 0, 1), P.spectral_u8(ref_d[1, 0]))
