@@ -120,6 +120,10 @@ MUDG_EXPORT int mudg_test_flash(const void* Q, int q_pitch, void* O, int o_pitch
                                 const void* K0, const void* V0, int pitch0, int len0, int nbatch0, int div0,
                                 const void* K1, const void* V1, int pitch1, int len1, int nbatch1, int div1, float scale,
                                 int backend, void* stream);
+/* debug: device buffer [3][96][8] int64 receiving the clock64 time line of CTA 0 of the next flash launches (NULL = off) */
+MUDG_EXPORT int mudg_test_flash_trace(void* buf);
+/* debug: tcgen05.mma issue-rate probe; out = device int64 [ctas][2] (clocks until issued, until complete) */
+MUDG_EXPORT int mudg_test_mma_probe(int variant, int reps, int ctas, int mode, void* out, void* stream);
 MUDG_EXPORT int mudg_test_temporal_attn(const void* qkv, void* out, int B, int T, int HW, int heads, float scale,
                                         void* stream);
 MUDG_EXPORT int mudg_test_groupnorm(const void* x, void* y, int S, int64_t rows_per_sample, int C, const float* gamma,

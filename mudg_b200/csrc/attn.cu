@@ -24,6 +24,8 @@ constexpr int TILE = 128 * 64 * 2;                       // 16 KB: 128 rows x 64
 constexpr int FA_SMEM = TILE /*Q*/ + 2 * 2 * TILE /*K,V ring*/ + 2 * TILE /*P*/ + 1024 + 256;
 
 struct FaParams {
+  long long* trace;   // debug (tests/gpu_trace_flash.py): clock64 time line of CTA 0, [3 roles][96 blocks][8 events]
+  int stagger;        // flash2: offset the two softmax groups by half a period (MUDG_FLASH_STAGGER=0 disables)
   int nseg;
   int len[2];
   int kv_div[2];
@@ -253,9 +255,16 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 //   raised when it grows by > 2^8 (lazy rescale: P <= 256 fits fp16), in which case the warp rescales its O rows
 //   in place (tcgen05.ld/st); the row sum l is a register.
 constexpr int F2_THREADS = 320;
-constexpr int F2_KV_STAGES = 3;
-constexpr int F2_SMEM = 2 * TILE /*Q0,Q1*/ + F2_KV_STAGES * 2 * TILE + 2 * TILE /*output staging*/ + 1024 + 256;
+constexpr int F2_KV_STAGES = 5;
+// Q0,Q1 (reused as the two output staging tiles once every S MMA of the tile has retired) + the K / V^T ring
+constexpr int F2_SMEM = 2 * TILE + F2_KV_STAGES * 2 * TILE + 1024 + 256;
 constexpr float F2_LAZY = 8.0f;
+
+#define F2_TRACE(role, blk, ev)                                                                        \
+  do {                                                                                                  \
+    if (p.trace != nullptr && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (blk) < 96)                \
+      p.trace[((role) * 96 + (blk)) * 8 + (ev)] = clock64();                                            \
+  } while (0)
 
 template <int NSEG, bool F2_POLY>
 __global__ void __launch_bounds__(F2_THREADS, 1)
@@ -266,16 +275,17 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                  // 2 tiles
   uint8_t* sKV = smem + 2 * TILE;                      // stage s: K at + s*2*TILE, V at + TILE
-  uint8_t* sOut = sKV + F2_KV_STAGES * 2 * TILE;       // tile i: 16 KB output staging at + i*TILE
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + 2 * TILE);
+  uint8_t* sOut = sQ;                                  // tile i: 16 KB output staging = its own (dead) Q tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + F2_KV_STAGES * 2 * TILE);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;                        // [3]
-  uint64_t* kv_empty = bars + 4;                       // [3]
-  uint64_t* s_full = bars + 7;                         // [2]
-  uint64_t* p_ready = bars + 9;                        // [2]
-  uint64_t* o_done = bars + 11;                        // [2]
-  uint64_t* s_free = bars + 13;                        // [2]  S tile copied to registers -> TMEM tile reusable
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* kv_full = bars + 1;                        // [F2_KV_STAGES]
+  uint64_t* kv_empty = kv_full + F2_KV_STAGES;         // [F2_KV_STAGES]
+  uint64_t* s_full = kv_empty + F2_KV_STAGES;          // [2]
+  uint64_t* p_ready = s_full + 2;                      // [2]
+  uint64_t* o_done = p_ready + 2;                      // [2]
+  uint64_t* s_free = o_done + 2;                       // [2]  S tile copied to registers -> TMEM tile reusable
+  uint64_t* exp_done = s_free + 2;                     // [2]  group i has finished the exponentials of a block (MUFU turn)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(exp_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 256, head = blockIdx.y, f = blockIdx.z;
@@ -286,6 +296,7 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     for (int i = 0; i < 2; i++) {
       mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); mbar_init(&o_done[i], 1); mbar_init(&s_free[i], 128);
     }
+    mbar_init(&exp_done[0], 128); mbar_init(&exp_done[1], 128);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -299,6 +310,11 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   nblk[0] = (p.len[0] + 127) >> 7;
   nblk[1] = NSEG > 1 ? (p.len[1] + 127) >> 7 : 0;
   const int nb = nblk[0] + nblk[1];
+  // The two softmax groups take turns on the MUFU unit: g0 exp(0), g1 exp(0), g0 exp(1), g1 exp(1), ...  Left alone they
+  // start in phase and stay there (or drift), so the unit idles whenever BOTH are in their TMEM-load / max / P-store
+  // phase and is oversubscribed when both exponentiate (ncu: XU pipe 61 % busy, clock64 trace: 2500 clk per exp phase
+  // instead of ~1100).  With the hand-over each group does its other work while its partner exponentiates.
+  const bool do_stagger = p.stagger != 0 && nb >= 4;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -316,58 +332,86 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           mbar_expect_tx(&kv_full[s], 2 * TILE);
           uint8_t* k_s = sKV + s * 2 * TILE;
           tma_load_5d(k_s, mk, &kv_full[s], head * 64, j * 128, kb, 0, 0);
-          tma_load_5d(k_s + TILE, mv, &kv_full[s], head * 64, j * 128, kb, 0, 0);
+          // V arrives TRANSPOSED ([d][kv], kv contiguous): two K-major SWIZZLE_128B atoms of 64 kv columns each
+          tma_load_5d(k_s + TILE, mv, &kv_full[s], j * 128, head * 64, kb, 0, 0);
+          tma_load_5d(k_s + TILE + TILE / 2, mv, &kv_full[s], j * 128 + 64, head * 64, kb, 0, 0);
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_f16(128, 128, 0, 0);
-      constexpr uint32_t idesc_o = umma_idesc_f16(128, 64, 0, 1);     // V MN-major
-      mbar_wait(q_full, 0);
-      auto issue_s = [&](int i, int it) {
-        const int s = it % F2_KV_STAGES;
-        const uint64_t dq = umma_desc_sw128(smem_u32(sQ + i * TILE), 16, 1024);
-        const uint64_t dk = umma_desc_sw128(smem_u32(sKV + s * 2 * TILE), 16, 1024);
+    // The WHOLE warp runs the issue loop (uniform control flow, descriptors in uniform registers) and one elected lane
+    // issues: the same code under `if (lane == 0)` spent ~140 clocks of dependent R2UR / ELECT / waterfall instructions
+    // per tcgen05.mma (clock64 trace), which made the issue thread -- not the tensor pipe or the MUFU -- the bottleneck.
+    constexpr uint32_t idesc_s = umma_idesc_f16(128, 128, 0, 0);
+    // P V with V^T K-major in shared memory: an MN-major B operand (V as it lies in the QKV rows) feeds the tensor core
+    // at a quarter of the rate (tests/gpu_probe_mma.py: 118 clk per N=64 step instead of 33)
+    constexpr uint32_t idesc_o = umma_idesc_f16(128, 64, 0, 0);
+    const uint64_t dq0 = umma_desc_sw128(smem_u32(sQ), 16, 1024);
+    const uint64_t dq1 = umma_desc_sw128(smem_u32(sQ + TILE), 16, 1024);
+    const uint64_t dkv0 = umma_desc_sw128(smem_u32(sKV), 16, 1024);
+    mbar_wait(q_full, 0);
+    // Event loop: each softmax group is served on its own -- S_i(b) as soon as K(b) has landed and group i holds S_i(b-1)
+    // in registers, P_i V(b) as soon as group i has stored P_i(b).  Nothing here makes one group wait for the other, so
+    // the half-period offset set up at the start (see `do_stagger`) survives: one group exponentiates (MUFU) while the
+    // other loads / reduces / stores.  Neither event is latency critical (both results are needed a whole block later),
+    // so an idle round sleeps instead of stealing issue slots from the softmax warps on this SM sub-partition.
+    const uint32_t tD[2] = {tmem_base, tmem_base + 128};
+    const uint32_t tOo[2] = {tmem_base + 256, tmem_base + 320};
+    const uint32_t tPp[2] = {tmem_base + 384, tmem_base + 448};
+    const uint64_t dq[2] = {dq0, dq1};
+    int nS[2] = {0, 0}, nP[2] = {0, 0};            // next block whose S / P V is to be issued, per group
+    uint32_t sS[2] = {0, 0}, phS[2] = {0, 0};      // kv ring stage / kv_full parity of block nS[i]
+    uint32_t sP[2] = {0, 0};                       // kv ring stage of block nP[i]
+    int seg_first = 0;
+    while (nP[0] < nb || nP[1] < nb) {
+      bool progress = false;
 #pragma unroll
-        for (int k = 0; k < 4; k++) umma_f16(tmem_base + i * 128, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-        umma_commit(&s_full[i]);
-      };
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      issue_s(0, 0);
-      issue_s(1, 0);
-      int seg_first = 0;   // global index of the first block of the current segment
-      for (int it = 0; it < nb; it++) {
-        if (NSEG > 1 && it == nblk[0]) seg_first = nblk[0];
-        const int s = it % F2_KV_STAGES;
-        // S of the next block as soon as the softmax groups hold the current S in registers: the tensor core works
-        // on S(it+1) while the groups exponentiate block it
-        if (it + 1 < nb) {
-          mbar_wait(&kv_full[(it + 1) % F2_KV_STAGES], ((it + 1) / F2_KV_STAGES) & 1);
-          for (int i = 0; i < 2; i++) {
-            mbar_wait(&s_free[i], it & 1);
+      for (int i = 0; i < 2; i++) {
+        if (nS[i] < nb) {
+          bool ok = mbar_test(&kv_full[sS[i]], phS[i]);
+          if (nS[i] > 0) ok = ok && mbar_test(&s_free[i], (uint32_t)(nS[i] - 1) & 1u);
+          if (__all_sync(0xffffffffu, ok)) {
             tc_fence_after();
-            issue_s(i, it + 1);
+            if (elect_one()) {
+              const uint64_t dk = dkv0 + (uint64_t)(sS[i] * ((2 * TILE) >> 4));
+#pragma unroll
+              for (int k = 0; k < 4; k++) umma_f16(tD[i], dq[i] + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+              umma_commit(&s_full[i]);
+            }
+            __syncwarp();
+            if (lane == 0) F2_TRACE(2, nS[i], i);                 // S_i(b) issued
+            nS[i]++;
+            if (++sS[i] == F2_KV_STAGES) { sS[i] = 0; phS[i] ^= 1u; }
+            progress = true;
           }
         }
-        const uint64_t dv = umma_desc_sw128(smem_u32(sKV + s * 2 * TILE + TILE), 1024, 1024);
-        for (int i = 0; i < 2; i++) {
-          mbar_wait(&p_ready[i], it & 1);
-          tc_fence_after();
-          const uint32_t tO = tmem_base + 256 + i * 64;
-          const uint32_t tP = tmem_base + 384 + i * 64;
-          const uint32_t acc0 = it != seg_first ? 1u : 0u;
+        if (nP[i] < nb) {
+          const bool ok = mbar_test(&p_ready[i], (uint32_t)nP[i] & 1u);
+          if (__all_sync(0xffffffffu, ok)) {
+            tc_fence_after();
+            if (NSEG > 1) seg_first = nP[i] >= nblk[0] ? nblk[0] : 0;
+            if (elect_one()) {
+              const uint64_t dv = dkv0 + (uint64_t)(sP[i] * ((2 * TILE) >> 4) + (TILE >> 4));
+              const uint32_t acc0 = nP[i] != seg_first ? 1u : 0u;
 #pragma unroll
-          for (int k = 0; k < 8; k++)     // K = 16 kv tokens = 8 TMEM columns of P, 16 smem rows of V
-            umma_f16_ts(tO, tP + k * 8, dv + (uint64_t)(k * (2048 >> 4)), idesc_o, (k != 0) ? 1u : acc0);
-          umma_commit(&o_done[i]);
+              for (int k = 0; k < 8; k++) {   // K = 16 kv tokens = 8 TMEM columns of P = 32 B inside a V^T atom (4 per atom)
+                const uint64_t dvk = dv + (uint64_t)((k >> 2) * ((TILE / 2) >> 4) + (k & 3) * 2);
+                umma_f16_ts(tOo[i], tPp[i] + k * 8, dvk, idesc_o, (k != 0) ? 1u : acc0);
+              }
+              umma_commit(&o_done[i]);
+              if (nP[i ^ 1] > nP[i]) umma_commit(&kv_empty[sP[i]]);   // the other tile's P V of this block is already in
+            }
+            __syncwarp();
+            if (lane == 0) F2_TRACE(2, nP[i], 2 + i);             // P_i V(b) issued
+            nP[i]++;
+            if (++sP[i] == F2_KV_STAGES) sP[i] = 0;
+            progress = true;
+          }
         }
-        umma_commit(&kv_empty[s]);
       }
+      if (!progress) __nanosleep(64);
     }
-    __syncwarp();
   } else {
     const int grp = (warp - 2) >> 2;                 // query tile handled by this softmax group
     const int q = warp & 3;
@@ -390,9 +434,11 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll 1
       for (int j = 0; j < nblk[sg]; j++, it++) {
         const int valid = p.len[sg] - j * 128;
+        if ((threadIdx.x & 127) == 64) F2_TRACE(grp, it, 0);     // ready for S(it)
         mbar_wait(&s_full[grp], it & 1);
         __syncwarp();
         tc_fence_after();
+        if ((threadIdx.x & 127) == 64) F2_TRACE(grp, it, 1);     // S(it) available
         // ---- the whole 128-column S row goes to registers in one TMEM round trip; the TMEM tile is then free
         uint32_t sr[4][32];
 #pragma unroll
@@ -400,6 +446,7 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&s_free[grp]);
+        if ((threadIdx.x & 127) == 64) F2_TRACE(grp, it, 2);     // S(it) in registers
         float mx = -INFINITY;
         if (valid >= 128) {
           float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // independent chains: the max is latency-bound
@@ -416,6 +463,12 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             for (int i = 0; i < 32; i++)
               if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(sr[c][i]));
         }
+        if (do_stagger) {
+          if (grp == 1) mbar_wait(&exp_done[0], (uint32_t)it & 1u);
+          else if (it > 0) mbar_wait(&exp_done[1], (uint32_t)(it - 1) & 1u);
+          __syncwarp();
+        }
+        if ((threadIdx.x & 127) == 64) F2_TRACE(grp, it, 5);     // MUFU turn acquired
         mx *= p.scale_log2;
         const bool grow = (j > 0) && (mx > m_used + F2_LAZY);
         const float m_old = m_used;
@@ -447,6 +500,8 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
               sr[c][i >> 1] = pack_half2(p0, p1);
             }
         }
+        if (do_stagger) mbar_arrive(&exp_done[grp]);
+        if ((threadIdx.x & 127) == 64) F2_TRACE(grp, it, 3);     // exponentials done
         // the previous P V of this tile must have retired before P (and possibly O) are overwritten
         if (j > 0) {
           mbar_wait(&o_done[grp], (it - 1) & 1);
@@ -480,6 +535,7 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_ready[grp]);
+        if ((threadIdx.x & 127) == 64) F2_TRACE(grp, it, 4);     // P(it) stored
       }
       // ---- segment done: O / l
       mbar_wait(&o_done[grp], (it - 1) & 1);
@@ -811,6 +867,125 @@ temporal_attn16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out,
   }
 }
 
+// ---------------------------------------------------------------- tcgen05.mma issue-rate probe (tests/gpu_probe_mma.py)
+// One thread issues `reps` MMAs of a given shape / operand source / accumulator pattern on garbage operands and times
+// issue -> completion with clock64.  Used to find out what actually paces the attention kernel's small MMAs.
+template <int variant>
+__device__ __forceinline__ void mma_probe_issue(int r, uint32_t tm, uint64_t da, uint64_t db, uint64_t dv) {
+  constexpr uint32_t i128 = umma_idesc_f16(128, 128, 0, 0), i256 = umma_idesc_f16(128, 256, 0, 0),
+                     i64 = umma_idesc_f16(128, 64, 0, 0), i64v = umma_idesc_f16(128, 64, 0, 1);
+  const uint32_t acc = r >= 4 ? 1u : 0u;
+  const uint64_t ko = 2 * (r & 3);
+  switch (variant) {
+    case 0: umma_f16(tm, da + ko, db + ko, i128, acc); break;                              // SS N128, one D
+    case 1: umma_f16(tm + (r & 1) * 128, da + ko, db + ko, i128, acc); break;              // SS N128, 2 D
+    case 2: umma_f16(tm, da + ko, db + ko, i256, acc); break;                              // SS N256, one D
+    case 3: umma_f16(tm, da + ko, db + ko, i64, acc); break;                               // SS N64, one D
+    case 4: umma_f16(tm + (r & 3) * 64, da + ko, db + ko, i64, acc); break;                // SS N64, 4 D
+    case 5: umma_f16_ts(tm, tm + 384 + (r & 7) * 8, dv + (uint64_t)((r & 7) * 128), i64v, acc); break;          // TS N64 MN-major B
+    case 6: umma_f16_ts(tm + (r & 1) * 64, tm + 384 + (r & 7) * 8, dv + (uint64_t)((r & 7) * 128), i64v, acc); break;
+    case 7: umma_f16_ts(tm + (r & 3) * 64, tm + 384 + (r & 7) * 8, dv + (uint64_t)((r & 7) * 128), i64v, acc); break;
+    case 8: umma_f16(tm + (r & 3) * 128, da + ko, db + ko, i128, acc); break;              // SS N128, 4 D
+    case 9: umma_f16_ts(tm, tm + 384 + (r & 7) * 8, db + ko, i64, acc); break;             // TS N64 K-major B
+    case 10: umma_f16_ts(tm, tm + 256 + (r & 7) * 8, db + ko, i128, acc); break;           // TS N128 K-major B
+    case 11: umma_f16_ts(tm, tm + 256 + (r & 7) * 8, db + ko, i256, acc); break;           // TS N256
+    default: break;
+  }
+}
+
+// mode 0: a single diverged thread issues (if (threadIdx.x == 0) ...); mode 1: the whole warp runs the loop and one
+// elected lane issues (uniform control flow, operands in uniform registers)
+template <int VARIANT>
+__global__ void __launch_bounds__(128, 1) mma_probe_kernel(int reps, int mode, long long* out) {
+  extern __shared__ __align__(1024) uint8_t psm[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(psm)[i] = 0x3c003c00u;   // 1.0h
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (threadIdx.x < 32) tmem_alloc<512>(&slot);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = slot;
+  const uint64_t da = umma_desc_sw128(smem_u32(psm), 16, 1024);                 // K-major 128 x 64
+  const uint64_t db = umma_desc_sw128(smem_u32(psm) + 32768, 16, 1024);         // K-major up to 256 x 64
+  const uint64_t dv = umma_desc_sw128(smem_u32(psm) + 65536, 1024, 1024);       // MN-major 128 x 64
+  if (mode == 0) {
+    if (threadIdx.x == 0) {
+      const long long t0 = clock64();
+      for (int r = 0; r < reps; r++) mma_probe_issue<VARIANT>(r, tm, da, db, dv);
+      const long long t1 = clock64();
+      umma_commit(&bar);
+      mbar_wait(&bar, 0);
+      const long long t2 = clock64();
+      out[blockIdx.x * 2] = t1 - t0;
+      out[blockIdx.x * 2 + 1] = t2 - t0;
+    }
+  } else if (threadIdx.x < 32) {
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; r++) {
+      if (elect_one()) mma_probe_issue<VARIANT>(r, tm, da, db, dv);
+      __syncwarp();
+    }
+    const long long t1 = clock64();
+    if (elect_one()) umma_commit(&bar);
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    const long long t2 = clock64();
+    if (threadIdx.x == 0) {
+      out[blockIdx.x * 2] = t1 - t0;
+      out[blockIdx.x * 2 + 1] = t2 - t0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (threadIdx.x < 32) tmem_dealloc<512>(tm);
+}
+
+// ---------------------------------------------------------------- V -> V^T (the P V MMA wants its B operand K-major)
+// V rows [nbatch][len] of pitch elements, head h at columns [h*64, h*64+64)  ->  VT [nbatch][heads*64][len_pad], kv contiguous.
+__global__ void __launch_bounds__(256) transpose_v_kernel(const __half* __restrict__ V, int pitch, int len, int heads,
+                                                          __half* __restrict__ VT, int len_pad) {
+  __shared__ __align__(16) __half tile[64][72];
+  const int kv0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+  const int t = threadIdx.x;
+  {
+    const int r = t >> 2;
+    const __half* src = V + ((int64_t)b * len + kv0 + r) * pitch + h * 64;
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int c = (t & 3) + 4 * u;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (kv0 + r < len) v = __ldg(reinterpret_cast<const uint4*>(src) + c);
+      *reinterpret_cast<uint4*>(&tile[r][c * 8]) = v;
+    }
+  }
+  __syncthreads();
+  {
+    const int d = t >> 2;
+    __half* dst = VT + (((int64_t)b * heads + h) * 64 + d) * len_pad + kv0;
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int c = (t & 3) + 4 * u;
+      if (kv0 + c * 8 >= len_pad) continue;
+      __align__(16) __half o[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) o[i] = tile[c * 8 + i][d];
+      *reinterpret_cast<uint4*>(dst + c * 8) = *reinterpret_cast<const uint4*>(o);
+    }
+  }
+}
+
+const CUtensorMap* vt_map(const __half* base, int len, int len_pad, int width, int batches) {
+  const uint64_t dims[5] = {(uint64_t)len, (uint64_t)width, (uint64_t)batches, 1, 1};
+  const uint64_t pb = (uint64_t)len_pad * 2;
+  const uint64_t str[4] = {pb, pb * width, pb * width * batches, pb * width * batches};
+  const uint32_t box[5] = {64, 64, 1, 1, 1};
+  return get_tmap(base, dims, str, box);
+}
+
 const CUtensorMap* rows_map(const __half* base, int width, int pitch, int rows, int batches) {
   const uint64_t dims[5] = {(uint64_t)width, (uint64_t)rows, (uint64_t)batches, 1, 1};
   const uint64_t pb = (uint64_t)pitch * 2;
@@ -821,11 +996,37 @@ const CUtensorMap* rows_map(const __half* base, int width, int pitch, int rows, 
 
 }  // namespace
 
+void transpose_v(const __half* V, int pitch, int len, int nbatch, int heads, __half* VT, int len_pad, cudaStream_t st) {
+  MUDG_REQUIRE(pitch % 8 == 0 && len_pad % 8 == 0 && len_pad >= len && len > 0, "transpose_v: pitch %d len %d pad %d", pitch, len, len_pad);
+  MUDG_REQUIRE(((reinterpret_cast<uintptr_t>(V) | reinterpret_cast<uintptr_t>(VT)) & 15) == 0, "transpose_v: alignment");
+  dim3 grid((len_pad + 63) / 64, heads, nbatch);
+  transpose_v_kernel<<<grid, 256, 0, st>>>(V, pitch, len, heads, VT, len_pad);
+  MUDG_CUDA(cudaGetLastError());
+}
+
 void flash_attention_simt(const FlashArgs& a, cudaStream_t st) {
   const int64_t total = (int64_t)a.F * a.heads * a.Nq;
   flash_simt_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(a);
   MUDG_CUDA(cudaGetLastError());
 }
+
+void mma_probe(int variant, int reps, int ctas, int mode, long long* out, cudaStream_t st) {
+#define MUDG_PROBE_CASE(V)                                                                                         \
+  case V:                                                                                                           \
+    MUDG_CUDA(cudaFuncSetAttribute(mma_probe_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));  \
+    mma_probe_kernel<V><<<ctas, 128, 96 * 1024, st>>>(reps, mode, out);                                            \
+    break;
+  switch (variant) {
+    MUDG_PROBE_CASE(0) MUDG_PROBE_CASE(1) MUDG_PROBE_CASE(2) MUDG_PROBE_CASE(3) MUDG_PROBE_CASE(4) MUDG_PROBE_CASE(5)
+    MUDG_PROBE_CASE(6) MUDG_PROBE_CASE(7) MUDG_PROBE_CASE(8) MUDG_PROBE_CASE(9) MUDG_PROBE_CASE(10) MUDG_PROBE_CASE(11)
+    default: MUDG_REQUIRE(false, "mma_probe: variant %d", variant);
+  }
+#undef MUDG_PROBE_CASE
+  MUDG_CUDA(cudaGetLastError());
+}
+
+static long long* g_flash_trace = nullptr;
+void flash_set_trace(long long* buf) { g_flash_trace = buf; }
 
 void flash_attention(const FlashArgs& a, cudaStream_t st) {
   static const bool force_simt = [] {
@@ -835,6 +1036,10 @@ void flash_attention(const FlashArgs& a, cudaStream_t st) {
   if (force_simt) return flash_attention_simt(a, st);
   MUDG_REQUIRE(a.nseg == 1 || a.nseg == 2, "nseg");
   MUDG_REQUIRE(a.q_pitch % 8 == 0 && a.o_pitch % 8 == 0, "pitch alignment");
+  static const bool use_v1 = [] {
+    const char* e = getenv("MUDG_FLASH_V1");
+    return e && e[0] == '1';
+  }();
   const int width = a.heads * 64;
   const CUtensorMap* mq = rows_map(a.Q, width, a.q_pitch, a.Nq, a.F);
   const CUtensorMap* mo = rows_map(a.O, width, a.o_pitch, a.Nq, a.F);
@@ -843,18 +1048,25 @@ void flash_attention(const FlashArgs& a, cudaStream_t st) {
   FaParams p{};
   p.nseg = a.nseg;
   p.scale_log2 = a.scale * 1.4426950408889634f;
+  static const int stagger_env = [] {
+    const char* e = getenv("MUDG_FLASH_STAGGER");
+    return e ? atoi(e) : 1;
+  }();
+  p.stagger = stagger_env;
+  p.trace = g_flash_trace;
   for (int i = 0; i < 2; i++) {
     const FlashSeg& s = a.seg[i < a.nseg ? i : 0];
     MUDG_REQUIRE(s.pitch % 8 == 0 && s.len > 0, "kv segment");
     mk[i] = rows_map(s.K, width, s.pitch, s.len, s.nbatch);
-    mv[i] = rows_map(s.V, width, s.pitch, s.len, s.nbatch);
+    if (use_v1) {
+      mv[i] = rows_map(s.V, width, s.pitch, s.len, s.nbatch);
+    } else {
+      MUDG_REQUIRE(s.VT != nullptr && s.vt_pitch % 8 == 0 && s.vt_pitch >= s.len, "flash attention needs V^T (transpose_v) of every kv segment");
+      mv[i] = vt_map(s.VT, s.len, s.vt_pitch, width, s.nbatch);
+    }
     p.len[i] = s.len;
     p.kv_div[i] = s.kv_div > 0 ? s.kv_div : 1;
   }
-  static const bool use_v1 = [] {
-    const char* e = getenv("MUDG_FLASH_V1");
-    return e && e[0] == '1';
-  }();
   static bool attr = false;
   if (!attr) {
     MUDG_CUDA(cudaFuncSetAttribute(flash_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));

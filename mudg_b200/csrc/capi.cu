@@ -193,8 +193,40 @@ MUDG_EXPORT int mudg_test_flash(const void* Q, int q_pitch, void* O, int o_pitch
   a.seg[0].pitch = pitch0; a.seg[0].len = len0; a.seg[0].nbatch = nbatch0; a.seg[0].kv_div = div0;
   a.seg[1].K = static_cast<const __half*>(K1); a.seg[1].V = static_cast<const __half*>(V1);
   a.seg[1].pitch = pitch1; a.seg[1].len = len1; a.seg[1].nbatch = nbatch1; a.seg[1].kv_div = div1;
-  if (backend == 0) flash_attention(a, S(stream));
-  else flash_attention_simt(a, S(stream));
+  if (backend == 0) {
+    // the tcgen05 kernel reads V transposed: build V^T of each segment in a (grow-only) scratch buffer of the test hook
+    static __half* scratch[2] = {nullptr, nullptr};
+    static size_t scratch_bytes[2] = {0, 0};
+    for (int i = 0; i < a.nseg; i++) {
+      FlashSeg& sg = a.seg[i];
+      const int pad = (sg.len + 7) / 8 * 8;
+      const size_t need = sizeof(__half) * (size_t)sg.nbatch * heads * 64 * pad;
+      if (scratch_bytes[i] < need) {
+        MUDG_CUDA(cudaDeviceSynchronize());
+        cudaFree(scratch[i]);
+        MUDG_CUDA(cudaMalloc(&scratch[i], need));
+        scratch_bytes[i] = need;
+      }
+      transpose_v(sg.V, sg.pitch, sg.len, sg.nbatch, heads, scratch[i], pad, S(stream));
+      sg.VT = scratch[i];
+      sg.vt_pitch = pad;
+    }
+    flash_attention(a, S(stream));
+  } else {
+    flash_attention_simt(a, S(stream));
+  }
+  MUDG_API_END
+}
+
+MUDG_EXPORT int mudg_test_mma_probe(int variant, int reps, int ctas, int mode, void* out, void* stream) {
+  MUDG_API_BEGIN
+  mma_probe(variant, reps, ctas, mode, static_cast<long long*>(out), S(stream));
+  MUDG_API_END
+}
+
+MUDG_EXPORT int mudg_test_flash_trace(void* buf) {
+  MUDG_API_BEGIN
+  flash_set_trace(static_cast<long long*>(buf));
   MUDG_API_END
 }
 

@@ -168,6 +168,8 @@ Model::~Model() {
   for (auto& kv : kv_) {
     cudaFree(kv.second.text);
     cudaFree(kv.second.img);
+    cudaFree(kv.second.text_vt);
+    cudaFree(kv.second.img_vt);
   }
 }
 
@@ -541,16 +543,21 @@ Act Model::spatial_transformer(const Act& xin, const Layer& l) {   // attention.
   Act qkv = linear(x, tb + ".attn1.qkv.weight", "", nullptr, false, 1.f, s1);
   release_bytes(s1);
   Act a1 = alloc(xin.B, xin.T, xin.H, xin.W, C);
+  const int hw_pad = round_up(HW, 8);
+  __half* vt = static_cast<__half*>(alloc_bytes(sizeof(__half) * (size_t)F * C * hw_pad));   // V^T [F][C][HW]
   if (live()) {
+    transpose_v(qkv.p + 2 * C, 3 * C, HW, F, l.heads, vt, hw_pad, st_);
     FlashArgs fa;
     fa.Q = qkv.p; fa.q_pitch = 3 * C; fa.O = a1.p; fa.o_pitch = C; fa.F = F; fa.Nq = HW; fa.heads = l.heads;
     fa.nseg = 1;
     fa.seg[0].K = qkv.p + C; fa.seg[0].V = qkv.p + 2 * C; fa.seg[0].pitch = 3 * C; fa.seg[0].len = HW;
+    fa.seg[0].VT = vt; fa.seg[0].vt_pitch = hw_pad;
     fa.seg[0].nbatch = F; fa.seg[0].kv_div = 1;
     fa.scale = 0.125f;
     flash_attention(fa, st_);
-    launches++;
+    launches += 2;
   }
+  release_bytes(vt);
   release(qkv);
   Act x1 = linear(a1, tb + ".attn1.to_out.0.weight", tb + ".attn1.to_out.0.bias", &x);
   release(a1);
@@ -569,8 +576,10 @@ Act Model::spatial_transformer(const Act& xin, const Layer& l) {   // attention.
     fa.Q = q.p; fa.q_pitch = C; fa.O = a2.p; fa.o_pitch = C; fa.F = F; fa.Nq = HW; fa.heads = l.heads;
     fa.nseg = 2;
     fa.seg[0].K = kc.text; fa.seg[0].V = kc.text + C; fa.seg[0].pitch = 2 * C; fa.seg[0].len = ucfg_.text_context_len;
+    fa.seg[0].VT = kc.text_vt; fa.seg[0].vt_pitch = round_up(ucfg_.text_context_len, 8);
     fa.seg[0].nbatch = N_; fa.seg[0].kv_div = T_real_;
     fa.seg[1].K = kc.img; fa.seg[1].V = kc.img + C; fa.seg[1].pitch = 2 * C;
+    fa.seg[1].VT = kc.img_vt; fa.seg[1].vt_pitch = round_up(ctx_per_frame_ ? 16 : ctx_Limg_, 8);
     if (ctx_per_frame_) { fa.seg[1].len = 16; fa.seg[1].nbatch = N_ * T_real_; fa.seg[1].kv_div = 1; }
     else { fa.seg[1].len = ctx_Limg_; fa.seg[1].nbatch = N_; fa.seg[1].kv_div = T_real_; }
     fa.scale = 0.125f;
@@ -757,6 +766,16 @@ void Model::set_context(const void* ctx, int dtype, int N, int L, int T, cudaStr
       tapgemm(g, st);
       launches++;
     }
+    // V^T of both segments for the tcgen05 attention kernel ([batches][C][len padded to 8], kv contiguous)
+    const int heads = C / 64;
+    const int tl_pad = round_up(tl, 8);
+    const int li = per_frame ? 16 : Limg, li_pad = round_up(li, 8), nbi = per_frame ? N * T : N;
+    const size_t tvb = sizeof(__half) * (size_t)N * C * tl_pad, ivb = sizeof(__half) * (size_t)nbi * C * li_pad;
+    if (kc.text_vt_bytes < tvb) { cudaFree(kc.text_vt); MUDG_CUDA(cudaMalloc(&kc.text_vt, tvb)); kc.text_vt_bytes = tvb; realloc = true; }
+    if (kc.img_vt_bytes < ivb) { cudaFree(kc.img_vt); MUDG_CUDA(cudaMalloc(&kc.img_vt, ivb)); kc.img_vt_bytes = ivb; realloc = true; }
+    transpose_v(kc.text + C, 2 * C, tl, N, heads, kc.text_vt, tl_pad, st);
+    transpose_v(kc.img + C, 2 * C, li, nbi, heads, kc.img_vt, li_pad, st);
+    launches += 2;
   };
   for (auto& b : in_blocks_) for (auto& l : b.layers) visit(l);
   for (auto& l : mid_.layers) visit(l);

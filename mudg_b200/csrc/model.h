@@ -62,6 +62,9 @@ struct KvCache {          // per SpatialTransformer: [N][77][2C] and [Nimg_batch
   __half* text = nullptr;
   __half* img = nullptr;
   size_t text_bytes = 0, img_bytes = 0;
+  __half* text_vt = nullptr;   // V halves transposed for the tcgen05 kernel: [N][C][80], [Nimg_batches][C][Limg padded to 8]
+  __half* img_vt = nullptr;
+  size_t text_vt_bytes = 0, img_vt_bytes = 0;
 };
 
 class Model {

@@ -37,6 +37,8 @@ void small_linear(const float* x, const __half* W, const float* bias, float* y, 
 struct FlashSeg {
   const __half* K = nullptr;
   const __half* V = nullptr;
+  const __half* VT = nullptr;   // V transposed by transpose_v: [nbatch][heads*64][vt_pitch], kv contiguous (the tcgen05 kernel reads this)
+  int vt_pitch = 0;             // >= len, multiple of 8
   int pitch = 0;       // row pitch (elements)
   int len = 0;         // tokens per kv batch
   int nbatch = 0;      // number of kv batches
@@ -53,7 +55,10 @@ struct FlashArgs {
   float scale = 0.125f;
 };
 void flash_attention(const FlashArgs& a, cudaStream_t st);
-void flash_attention_simt(const FlashArgs& a, cudaStream_t st);   // CUDA-core checker (debug / MUDG_FORCE_SIMT)
+void transpose_v(const __half* V, int pitch, int len, int nbatch, int heads, __half* VT, int len_pad, cudaStream_t st);
+void flash_attention_simt(const FlashArgs& a, cudaStream_t st);
+void mma_probe(int variant, int reps, int ctas, int mode, long long* out, cudaStream_t st);   // debug: tcgen05.mma issue-rate probe
+void flash_set_trace(long long* buf);   // debug: clock64 time line of CTA 0 ([3][96][8] int64), null = off   // CUDA-core checker (debug / MUDG_FORCE_SIMT)
 
 // Temporal self-attention over T for every (b, h, w, head): qkv rows [B*T*HW][3*inner] (q | k | v), out [rows][inner]
 void temporal_attention(const __half* qkv, __half* out, int B, int T, int HW, int heads, float scale, cudaStream_t st);

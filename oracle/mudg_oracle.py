@@ -716,3 +716,30 @@ def ddim_sample(unet_sd: SD, ucfg: UNetCfg, tab: DiffusionTables, *, S: int, sha
             v_u = unet_forward(unet_sd, ucfg, xc, ts, class_label, uc_context, fs)
         x, _ = ddim_step(tab, sch, index, x, v_c, v_u, draw(i + 1), cfg_scale, guidance_rescale)
     return x
+
+
+@torch.no_grad()
+def ddim_sample_multicond(unet_sd: SD, ucfg: UNetCfg, tab: DiffusionTables, *, S: int, shape, c_concat: Tensor,
+                          context: Tensor, uc_context: Tensor, uc_img_context: Tensor, class_label: Tensor, fs: Tensor,
+                          cfg_scale: float, cfg_img: Optional[float], guidance_rescale: float = 0.0, eta: float = 1.0,
+                          spacing: str = "uniform_trailing", noises: Optional[List[Tensor]] = None) -> Tensor:
+    """DDIMSampler_multicond (ddim_multiplecond.py:210-237): three UNet evaluations per step,
+    v = v_u + cfg_img (v_ui - v_u) + s (v_c - v_ui), then the single-guidance update (ddim_multiplecond.py:238-284)."""
+    sch = make_ddim_schedule(tab, S, spacing, eta)
+    draw = (lambda i: noises[i]) if noises is not None else (lambda i: torch.randn(shape))
+    if cfg_img is None:
+        cfg_img = cfg_scale
+    x = draw(0)
+    B = shape[0]
+    for i, step in enumerate(np.flip(sch.timesteps)):
+        index = S - i - 1
+        ts = torch.full((B,), int(step), dtype=torch.long)
+        xc = torch.cat([x, c_concat], dim=1)
+        v_c = unet_forward(unet_sd, ucfg, xc, ts, class_label, context, fs)
+        v_u = unet_forward(unet_sd, ucfg, xc, ts, class_label, uc_context, fs)
+        v_ui = unet_forward(unet_sd, ucfg, xc, ts, class_label, uc_img_context, fs)
+        v = v_u + cfg_img * (v_ui - v_u) + cfg_scale * (v_c - v_ui)
+        if guidance_rescale > 0.0:
+            v = rescale_noise_cfg(v, v_c, guidance_rescale)
+        x, _ = ddim_step(tab, sch, index, x, v, None, draw(i + 1), 1.0, 0.0)
+    return x

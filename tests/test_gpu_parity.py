@@ -257,8 +257,11 @@ def test_postdecode_full_size_properties():
     assert torch.equal(rgb2[2], rgb[2]) and torch.equal(cls2[2], cls[2])   # semantic: idempotent
     pal = torch.tensor(P.PALETTE, dtype=torch.uint8, device="cuda")
     assert torch.equal(pal[cls[2].long()].permute(0, 3, 1, 2), rgb[2])
-    col_u8 = postdecode(frames[1:2], [0])[0][0].float()               # depth == mean of the colour conversion / 255
-    assert torch.equal(depth[1], col_u8.sum(1) / 3 / 255)
+    # depth == mean of the colour conversion / 255, whole clip (host fp32 division: torch's CUDA `/ scalar` multiplies by
+    # the reciprocal and is not the reference's arithmetic)
+    col_u8 = postdecode(frames[1:2], [0])[0][0].cpu().numpy().astype(np.float32)
+    want = (col_u8.sum(1) / np.float32(3.0)) / np.float32(255.0)
+    assert depth[1].cpu().numpy().tobytes() == want.tobytes()
     assert float(depth[1].min()) >= 0.0 and float(depth[1].max()) <= 1.0
 
 
