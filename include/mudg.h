@@ -26,7 +26,7 @@ extern "C" {
 typedef struct MudgCtx MudgCtx;
 
 enum { MUDG_F32 = 0, MUDG_F16 = 1, MUDG_U8 = 2 /* mudg_postdecode input only */ };
-enum { MUDG_UNET = 0, MUDG_VAE = 1 };
+enum { MUDG_UNET = 0, MUDG_VAE = 1, MUDG_RESAMPLER = 2 };
 
 /* unet_config.params of configs/stage{1,2}-*_infer.yaml:26-56 (only the keys that shape the graph) */
 typedef struct {
@@ -98,6 +98,13 @@ enum { MUDG_POST_COLOR = 0, MUDG_POST_DEPTH = 1, MUDG_POST_SEMANTIC = 2 };
 MUDG_EXPORT int mudg_postdecode(const void* frames, int dtype, int B, int T, int H, int W, const int* modes,
                                 void* rgb_u8, void* depth_f32, void* class_u8, void* stream);
 
+/* "Next" row: Resampler.forward (lvdm/modules/encoders/resampler.py:131-144, with
+ * PerceiverAttention :48-101 and FeedForward :31-37) -- the once-per-clip projection of the image-encoder tokens to the
+ * UNet's image context.  Weights: state_dict keys of the reference module loaded with which = MUDG_RESAMPLER
+ * ("latents" as [num_queries*video_length, dim]); dimensions are derived from the shapes at mudg_finalize_weights.
+ * x [B, L, embedding_dim] (MUDG_F32 | MUDG_F16) -> out [B, num_queries*video_length, output_dim] fp32. */
+MUDG_EXPORT int mudg_resampler_forward(MudgCtx* ctx, const void* x, int dtype, int B, int L, void* out, void* stream);
+
 /* colormap(image, cmap="Spectral", bytes=True) of the reference (eval_tools.py:137-250, method_custom): map fp32 [n] in
  * [0,1] (clamped) -> out_u8 [n, 3] (HWC).  Used for the ground-truth depth visualisation (eval_tools.py:82). */
 MUDG_EXPORT int mudg_colormap_spectral(const void* map_f32, int64_t n, void* out_u8, void* stream);
@@ -122,6 +129,8 @@ MUDG_EXPORT int mudg_test_flash(const void* Q, int q_pitch, void* O, int o_pitch
                                 int backend, void* stream);
 /* debug: device buffer [3][96][8] int64 receiving the clock64 time line of CTA 0 of the next flash launches (NULL = off) */
 MUDG_EXPORT int mudg_test_flash_trace(void* buf);
+/* debug: device buffer [4][64][8] int64 receiving the clock64 time line of CTA 0 of the next pair-GEMM launches */
+MUDG_EXPORT int mudg_test_gemm_trace(void* buf);
 /* debug: tcgen05.mma issue-rate probe; out = device int64 [ctas][2] (clocks until issued, until complete) */
 MUDG_EXPORT int mudg_test_mma_probe(int variant, int reps, int ctas, int mode, void* out, void* stream);
 MUDG_EXPORT int mudg_test_temporal_attn(const void* qkv, void* out, int B, int T, int HW, int heads, float scale,

@@ -41,6 +41,19 @@ class DiffusionWrapper(nn.Module):
         self.diffusion_model = instantiate_from_config(diff_model_config)
         self.conditioning_key = conditioning_key
 
+    def _context(self, c_crossattn):
+        """torch.cat(c_crossattn, 1) of the reference (ddpm3d.py:1322), but the SAME tensor object for the same inputs:
+        the context is constant over the DDIM steps and the UNet keys its cross-attention K/V cache on the tensor, so a
+        fresh concatenation per step would recompute all 16 layers' K/V (and synchronise) fifty times per clip."""
+        if len(c_crossattn) == 1:
+            return c_crossattn[0]
+        key = tuple((id(c), c._version) for c in c_crossattn)
+        cache = getattr(self, "_ctx_cache", None)
+        if cache is None or cache[0] != key:
+            cache = (key, torch.cat(c_crossattn, 1), list(c_crossattn))
+            self._ctx_cache = cache
+        return cache[1]
+
     def forward(self, x, t, c_label=None, c_concat=None, c_crossattn=None, c_adm=None, s=None, mask=None, **kwargs):
         key = self.conditioning_key
         if key is None:
@@ -48,11 +61,10 @@ class DiffusionWrapper(nn.Module):
         if key == "concat":
             return self.diffusion_model(torch.cat([x] + c_concat, dim=1), t, **kwargs)
         if key == "crossattn":
-            return self.diffusion_model(x, t, context=torch.cat(c_crossattn, 1), **kwargs)
+            return self.diffusion_model(x, t, context=self._context(c_crossattn), **kwargs)
         if key == "hybrid":
             xc = torch.cat([x] + c_concat, dim=1)            # [b, 4+8, t, h, w]
-            cc = torch.cat(c_crossattn, 1)
-            return self.diffusion_model(xc, t, c_label=c_label, context=cc, **kwargs)
+            return self.diffusion_model(xc, t, c_label=c_label, context=self._context(c_crossattn), **kwargs)
         raise NotImplementedError(f"conditioning_key {key!r} is not used by the MuDG sampler path")
 
 

@@ -5,7 +5,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmudg_sm100.so")
+LIB_PATH = os.environ.get("MUDG_LIB_PATH") or os.path.join(_HERE, "libmudg_sm100.so")   # override: A/B builds of the same ABI
 _lib = None
 
 

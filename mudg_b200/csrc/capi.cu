@@ -55,7 +55,9 @@ MUDG_EXPORT int mudg_load_weight(MudgCtx* ctx, int which, const char* key, const
                                  const int64_t* shape, int ndim, void* stream) {
   MUDG_API_BEGIN
   MUDG_REQUIRE(ctx && key && dev_ptr && shape, "null argument");
-  (which == MUDG_VAE ? ctx->model.vae_w : ctx->model.unet_w).load(key, dev_ptr, dtype, shape, ndim, S(stream));
+  MUDG_REQUIRE(which == MUDG_UNET || which == MUDG_VAE || which == MUDG_RESAMPLER, "unknown weight set %d", which);
+  WeightStore& ws = which == MUDG_VAE ? ctx->model.vae_w : (which == MUDG_RESAMPLER ? ctx->model.res_w : ctx->model.unet_w);
+  ws.load(key, dev_ptr, dtype, shape, ndim, S(stream));
   MUDG_API_END
 }
 
@@ -123,6 +125,14 @@ MUDG_EXPORT int mudg_postdecode(const void* frames, int dtype, int B, int T, int
   MUDG_REQUIRE(H >= 1 && W >= 1, "postdecode: empty frame");
   postdecode(frames, dtype, static_cast<uint8_t*>(rgb_u8), static_cast<float*>(depth_f32),
              static_cast<uint8_t*>(class_u8), B, T, (int64_t)H * W, modes, S(stream));
+  MUDG_API_END
+}
+
+MUDG_EXPORT int mudg_resampler_forward(MudgCtx* ctx, const void* x, int dtype, int B, int L, void* out, void* stream) {
+  MUDG_API_BEGIN
+  MUDG_REQUIRE(ctx && x && out, "null argument");
+  MUDG_REQUIRE(dtype == MUDG_F32 || dtype == MUDG_F16, "resampler: dtype %d", dtype);
+  ctx->model.resampler_forward(x, dtype, B, L, out, S(stream));
   MUDG_API_END
 }
 
@@ -215,6 +225,12 @@ MUDG_EXPORT int mudg_test_flash(const void* Q, int q_pitch, void* O, int o_pitch
   } else {
     flash_attention_simt(a, S(stream));
   }
+  MUDG_API_END
+}
+
+MUDG_EXPORT int mudg_test_gemm_trace(void* buf) {
+  MUDG_API_BEGIN
+  gemm_set_trace(static_cast<long long*>(buf));
   MUDG_API_END
 }
 

@@ -506,6 +506,29 @@ void im2col_s2(const __half* x, __half* y, int F, int H, int W, int C, int pad, 
   MUDG_CUDA(cudaGetLastError());
 }
 
+// exact (erf) GELU in place, fp16 (the Resampler's FeedForward, resampler.py:31-37: nn.GELU())
+__global__ void gelu_inplace_kernel(__half* __restrict__ x, int64_t n8) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    uint4 v = reinterpret_cast<uint4*>(x)[i];
+    __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      float2 f = __half22float2(h[k]);
+      f.x = 0.5f * f.x * (1.f + erff(f.x * 0.70710678118654752f));
+      f.y = 0.5f * f.y * (1.f + erff(f.y * 0.70710678118654752f));
+      h[k] = __floats2half2_rn(f.x, f.y);
+    }
+    reinterpret_cast<uint4*>(x)[i] = v;
+  }
+}
+void gelu_inplace(__half* x, int64_t n, cudaStream_t st) {
+  MUDG_REQUIRE(n % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "gelu_inplace: alignment");
+  const int64_t n8 = n / 8;
+  const int blocks = (int)std::min<int64_t>((n8 + 255) / 256, (int64_t)sm_count() * 8);
+  gelu_inplace_kernel<<<blocks, 256, 0, st>>>(x, n8);
+  MUDG_CUDA(cudaGetLastError());
+}
+
 void softmax_rows(__half* x, int64_t rows, int n, cudaStream_t st) {
   softmax_rows_kernel<<<(unsigned)rows, 256, 0, st>>>(x, rows, n);
   MUDG_CUDA(cudaGetLastError());

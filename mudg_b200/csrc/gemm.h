@@ -60,6 +60,7 @@ void tapgemm_generic(const TapGemmGeneric& g, cudaStream_t st);
 // dispatch: tensor cores unless MUDG_FORCE_SIMT=1 (debug) or the layer is not eligible
 void tapgemm(const TapGemm& g, cudaStream_t st);
 
+void gemm_set_trace(long long* buf);   // debug: clock64 time line of the pair GEMM's CTA 0 ([4][64][8] int64), null = off
 void gemm_profile_enable(bool on);
 bool gemm_profile_active();
 void gemm_profile_read(double* ms_total, double* flops_total, int64_t* launches);

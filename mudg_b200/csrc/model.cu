@@ -3,6 +3,8 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <cstdio>
+#include <ctime>
 
 namespace mudg {
 
@@ -171,6 +173,8 @@ Model::~Model() {
     cudaFree(kv.second.text_vt);
     cudaFree(kv.second.img_vt);
   }
+  cudaFree(ctx_text_stage_);
+  cudaFree(ctx_img_stage_);
 }
 
 // mirrors UNetModel.__init__ (openaimodel3d.py:398-565)
@@ -248,6 +252,31 @@ void Model::build_plan() {
 }
 
 void Model::finalize(int which, cudaStream_t st) {
+  if (which == MUDG_RESAMPLER) {
+    // touch every key Resampler.forward needs and derive the dimensions from the shapes (resampler.py:104-129)
+    WeightStore& w = res_w;
+    rs_ = ResamplerDims{};
+    rs_.nq = w.W("latents").O; rs_.dim = w.W("latents").I;
+    rs_.emb = w.W("proj_in.weight").I; rs_.outd = w.W("proj_out.weight").O;
+    MUDG_REQUIRE(w.W("proj_in.weight").O == rs_.dim && w.W("proj_out.weight").I == rs_.dim, "Resampler: proj_in / proj_out width");
+    w.V("proj_in.bias"); w.V("proj_out.bias"); w.V("norm_out.weight"); w.V("norm_out.bias");
+    while (w.hasW("layers." + std::to_string(rs_.depth) + ".0.to_q.weight")) {
+      const std::string a = "layers." + std::to_string(rs_.depth) + ".0", f = "layers." + std::to_string(rs_.depth) + ".1";
+      const int inner = w.W(a + ".to_q.weight").O;
+      MUDG_REQUIRE(inner % 64 == 0 && w.W(a + ".to_kv.weight").O == 2 * inner && w.W(a + ".to_out.weight").I == inner,
+                   "Resampler layer %d: dim_head must be 64 (inner %d)", rs_.depth, inner);
+      MUDG_REQUIRE(rs_.depth == 0 || inner == rs_.inner, "Resampler: layers differ");
+      rs_.inner = inner; rs_.heads = inner / 64;
+      rs_.ff = w.W(f + ".1.weight").O;
+      MUDG_REQUIRE(w.W(f + ".3.weight").I == rs_.ff, "Resampler FF width");
+      for (const char* n : {".norm1", ".norm2"}) { w.V(a + n + ".weight"); w.V(a + n + ".bias"); }
+      w.V(f + ".0.weight"); w.V(f + ".0.bias");
+      rs_.depth++;
+    }
+    MUDG_REQUIRE(rs_.depth > 0, "Resampler: no layers loaded");
+    res_ready_ = true;
+    return;
+  }
   if (which == MUDG_VAE) {
     // touch every key Decoder.forward needs (throws on a missing one)
     const MudgVaeConfig& v = vcfg_;
@@ -544,9 +573,10 @@ Act Model::spatial_transformer(const Act& xin, const Layer& l) {   // attention.
   release_bytes(s1);
   Act a1 = alloc(xin.B, xin.T, xin.H, xin.W, C);
   const int hw_pad = round_up(HW, 8);
-  __half* vt = static_cast<__half*>(alloc_bytes(sizeof(__half) * (size_t)F * C * hw_pad));   // V^T [F][C][HW]
+  static const bool no_vt = [] { const char* e = getenv("MUDG_NO_VT"); return e && e[0] == '1'; }();   // debug (with MUDG_FLASH_V1=1)
+  __half* vt = static_cast<__half*>(alloc_bytes(no_vt ? 1024 : sizeof(__half) * (size_t)F * C * hw_pad));   // V^T [F][C][HW]
   if (live()) {
-    transpose_v(qkv.p + 2 * C, 3 * C, HW, F, l.heads, vt, hw_pad, st_);
+    if (!no_vt) transpose_v(qkv.p + 2 * C, 3 * C, HW, F, l.heads, vt, hw_pad, st_);
     FlashArgs fa;
     fa.Q = qkv.p; fa.q_pitch = 3 * C; fa.O = a1.p; fa.o_pitch = C; fa.F = F; fa.Nq = HW; fa.heads = l.heads;
     fa.nseg = 1;
@@ -737,16 +767,40 @@ void Model::unet_body(const void* x, const int64_t* t, const int64_t* label, con
 }
 
 // ================================================================ context (cross-attention K/V cache)
+static bool dbg_timing() {
+  static const bool on = [] { const char* e = getenv("MUDG_DEBUG_TIMING"); return e && e[0] == '1'; }();
+  return on;
+}
+static double now_ms() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 void Model::set_context(const void* ctx, int dtype, int N, int L, int T, cudaStream_t st) {
   MUDG_REQUIRE(unet_ready_, "weights not finalized");
+  const double t_begin = dbg_timing() ? now_ms() : 0.0;
   const int tl = ucfg_.text_context_len, D = ucfg_.context_dim;
   MUDG_REQUIRE(L > tl, "context needs image tokens after the %d text tokens (L=%d)", tl, L);
   const int Limg = L - tl;
   const bool per_frame = (L == tl + 16 * T);     // openaimodel3d.py:581 hard-coded split
   bool realloc = (N != ctx_N_ || L != ctx_L_ || T != ctx_T_);
-  __half *text = nullptr, *img = nullptr;
-  MUDG_CUDA(cudaMalloc(&text, sizeof(__half) * (size_t)N * tl * D));
-  MUDG_CUDA(cudaMalloc(&img, sizeof(__half) * (size_t)N * Limg * D));
+  // fp16 copies of the text / image rows: persistent, grow-only staging (no cudaMalloc / cudaFree / host sync per call:
+  // a caller that re-creates the context tensor every DDIM step would otherwise stall the whole pipeline on them)
+  const size_t text_b = sizeof(__half) * (size_t)N * tl * D, img_b = sizeof(__half) * (size_t)N * Limg * D;
+  if (ctx_text_stage_bytes_ < text_b) {
+    MUDG_CUDA(cudaDeviceSynchronize());
+    cudaFree(ctx_text_stage_);
+    MUDG_CUDA(cudaMalloc(&ctx_text_stage_, text_b));
+    ctx_text_stage_bytes_ = text_b;
+  }
+  if (ctx_img_stage_bytes_ < img_b) {
+    MUDG_CUDA(cudaDeviceSynchronize());
+    cudaFree(ctx_img_stage_);
+    MUDG_CUDA(cudaMalloc(&ctx_img_stage_, img_b));
+    ctx_img_stage_bytes_ = img_b;
+  }
+  __half *text = ctx_text_stage_, *img = ctx_img_stage_;
   gather_rows_f16(ctx, dtype == MUDG_F32, text, N, L, 0, tl, D, st);
   gather_rows_f16(ctx, dtype == MUDG_F32, img, N, L, tl, Limg, D, st);
   auto visit = [&](const Layer& l) {
@@ -754,8 +808,8 @@ void Model::set_context(const void* ctx, int dtype, int N, int L, int T, cudaStr
     const int C = l.ch;
     KvCache& kc = kv_[l.prefix];
     const size_t tb = sizeof(__half) * (size_t)N * tl * 2 * C, ib = sizeof(__half) * (size_t)N * Limg * 2 * C;
-    if (kc.text_bytes < tb) { cudaFree(kc.text); MUDG_CUDA(cudaMalloc(&kc.text, tb)); kc.text_bytes = tb; realloc = true; }
-    if (kc.img_bytes < ib) { cudaFree(kc.img); MUDG_CUDA(cudaMalloc(&kc.img, ib)); kc.img_bytes = ib; realloc = true; }
+    if (kc.text_bytes < tb) { MUDG_CUDA(cudaDeviceSynchronize()); cudaFree(kc.text); MUDG_CUDA(cudaMalloc(&kc.text, tb)); kc.text_bytes = tb; realloc = true; }
+    if (kc.img_bytes < ib) { MUDG_CUDA(cudaDeviceSynchronize()); cudaFree(kc.img); MUDG_CUDA(cudaMalloc(&kc.img, ib)); kc.img_bytes = ib; realloc = true; }
     const std::string tbp = l.prefix + ".transformer_blocks.0.attn2.";
     for (int k = 0; k < 2; k++) {
       const Weight& w = unet_w.W(tbp + (k ? "kv_img.weight" : "kv_text.weight"));
@@ -780,9 +834,7 @@ void Model::set_context(const void* ctx, int dtype, int N, int L, int T, cudaStr
   for (auto& b : in_blocks_) for (auto& l : b.layers) visit(l);
   for (auto& l : mid_.layers) visit(l);
   for (auto& b : out_blocks_) for (auto& l : b.layers) visit(l);
-  MUDG_CUDA(cudaStreamSynchronize(st));   // once per clip; the staging buffers are freed here
-  cudaFree(text);
-  cudaFree(img);
+  if (dbg_timing()) fprintf(stderr, "[mudg] set_context: issued in %.1f ms, realloc %d\n", now_ms() - t_begin, (int)realloc);
   ctx_N_ = N; ctx_L_ = L; ctx_T_ = T; ctx_Limg_ = Limg; ctx_per_frame_ = per_frame;
   ctx_version_ += realloc ? 1 : 0;     // K/V buffers moved (or the token layout changed): graphs must be re-captured
 }
@@ -829,8 +881,10 @@ void Model::unet_forward(const void* x, const int64_t* t, const int64_t* label, 
   GraphSlot& g = graphs_[key];
   const size_t xin = sizeof(float) * (size_t)N * ucfg_.in_channels * T * h * w;
   const size_t xout = sizeof(__half) * (size_t)N * ucfg_.out_channels * T * h * w;
+  if (dbg_timing() && g.ctx_version != ctx_version_) fprintf(stderr, "[mudg] unet_forward: graph invalidated (context version)\n");
   if (g.ctx_version != ctx_version_) {                     // set_context may have re-allocated the K/V caches
-    if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    for (auto& e : g.ring) { if (e) cudaGraphExecDestroy(e); e = nullptr; }
+    g.exec = nullptr;
     g.runs = 0;
     g.ctx_version = ctx_version_;
   }
@@ -844,7 +898,8 @@ void Model::unet_forward(const void* x, const int64_t* t, const int64_t* label, 
   MUDG_CUDA(cudaMemcpyAsync(g.in_idx + N, label, sizeof(int64_t) * N, cudaMemcpyDeviceToDevice, st));
   MUDG_CUDA(cudaMemcpyAsync(g.in_idx + 2 * N, fs, sizeof(int64_t) * N, cudaMemcpyDeviceToDevice, st));
   if (g.exec) {
-    MUDG_CUDA(cudaGraphLaunch(g.exec, st));
+    MUDG_CUDA(cudaGraphLaunch(g.ring[g.next], st));
+    g.next = (g.next + 1) % GraphSlot::GRAPH_RING;
     launches += g.launches;
   } else if (g.runs == 0) {
     // first call: eager (sets kernel attributes, fills the tensor-map cache)
@@ -862,9 +917,11 @@ void Model::unet_forward(const void* x, const int64_t* t, const int64_t* label, 
       throw;
     }
     MUDG_CUDA(cudaStreamEndCapture(st, &graph));
-    MUDG_CUDA(cudaGraphInstantiate(&g.exec, graph, 0));
+    for (auto& e : g.ring) MUDG_CUDA(cudaGraphInstantiate(&e, graph, 0));
     cudaGraphDestroy(graph);
-    MUDG_CUDA(cudaGraphLaunch(g.exec, st));
+    g.exec = g.ring[0];
+    g.next = 1;
+    MUDG_CUDA(cudaGraphLaunch(g.ring[0], st));
   }
   g.runs++;
   MUDG_CUDA(cudaMemcpyAsync(out, g.out, xout, cudaMemcpyDeviceToDevice, st));
@@ -872,7 +929,7 @@ void Model::unet_forward(const void* x, const int64_t* t, const int64_t* label, 
 
 void Model::drop_graphs() {
   for (auto& kv : graphs_) {
-    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    for (auto& e : kv.second.ring) { if (e) cudaGraphExecDestroy(e); e = nullptr; }
     kv.second.exec = nullptr;
     kv.second.runs = 0;
   }
@@ -1084,6 +1141,107 @@ void Model::vae_encode(const void* x, int F, int H, int W, void* moments, cudaSt
   for (int f = 0; f < F; f++)
     vae_encode_body(static_cast<const float*>(x) + (size_t)f * 3 * H * W, H, W,
                     static_cast<float*>(moments) + (size_t)f * 2 * v.z_channels * (H / 8) * (W / 8));
+}
+
+}  // namespace mudg
+
+// ================================================================ Resampler ("next" row f.3; resampler.py:48-144)
+// Once per clip: [B, 257, 1280] image-encoder tokens -> [B, 16*T, 1024] image context.  Same kernels as the UNet: tcgen05
+// tap-GEMM for every Linear (bias / residual fused), flash attention (d = 64) over the [x ; latents] keys, warp-per-row
+// LayerNorm, plus an in-place erf GELU.
+namespace mudg {
+
+void Model::resampler_body(const void* x, int dtype, int B, int L, void* out) {
+  ws_ = &res_w;
+  arena_.reset();
+  const ResamplerDims& r = rs_;
+  const int Lkv = L + r.nq;
+  auto rows = [&](int n_rows, int width) { return alloc(1, 1, 1, n_rows, width); };
+  Act xin = rows(B * L, r.emb);
+  Act lat = rows(B * r.nq, r.dim);
+  if (live()) {
+    cast_to_f16(x, dtype == MUDG_F32, xin.p, (int64_t)B * L * r.emb, st_);
+    for (int b = 0; b < B; b++)      // latents.repeat(B, 1, 1)
+      MUDG_CUDA(cudaMemcpyAsync(lat.p + (size_t)b * r.nq * r.dim, res_w.W("latents").w, sizeof(__half) * (size_t)r.nq * r.dim,
+                                cudaMemcpyDeviceToDevice, st_));
+    launches += 1 + B;
+  }
+  Act xp = linear(xin, "proj_in.weight", "proj_in.bias", nullptr);
+  release(xin);
+  for (int i = 0; i < r.depth; i++) {
+    const std::string a = "layers." + std::to_string(i) + ".0", f = "layers." + std::to_string(i) + ".1";
+    // PerceiverAttention.forward (resampler.py:66-101)
+    Act xn = layer_norm(xp, a + ".norm1");
+    Act ln = layer_norm(lat, a + ".norm2");
+    Act q = linear(ln, a + ".to_q.weight", "", nullptr);
+    Act kvin = rows(B * Lkv, r.dim);               // torch.cat((x, latents), dim=-2)
+    if (live()) {
+      const size_t rowb = sizeof(__half) * (size_t)r.dim;
+      MUDG_CUDA(cudaMemcpy2DAsync(kvin.p, rowb * Lkv, xn.p, rowb * L, rowb * L, B, cudaMemcpyDeviceToDevice, st_));
+      MUDG_CUDA(cudaMemcpy2DAsync(kvin.p + (size_t)L * r.dim, rowb * Lkv, ln.p, rowb * r.nq, rowb * r.nq, B,
+                                  cudaMemcpyDeviceToDevice, st_));
+      launches += 2;
+    }
+    release(xn);
+    release(ln);
+    Act kv = linear(kvin, a + ".to_kv.weight", "", nullptr);      // [B*Lkv][k | v]
+    release(kvin);
+    const int pad = round_up(Lkv, 8);
+    __half* vt = static_cast<__half*>(alloc_bytes(sizeof(__half) * (size_t)B * r.inner * pad));
+    Act o = rows(B * r.nq, r.inner);
+    if (live()) {
+      transpose_v(kv.p + r.inner, 2 * r.inner, Lkv, B, r.heads, vt, pad, st_);
+      FlashArgs fa;
+      fa.Q = q.p; fa.q_pitch = r.inner; fa.O = o.p; fa.o_pitch = r.inner; fa.F = B; fa.Nq = r.nq; fa.heads = r.heads;
+      fa.nseg = 1;
+      fa.seg[0].K = kv.p; fa.seg[0].V = kv.p + r.inner; fa.seg[0].pitch = 2 * r.inner; fa.seg[0].len = Lkv;
+      fa.seg[0].VT = vt; fa.seg[0].vt_pitch = pad; fa.seg[0].nbatch = B; fa.seg[0].kv_div = 1;
+      fa.scale = 0.125f;                            // (q * 64^-1/4) . (k * 64^-1/4)
+      flash_attention(fa, st_);
+      launches += 2;
+    }
+    release_bytes(vt);
+    release(kv);
+    release(q);
+    Act lat2 = linear(o, a + ".to_out.weight", "", &lat);         // attn(x, latents) + latents
+    release(o);
+    release(lat);
+    // FeedForward (resampler.py:31-37): LayerNorm -> Linear -> GELU -> Linear, + latents
+    Act hn = layer_norm(lat2, f + ".0");
+    Act h1 = linear(hn, f + ".1.weight", "", nullptr);
+    release(hn);
+    if (live()) {
+      gelu_inplace(h1.p, (int64_t)h1.rows() * h1.C, st_);
+      launches++;
+    }
+    lat = linear(h1, f + ".3.weight", "", &lat2);
+    release(h1);
+    release(lat2);
+  }
+  release(xp);
+  Act po = linear(lat, "proj_out.weight", "proj_out.bias", nullptr);
+  release(lat);
+  Act y = layer_norm(po, "norm_out");
+  release(po);
+  if (live()) {
+    cast_to_f32(y.p, false, static_cast<float*>(out), (int64_t)y.rows() * y.C, st_);
+    launches++;
+  }
+  release(y);
+}
+
+void Model::resampler_forward(const void* x, int dtype, int B, int L, void* out, cudaStream_t st) {
+  MUDG_REQUIRE(res_ready_, "Resampler weights not finalized");
+  MUDG_REQUIRE(B >= 1 && L >= 1, "Resampler: empty input");
+  arena_.planning = true; planning_ = true;
+  arena_.reset_high();
+  resampler_body(nullptr, dtype, B, L, nullptr);
+  const size_t need = arena_.high_water();
+  arena_.planning = false; planning_ = false;
+  arena_.reset();
+  ensure_arena(need);
+  st_ = st;
+  resampler_body(x, dtype, B, L, out);
 }
 
 }  // namespace mudg

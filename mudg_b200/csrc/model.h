@@ -72,13 +72,15 @@ class Model {
   Model(int device, const MudgUNetConfig& u, const MudgVaeConfig& v);
   ~Model();
 
-  WeightStore unet_w, vae_w;
+  WeightStore unet_w, vae_w, res_w;   // res_w: Resampler (image_proj_model), "next" row f.3
   void finalize(int which, cudaStream_t st);
   void set_context(const void* ctx, int dtype, int N, int L, int T, cudaStream_t st);
   void unet_forward(const void* x, const int64_t* t, const int64_t* label, const int64_t* fs, int N, int T, int h, int w,
                     void* out, cudaStream_t st);
   void vae_decode(const void* z, int F, int h, int w, void* out, cudaStream_t st);
   void vae_encode(const void* x, int F, int H, int W, void* moments, cudaStream_t st);
+  // Resampler.forward (resampler.py:131-144): x [B, L, embedding_dim] -> out [B, num_queries*video_length, output_dim] fp32
+  void resampler_forward(const void* x, int dtype, int B, int L, void* out, cudaStream_t st);
   size_t plan_unet(int N, int T, int h, int w);
   size_t plan_vae(int h, int w);
   int64_t launches = 0;
@@ -92,7 +94,9 @@ class Model {
   std::vector<Block> in_blocks_, out_blocks_;
   Block mid_;
   int n_res_ = 0;
-  bool unet_ready_ = false, vae_ready_ = false, vae_enc_ready_ = false;
+  bool unet_ready_ = false, vae_ready_ = false, vae_enc_ready_ = false, res_ready_ = false;
+  struct ResamplerDims { int nq = 0, dim = 0, emb = 0, outd = 0, depth = 0, heads = 0, inner = 0, ff = 0; } rs_;
+  void resampler_body(const void* x, int dtype, int B, int L, void* out);
 
   // ---- per-call state
   Arena arena_;
@@ -102,11 +106,20 @@ class Model {
   int ctx_N_ = 0, ctx_L_ = 0, ctx_T_ = 0, ctx_Limg_ = 0;
   bool ctx_per_frame_ = false;
   std::unordered_map<std::string, KvCache> kv_;
+  __half *ctx_text_stage_ = nullptr, *ctx_img_stage_ = nullptr;   // fp16 staging of the context rows (grow-only)
+  size_t ctx_text_stage_bytes_ = 0, ctx_img_stage_bytes_ = 0;
   std::vector<float*> emb_out_;   // per ResBlock [N][Cout]
   int T_real_ = 1;                // frames per sample of the current forward
   int N_ = 1;
   struct GraphSlot {
-    cudaGraphExec_t exec = nullptr;
+    // Ring of executable graphs instantiated from ONE capture: a cudaGraphExec_t cannot run concurrently with itself and
+    // cudaGraphLaunch blocks the HOST until its previous launch has finished, which put the Python sampler loop in
+    // lock-step with the GPU (measured: 144 ms inside every unet_forward call) -- any host hiccup then idles the GPU.
+    // With a ring the host queues GRAPH_RING - 1 steps ahead.
+    static constexpr int GRAPH_RING = 8;
+    cudaGraphExec_t exec = nullptr;          // == ring[0] once captured (non-null <=> captured)
+    cudaGraphExec_t ring[GRAPH_RING] = {};
+    int next = 0;
     float* in_x = nullptr;
     int64_t* in_idx = nullptr;
     __half* out = nullptr;

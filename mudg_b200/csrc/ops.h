@@ -18,6 +18,7 @@ void concat_channels(const __half* a, int Ca, const __half* b, int Cb, __half* o
 void upsample2x(const __half* x, __half* y, int F, int H, int W, int C, cudaStream_t st);
 void im2col_s2(const __half* x, __half* y, int F, int H, int W, int C, int pad, cudaStream_t st);   // Ho = (H + pad - 2) / 2 + 1
 void softmax_rows(__half* x, int64_t rows, int n, cudaStream_t st);
+void gelu_inplace(__half* x, int64_t n, cudaStream_t st);   // exact erf GELU, fp16, n % 8 == 0
 void pack_weight(const void* src, bool src_fp32, __half* dst, int O, int I, int taps, int Ipad, cudaStream_t st);
 void cast_to_f32(const void* src, bool src_fp32, float* dst, int64_t n, cudaStream_t st);
 void cast_to_f16(const void* src, bool src_fp32, __half* dst, int64_t n, cudaStream_t st);

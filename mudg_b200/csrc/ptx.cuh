@@ -114,6 +114,7 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---------------------------------------------------------------- TMEM
@@ -241,6 +242,12 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Same arrival without the cluster-scope release (which costs ~900 clocks: it drains every outstanding memory operation
+// of the thread).  For "my tcgen05.ld of this accumulator have completed" no memory ordering is needed: the loads have
+// retired (tcgen05.wait::ld) and tcgen05.fence::before_thread_sync orders them before the arrival.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load issued by either CTA of a pair: data lands in THIS CTA's smem, the transaction bytes are signalled on the
 // mbarrier at shared::cluster address `bar_cluster_addr` (the leader CTA's "full" barrier).

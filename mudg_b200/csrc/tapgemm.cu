@@ -689,7 +689,14 @@ struct G3Params {
   int dimW, dimH, dimB;
   const __half* R;
   int alpha_is_one;
+  int dbg;                      // debug experiments (MUDG_GEMM_DBG): 1 = do not issue the output TMA stores
+  long long* trace;             // debug (tests/gpu_trace_gemm.py): clock64 time line of cluster 0 / rank 0, [4 roles][64 tiles][8]
 };
+
+#define G3_TRACE(role, lt_, ev)                                                                       \
+  do {                                                                                                 \
+    if (p.trace != nullptr && blockIdx.x == 0 && (lt_) < 64) p.trace[((role) * 64 + (lt_)) * 8 + (ev)] = clock64(); \
+  } while (0)
 
 __device__ __forceinline__ G2Tile g3_decode(const G3Params& p, int tile, int rank) {
   G2Tile t;
@@ -751,8 +758,10 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint32_t s = 0, ph = 1;                 // stage, parity to wait for on its "empty" barrier
     const uint32_t full0 = mapa_u32(&full[0], 0);
     const int ntaps = p.b.ntaps, kchunks = p.b.kchunks;
-    for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters) {
+    uint32_t plt = 0;
+    for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters, plt++) {
       const G2Tile tl = g3_decode(p, tile, (int)rank);
+      if (lane == 0) G3_TRACE(0, plt, 0);                 // producer starts the tile
       const CUtensorMap* mb = (tl.bn == p.bn_first) ? &tmB0 : &tmB1;
       const int brow = tl.n0 + (int)rank * (tl.bn >> 1);
       const uint32_t stage_tx = 2u * (uint32_t)(G3_A_BYTES + (tl.bn >> 1) * (BK * 2));
@@ -771,6 +780,7 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (++s == G3_STAGES) { s = 0; ph ^= 1u; }
         }
       }
+      if (lane == 0) G3_TRACE(0, plt, 1);                 // all loads of the tile issued
     }
   } else if (warp == 1) {
     if (rank == 0) {                         // whole warp loops (uniform registers), one elected lane issues
@@ -780,13 +790,16 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters, lt++) {
         const G2Tile tl = g3_decode(p, tile, 0);
         const uint32_t acc = lt & 1;
+        if (lane == 0) G3_TRACE(1, lt, 0);                     // issuer ready for the tile
         mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);      // both CTAs' epilogues have drained this accumulator
         tc_fence_after();
+        if (lane == 0) G3_TRACE(1, lt, 1);                     // accumulator free
         const uint32_t idesc = umma_idesc_f16(256, tl.bn, 0, 0);
         const uint32_t d_tmem = tmem_base + acc * 256;
         for (int k = 0; k < ktotal; k++) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
+          if (k == 0 && lane == 0) G3_TRACE(1, lt, 2);         // first operands landed
           if (elect_one()) {
             const uint64_t so = (uint64_t)(s * (G3_STAGE_BYTES >> 4));     // descriptor start address: 16 B units
 #pragma unroll
@@ -798,6 +811,7 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           __syncwarp();
           if (++s == G3_STAGES) { s = 0; ph ^= 1u; }
         }
+        if (lane == 0) G3_TRACE(1, lt, 3);                     // last MMA of the tile issued
       }
     }
   } else {
@@ -822,6 +836,10 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int it_ = r % p.b.bt;
     const int ib_ = r / p.b.bt;
     const int csh = p.b.geglu ? 7 : 6;          // accumulator columns per chunk: 64, or 128 (64 value + 64 gate)
+    auto arrive_empty = [&](uint32_t bar) {     // MUDG_GEMM_DBG bit 1: fall back to the (slow) release arrive
+      if (p.dbg & 2) mbar_arrive_cluster(bar);
+      else mbar_arrive_cluster_relaxed(bar);
+    };
     uint32_t lt = 0;
     for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters, lt++) {
       const G2Tile tl = g3_decode(p, tile, (int)rank);
@@ -833,7 +851,7 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       cc += (uint32_t)nchunks;
       if (mine == 0) {
         mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
-        if (issuer) mbar_arrive_cluster(empty_bar);
+        if (issuer) arrive_empty(empty_bar);
         __syncwarp();
         continue;
       }
@@ -905,7 +923,7 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           __syncwarp();
           group_sync();                         // every thread of the group is past its TMEM reads and smem writes
           if (issuer) {
-            if (ci == mine - 1) mbar_arrive_cluster(empty_bar);
+            if (ci == mine - 1) arrive_empty(empty_bar);
             tma_store_5d(&tmD, stg, nbase / 2, tl.w0, tl.h0, tl.t0, tl.b0);
             tma_store_commit();
           }
@@ -936,9 +954,11 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
         for (int j = 0; j < 4; j++) res_nxt[j] = __ldg(rp + first * 8 + j);
       }
+      if (q == 2 && lane == 0) G3_TRACE(2 + grp, lt, 0);       // epilogue group ready for the tile
       mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
       __syncwarp();
       tc_fence_after();
+      if (q == 2 && lane == 0) G3_TRACE(2 + grp, lt, 1);       // accumulator complete
       const int nslices = mine * 2;          // my 32-column slices, two per chunk
 #pragma unroll 1
       for (int sl = 0; sl < nslices; sl++) {
@@ -1016,12 +1036,15 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           __syncwarp();
           group_sync();
           if (issuer) {
-            if (sl == nslices - 1) mbar_arrive_cluster(empty_bar);   // the whole group is past its TMEM reads
-            tma_store_5d(&tmD, stg, tl.n0 + ch * 64, tl.w0, tl.h0, tl.t0, tl.b0);
-            tma_store_commit();
+            if (sl == nslices - 1) arrive_empty(empty_bar);   // the whole group is past its TMEM reads
+            if (!(p.dbg & 1)) {
+              tma_store_5d(&tmD, stg, tl.n0 + ch * 64, tl.w0, tl.h0, tl.t0, tl.b0);
+              tma_store_commit();
+            }
           }
           __syncwarp();
           chunk_no++;
+          if (q == 2 && lane == 0) G3_TRACE(2 + grp, lt, 2 + (sl >> 1));   // chunk stored
         }
       }
     }
@@ -1220,6 +1243,9 @@ void tapgemm_tc(const TapGemm& g, cudaStream_t st) {
 }
 
 // CTA-pair kernel (tapgemm_tc3_kernel): large problems only (several waves of 256 x 256 tiles over the 74 TPCs)
+static long long* g_gemm_trace = nullptr;
+void gemm_set_trace(long long* buf) { g_gemm_trace = buf; }
+
 bool tapgemm_pair_wanted(const TapGemm& g, int64_t m_tiles, int nt128) {
   static const int mode = [] {
     const char* e = getenv("MUDG_GEMM_PAIR");
@@ -1263,6 +1289,12 @@ void tapgemm_tc3(const TapGemm& g, cudaStream_t st) {
   p.dimW = g.W; p.dimH = g.H; p.dimB = g.B;
   p.R = g.R;
   p.alpha_is_one = g.alpha == 1.f ? 1 : 0;
+  p.trace = g_gemm_trace;
+  static const int dbg_env = [] {
+    const char* e = getenv("MUDG_GEMM_DBG");
+    return e ? atoi(e) : 0;
+  }();
+  p.dbg = dbg_env;
 
   const uint64_t C = g.Cin, No = p.b.n_out, Ktot = (uint64_t)g.ntaps * g.Cin;
   const uint64_t adims[5] = {C, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.T, (uint64_t)g.B};

@@ -14,7 +14,7 @@ import torch
 from ._lib import MudgError, check, cur_stream, lib, ptr
 
 MUDG_F32, MUDG_F16, MUDG_U8 = 0, 1, 2
-MUDG_UNET, MUDG_VAE = 0, 1
+MUDG_UNET, MUDG_VAE, MUDG_RESAMPLER = 0, 1, 2
 MUDG_POST_COLOR, MUDG_POST_DEPTH, MUDG_POST_SEMANTIC = 0, 1, 2
 # class labels the driver gives the three modalities (virtual_pose_render.py:247-318)
 LABEL_TO_POST_MODE = {0: MUDG_POST_COLOR, 500: MUDG_POST_DEPTH, 1: MUDG_POST_SEMANTIC}
@@ -77,13 +77,17 @@ def _arr8(values: Sequence[int]):
     return (ctypes.c_int * 8)(*(vals + [0] * (8 - len(vals)))), len(vals)
 
 
+# smallest graph the library accepts: for contexts that only run the Resampler / post-decode kernels
+_MINIMAL_UNET = dict(in_channels=8, out_channels=4, model_channels=32, num_res_blocks=1, channel_mult=(1,),
+                     attention_resolutions=(1,), num_head_channels=64, context_dim=64)
 _DEFAULT_VAE = dict(ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2, z_channels=4, out_ch=3, embed_dim=4)
 
 
 class Engine:
-    def __init__(self, unet: Mapping, vae: Optional[Mapping] = None, device: Optional[int] = None):
+    def __init__(self, unet: Optional[Mapping] = None, vae: Optional[Mapping] = None, device: Optional[int] = None):
         if not torch.cuda.is_available():
             raise MudgError("mudg_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        unet = dict(_MINIMAL_UNET) if unet is None else unet
         self.device = torch.cuda.current_device() if device is None else int(device)
         vae = dict(_DEFAULT_VAE, **(vae or {}))
         uc = _UNetConfig()
@@ -138,6 +142,8 @@ class Engine:
             if t.dtype not in (torch.float32, torch.float16):
                 t = t.float()
             g = t.to(dev, non_blocking=True).contiguous()
+            if which == MUDG_RESAMPLER and key == "latents":      # [1, nq, dim] parameter -> a [nq, dim] row matrix
+                g = g.reshape(-1, g.shape[-1])
             shape = (ctypes.c_int64 * max(1, g.dim()))(*g.shape)
             check(L.mudg_load_weight(self._h, which, key.encode(), ptr(g), MUDG_F32 if g.dtype == torch.float32 else MUDG_F16,
                                      shape, g.dim(), cur_stream()))
@@ -190,6 +196,18 @@ class Engine:
         x = x.detach().float().contiguous()
         out = torch.empty((F_, 2 * self.z_channels, H // 8, W // 8), device=x.device, dtype=torch.float32)
         check(lib().mudg_vae_encode(self._h, ptr(x), F_, H, W, ptr(out), cur_stream()))
+        return out
+
+    def resampler_forward(self, x: torch.Tensor, n_out: int, out_dim: int) -> torch.Tensor:
+        """x [B, L, embedding_dim] -> [B, n_out, out_dim] fp32 (Resampler.forward)."""
+        x = x.detach()
+        if x.dtype not in (torch.float32, torch.float16):
+            x = x.float()
+        x = x.contiguous()
+        B, L, _ = x.shape
+        out = torch.empty((B, n_out, out_dim), device=x.device, dtype=torch.float32)
+        check(lib().mudg_resampler_forward(self._h, ptr(x), MUDG_F32 if x.dtype == torch.float32 else MUDG_F16, B, L, ptr(out),
+                                           cur_stream()))
         return out
 
     def ddim_step(self, x, v_cond, v_uncond, noise, *, cfg_scale, guidance_rescale, sqrt_ac, sqrt_1mac, rescale,

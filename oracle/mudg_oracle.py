@@ -743,3 +743,55 @@ def ddim_sample_multicond(unet_sd: SD, ucfg: UNetCfg, tab: DiffusionTables, *, S
             v = rescale_noise_cfg(v, v_c, guidance_rescale)
         x, _ = ddim_step(tab, sch, index, x, v, None, draw(i + 1), 1.0, 0.0)
     return x
+
+
+# ================================================================ Resampler
+# Perceiver resampler that turns the image-encoder tokens into the UNet's image context
+# (lvdm/modules/encoders/resampler.py:48-144): [B, n1, embedding_dim] -> [B, num_queries * video_length, output_dim].
+def resampler_param_shapes(dim=1024, depth=4, dim_head=64, heads=12, num_queries=16, embedding_dim=1280, output_dim=1024,
+                           ff_mult=4, video_length=16) -> Dict[str, Tuple[int, ...]]:
+    nq = num_queries * (video_length if video_length is not None else 1)
+    inner = dim_head * heads
+    s: Dict[str, Tuple[int, ...]] = {"latents": (1, nq, dim), "proj_in.weight": (dim, embedding_dim), "proj_in.bias": (dim,),
+                                     "proj_out.weight": (output_dim, dim), "proj_out.bias": (output_dim,),
+                                     "norm_out.weight": (output_dim,), "norm_out.bias": (output_dim,)}
+    for i in range(depth):
+        a, f = f"layers.{i}.0", f"layers.{i}.1"
+        for n in ("norm1", "norm2"):
+            s[f"{a}.{n}.weight"] = (dim,)
+            s[f"{a}.{n}.bias"] = (dim,)
+        s[f"{a}.to_q.weight"] = (inner, dim)
+        s[f"{a}.to_kv.weight"] = (2 * inner, dim)
+        s[f"{a}.to_out.weight"] = (dim, inner)
+        s[f"{f}.0.weight"] = (dim,)
+        s[f"{f}.0.bias"] = (dim,)
+        s[f"{f}.1.weight"] = (int(dim * ff_mult), dim)
+        s[f"{f}.3.weight"] = (dim, int(dim * ff_mult))
+    return s
+
+
+@torch.no_grad()
+def resampler_forward(sd: SD, x: Tensor, heads: int, dim_head: int = 64) -> Tensor:
+    """Resampler.forward (resampler.py:131-144) with PerceiverAttention.forward (:66-101) and FeedForward (:31-37)."""
+    F = torch.nn.functional
+    depth = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("layers."))
+    b = x.shape[0]
+    lat = sd["latents"].repeat(b, 1, 1)
+    x = F.linear(x, sd["proj_in.weight"], sd["proj_in.bias"])
+    scale = 1.0 / math.sqrt(math.sqrt(dim_head))
+    for i in range(depth):
+        a, f = f"layers.{i}.0", f"layers.{i}.1"
+        xn = F.layer_norm(x, x.shape[-1:], sd[f"{a}.norm1.weight"], sd[f"{a}.norm1.bias"])
+        ln = F.layer_norm(lat, lat.shape[-1:], sd[f"{a}.norm2.weight"], sd[f"{a}.norm2.bias"])
+        q = F.linear(ln, sd[f"{a}.to_q.weight"])
+        k, v = F.linear(torch.cat((xn, ln), dim=-2), sd[f"{a}.to_kv.weight"]).chunk(2, dim=-1)
+        split = lambda t: t.view(b, t.shape[1], heads, -1).transpose(1, 2)
+        q, k, v = split(q), split(k), split(v)
+        w = torch.softmax(((q * scale) @ (k * scale).transpose(-2, -1)).float(), dim=-1).type(q.dtype)
+        o = (w @ v).permute(0, 2, 1, 3).reshape(b, lat.shape[1], -1)
+        lat = F.linear(o, sd[f"{a}.to_out.weight"]) + lat
+        h = F.layer_norm(lat, lat.shape[-1:], sd[f"{f}.0.weight"], sd[f"{f}.0.bias"])
+        h = F.linear(F.gelu(F.linear(h, sd[f"{f}.1.weight"])), sd[f"{f}.3.weight"])
+        lat = h + lat
+    lat = F.linear(lat, sd["proj_out.weight"], sd["proj_out.bias"])
+    return F.layer_norm(lat, lat.shape[-1:], sd["norm_out.weight"], sd["norm_out.bias"])

@@ -292,3 +292,54 @@ def test_eval_tools_dropin(tmp_path):
     assert np.array_equal(vis.numpy(), rv) and np.array_equal(idx.numpy(), rc)
     dv = np.array(E.visualize_depth(ref_d[1, 0][None])[0])
     assert np.array_equal(dv.transpose(2, 0, 1), P.spectral_u8(ref_d[1, 0]))
+
+
+def test_multicond_sampler_vs_reference_golden(golden_dir):
+    """Next row f.4: lvdm.models.samplers.ddim_multiplecond.DDIMSampler (separate image / text guidance, three UNet
+    evaluations per step) through the drop-in classes against the reference's own sampler output (2 steps, text scale 7.5,
+    image scale 3.0, guidance_rescale 0.7, eta 1; oracle/make_golden_multicond.py)."""
+    from mudg_b200 import compat
+    compat.install()
+    from omegaconf import OmegaConf
+    from utils.utils import instantiate_from_config
+    from lvdm.models.samplers.ddim_multiplecond import DDIMSampler
+    import lvdm.models.samplers.ddim_multiplecond as mc_mod
+    from oracle import mudg_oracle as O
+    cfg = OmegaConf.load(os.path.join(ROOT, "configs", "stage2-1024_mdm_waymo_infer_synthetic.yaml")).model
+    p = cfg.params
+    p.unet_config.params.model_channels = 64
+    p.unet_config.params.temporal_length = 4
+    p.first_stage_config.params.ddconfig.ch = 64
+    p.image_size = [16, 16]
+    model = instantiate_from_config(cfg)
+    sd = O.seeded_state_dict(O.unet_param_shapes(O.UNetCfg(model_channels=64, temporal_length=4)), seed=1)
+    model.model.diffusion_model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    d = np.load(os.path.join(golden_dir, "ddim_multicond_small.npz"))
+    t = lambda a: torch.from_numpy(a).cuda()
+    ctx, uc_ctx = t(d["ctx"]), t(d["uc_ctx"])
+    uc_img_ctx = torch.cat([uc_ctx[:, :77], ctx[:, 77:]], dim=1)
+    cc = t(d["c_concat"])
+    cond = {"c_crossattn": [ctx], "c_concat": [cc]}
+    uc = {"c_crossattn": [uc_ctx], "c_concat": [cc]}
+    uc2 = {"c_crossattn": [uc_img_ctx], "c_concat": [cc]}
+    torch.manual_seed(321)
+    draws = [torch.randn(2, 4, 4, 16, 16) for _ in range(3)]
+    it = iter(draws[1:])
+    orig = mc_mod.noise_like
+    mc_mod.noise_like = lambda shape, device, repeat=False: next(it).to(device)
+    try:
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            z, _ = DDIMSampler(model).sample(
+                S=2, conditioning=cond, batch_size=2, shape=[4, 4, 16, 16], verbose=False,
+                unconditional_guidance_scale=7.5, unconditional_conditioning=uc, eta=1.0, cfg_img=3.0, mask=None, x0=None,
+                fs=t(d["fs"]), timestep_spacing="uniform_trailing", guidance_rescale=0.7, sparse_x=None,
+                class_label=t(d["lab"])[:, None], unconditional_conditioning_img_nonetext=uc2, x_T=draws[0].cuda())
+    finally:
+        mc_mod.noise_like = orig
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(d["samples"])
+    err = (z.float().cpu() - ref).abs()
+    psnr = 10 * torch.log10(ref.abs().max() ** 2 / ((z.float().cpu() - ref) ** 2).mean())
+    print(f"2-step multicond sample: max|d|={float(err.max()):.4f} latent PSNR={float(psnr):.1f} dB")
+    assert float(err.max()) < 0.15 and float(psnr) > 40.0

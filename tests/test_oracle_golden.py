@@ -110,3 +110,20 @@ def test_ddim_sample_matches_reference(golden_dir):
     vsd = O.seeded_state_dict(O.vae_param_shapes(vcfg), seed=2)
     frames = O.decode_first_stage(vsd, vcfg, t(d["samples"]))
     assert float((frames - t(d["frames"]).float()).abs().max()) < 5e-3    # fixture stored as fp16
+
+
+def test_multicond_sample_matches_reference(golden_dir):
+    """DDIMSampler_multicond (three UNet evaluations per step) restated in the oracle vs the reference's own output."""
+    d = np.load(os.path.join(golden_dir, "ddim_multicond_small.npz"))
+    cfg = O.UNetCfg(model_channels=64, temporal_length=4)
+    sd = O.seeded_state_dict(O.unet_param_shapes(cfg), seed=1)
+    tab = O.make_tables(base_scale=0.3)
+    t = lambda k: torch.from_numpy(d[k])
+    ctx, uc_ctx = t("ctx"), t("uc_ctx")
+    uc_img = torch.cat([uc_ctx[:, :77], ctx[:, 77:]], dim=1)
+    torch.manual_seed(321)
+    noises = [torch.randn(2, 4, 4, 16, 16) for _ in range(3)]
+    out = O.ddim_sample_multicond(sd, cfg, tab, S=2, shape=(2, 4, 4, 16, 16), c_concat=t("c_concat"), context=ctx,
+                                  uc_context=uc_ctx, uc_img_context=uc_img, class_label=t("lab"), fs=t("fs"), cfg_scale=7.5,
+                                  cfg_img=3.0, guidance_rescale=0.7, eta=1.0, noises=noises)
+    assert float((out - t("samples")).abs().max()) < 1e-3
