@@ -7,7 +7,8 @@ Weights are seeded-random of the reference architecture (no checkpoint is reacha
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config mdm1024|mdm512|mdm1024_t64]
 
 Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM; `e2e`: same call with pinned HOST buffers copied
-H2D every step and the decoded frames read back D2H inside the timed region.
+H2D every step, the decoded clip converted to uint8 frames on the GPU (mudg_postdecode) and read back D2H inside the
+timed region.
 --impl reference: the CPU oracle port (oracle/mudg_oracle.py -- the reference itself is Python and cannot travel to
 the GPU box) timed on the host cores on a bounded sample; rank 0 only.
 """
@@ -31,6 +32,7 @@ CONFIGS = {
     "mdm1024_t64": ("stage2-1024_mdm_waymo_infer_synthetic.yaml", 64, 72, 128, 50, 7.5, 0.7, 212.49, 5.7543),
 }
 METRIC = "denoised frames/sec @576x1024x16f, 50 DDIM steps"
+TRAFFIC_CONV_L0 = 547.5e6      # dram read 379.4 MB + write 168.0 MB (profiles/r1_tapgemm_tc3_conv_l0.md)
 
 
 def peaks():
@@ -241,16 +243,19 @@ def main():
     clocks = sampler_clock.stop()
     launches = eng.launch_count() + veng.launch_count() - l0
 
-    # ---- e2e: pinned host inputs -> H2D every step, decoded frames -> D2H (uint8-free: fp16 as produced) ----
+    # ---- e2e: pinned host inputs -> H2D every step; decoded clip -> uint8 frames on the GPU (the driver's post-decode
+    # step, mudg_postdecode) -> D2H of the uint8 frames the driver writes to disk ----
+    from mudg_b200.engine import postdecode, MUDG_POST_COLOR
     host = make_cond(123 + rank, None, pin=True)
-    out_host = torch.empty((B, 3, T, 8 * h, 8 * w), dtype=torch.float16).pin_memory()
+    out_host = torch.empty((B, T, 3, 8 * h, 8 * w), dtype=torch.uint8).pin_memory()
     sync_all()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for i in range(args.steps):
         c = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
         fr = clip(c, 123 + rank + world * i)
-        out_host.copy_(fr, non_blocking=True)
+        rgb, _, _ = postdecode(fr, [MUDG_POST_COLOR] * B)
+        out_host.copy_(rgb, non_blocking=True)
     e3.record()
     sync_all()
     ms_e2e = e2.elapsed_time(e3)
@@ -293,14 +298,15 @@ def main():
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "tapgemm_tc2_kernel (tcgen05 tap-GEMM: all Linear/Conv2d/Conv3d layers)",
+            "roofline": {"bound": "tensor", "kernel": "tapgemm_tc3_kernel / tapgemm_tc2_kernel (tcgen05 tap-GEMM, CTA-pair and single-CTA variants: all Linear/Conv2d/Conv3d layers)",
                          "achieved": gemm_tf, "peak": sus, "unit": "TFLOP/s", "frac": gemm_tf / sus, "peak_source": how,
                          "launches_timed": int(gn.value), "kernel_ms_per_step": gms.value,
                          "kernel_share_of_step": gms.value / ms_prof, "instrumented_step_ms": ms_prof,
                          "how": "CUDA-event pair around each launch, one extra (eager) clip after the timed region",
                          # dram__bytes_read+write of ONE launch of this kernel from the committed ncu --set full capture
-                         # (profiles/r1_tapgemm_tc2_conv_l0.md: level-0 3x3 conv 320->320, 0.544 TFLOP, 380 MB algorithmic)
-                         "traffic": 341.4e6, "traffic_unit": "bytes/launch (level-0 conv capture)",
+                         # (profiles/r1_tapgemm_tc3_conv_l0.md: level-0 3x3 conv 320->320, 0.544 TFLOP, 566 MB algorithmic
+                         # = activation in + residual in + out)
+                         "traffic": TRAFFIC_CONV_L0, "traffic_unit": "bytes/launch (level-0 conv capture)",
                          "path": {"achieved": path_tf, "frac": path_tf / sus, "algorithmic_tflop_per_clip": flops_clip / 1e12}},
         }
         if not args.no_cpu_baseline:

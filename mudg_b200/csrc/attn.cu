@@ -487,6 +487,10 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
               const float p1 = ((i & 2) && F2_POLY) ? ex2_poly(a1) : ex2_approx(a1);
               l4[(i >> 1) & 3] += p0 + p1;
               sr[c][i >> 1] = pack_half2(p0, p1);
+              // early hand-over of the MUFU turn: the partner group may start its exponentials when 3/4 (or 1/2) of
+              // mine are done, so the unit has a second warp to pick from during my (single-warp, latency-limited) tail
+              if (i == 30 && do_stagger && ((c == 2 && p.stagger == 2) || (c == 1 && p.stagger == 3) || (c == 0 && p.stagger == 4)))
+                mbar_arrive_after(&exp_done[grp], sr[c][15]);
             }
           lsum = (l4[0] + l4[1]) + (l4[2] + l4[3]);
         } else {
@@ -500,7 +504,7 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
               sr[c][i >> 1] = pack_half2(p0, p1);
             }
         }
-        if (do_stagger) mbar_arrive(&exp_done[grp]);
+        if (do_stagger && (p.stagger == 1 || p.stagger > 4 || valid < 128)) mbar_arrive(&exp_done[grp]);
         if ((threadIdx.x & 127) == 64) F2_TRACE(grp, it, 3);     // exponentials done
         // the previous P V of this tile must have retired before P (and possibly O) are overwritten
         if (j > 0) {
@@ -1049,8 +1053,8 @@ void flash_attention(const FlashArgs& a, cudaStream_t st) {
   p.nseg = a.nseg;
   p.scale_log2 = a.scale * 1.4426950408889634f;
   static const int stagger_env = [] {
-    const char* e = getenv("MUDG_FLASH_STAGGER");
-    return e ? atoi(e) : 1;
+    const char* e = getenv("MUDG_FLASH_STAGGER");   // 0 off, 1 hand over after all exponentials, 2 / 3 / 4 after 3/4, 1/2, 1/4
+    return e ? atoi(e) : 3;
   }();
   p.stagger = stagger_env;
   p.trace = g_flash_trace;

@@ -34,6 +34,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// arrive that the compiler may not schedule before `dep` has been computed (the value itself is not used)
+__device__ __forceinline__ void mbar_arrive_after(uint64_t* bar, uint32_t dep) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];  // after %1" ::"r"(smem_u32(bar)), "r"(dep) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
   asm volatile(

@@ -94,11 +94,45 @@ def test_product_path_fails_loudly_without_gpu():
 def test_product_does_not_import_oracle():
     """The oracle is test infrastructure: nothing under mudg_b200/, lvdm/, utils/ may reference it."""
     pat = re.compile(r"^\s*(from|import)\s+oracle\b|mudg_oracle", re.M)
-    for top in ("mudg_b200", "lvdm", "utils"):
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|mudg_oracle|post_oracle", re.M)
+    for top in ("mudg_b200", "lvdm", "utils", "virtual_render"):
         for dp, _, files in os.walk(os.path.join(ROOT, top)):
             for f in files:
                 if f.endswith((".py", ".cu", ".h", ".cuh")):
                     assert not pat.search(open(os.path.join(dp, f)).read()), os.path.join(dp, f)
+
+
+def test_next_rows_fail_loudly_without_gpu():
+    """Resampler (f.3) and the post-decode helpers (f.2): reference surface present, no CPU fallback behind it."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mudg_b200._lib import MudgError
+    from lvdm.modules.encoders.resampler import Resampler
+    from virtual_render import eval_tools as E
+    m = Resampler(dim=128, depth=1, dim_head=64, heads=2, num_queries=4, embedding_dim=96, output_dim=128, video_length=4)
+    assert set(m.state_dict()) >= {"latents", "proj_in.weight", "layers.0.0.to_kv.weight", "layers.0.1.3.weight", "norm_out.bias"}
+    with pytest.raises(MudgError):
+        m(torch.zeros(1, 9, 96))
+    for name in ("save_virtual_color_results", "save_virtual_depth_results", "save_virtual_semantic_results", "colormap",
+                 "visualize_depth", "visualize_semantic"):
+        assert callable(getattr(E, name))
+    with pytest.raises(MudgError):
+        E.visualize_semantic(torch.zeros(3, 4, 8, dtype=torch.uint8))
+    with pytest.raises(MudgError):
+        E.convert_clip(torch.zeros(1, 3, 2, 4, 8), 0)
+
+
+def test_context_tensor_identity_is_kept():
+    """DiffusionWrapper hands the UNet the SAME context tensor object every DDIM step (the K/V cache is keyed on it)."""
+    from lvdm.models.ddpm3d import DiffusionWrapper
+    w = DiffusionWrapper.__new__(DiffusionWrapper)
+    a, b = torch.zeros(1, 77, 8), torch.ones(1, 16, 8)
+    assert DiffusionWrapper._context(w, [a]) is a
+    c1 = DiffusionWrapper._context(w, [a, b])
+    assert DiffusionWrapper._context(w, [a, b]) is c1 and torch.equal(c1, torch.cat([a, b], 1))
+    b.add_(1)                                   # in-place change -> new version -> re-concatenated
+    c2 = DiffusionWrapper._context(w, [a, b])
+    assert c2 is not c1 and torch.equal(c2, torch.cat([a, b], 1))
 
 
 def test_c_abi_exports_every_declared_symbol():

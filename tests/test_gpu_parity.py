@@ -343,3 +343,37 @@ def test_multicond_sampler_vs_reference_golden(golden_dir):
     psnr = 10 * torch.log10(ref.abs().max() ** 2 / ((z.float().cpu() - ref) ** 2).mean())
     print(f"2-step multicond sample: max|d|={float(err.max()):.4f} latent PSNR={float(psnr):.1f} dB")
     assert float(err.max()) < 0.15 and float(psnr) > 40.0
+
+
+def test_resampler_vs_reference_golden(golden_dir):
+    """Next row f.3: lvdm.modules.encoders.resampler.Resampler (drop-in, one C-ABI call) against the reference module's
+    output on the same seeded weights; then the shipped full-size configuration against the oracle."""
+    from lvdm.modules.encoders.resampler import Resampler
+    from oracle import mudg_oracle as O
+    g = np.load(os.path.join(golden_dir, "resampler_small.npz"))
+    cfg = dict(dim=128, depth=2, dim_head=64, heads=2, num_queries=4, embedding_dim=96, output_dim=128, ff_mult=4, video_length=4)
+    sd = O.seeded_state_dict(O.resampler_param_shapes(**cfg), seed=5)
+    m = Resampler(**cfg)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    y = m(torch.from_numpy(g["x"]).cuda())
+    torch.cuda.synchronize()
+    err = (y.float().cpu() - torch.from_numpy(g["y"])).abs()
+    assert y.shape == (3, 16, 128) and float(err.max()) < 0.03 and float(err.mean()) < 0.004, (float(err.max()), float(err.mean()))
+    # full size (infer yaml): [2, 257, 1280] -> [2, 256, 1024]
+    full = dict(dim=1024, depth=4, dim_head=64, heads=12, num_queries=16, embedding_dim=1280, output_dim=1024, ff_mult=4,
+                video_length=16)
+    fsd = O.seeded_state_dict(O.resampler_param_shapes(**full), seed=6)
+    mf = Resampler(**full)
+    mf.load_state_dict(fsd, strict=True)
+    mf = mf.cuda().eval()
+    gen = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 257, 1280, generator=gen)
+    ref = O.resampler_forward(fsd, x, heads=12)
+    out = mf(x.cuda())
+    torch.cuda.synchronize()
+    ferr = (out.float().cpu() - ref).abs()
+    assert out.shape == (2, 256, 1024) and float(ferr.max()) < 0.05 and float(ferr.mean()) < 0.005, (float(ferr.max()), float(ferr.mean()))
+    # batch independence (size-independent property): sample 1 alone == sample 1 of the batch
+    one = mf(x[1:2].cuda())
+    assert float((one[0].float() - out[1].float()).abs().max()) < 2e-2

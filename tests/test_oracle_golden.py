@@ -127,3 +127,14 @@ def test_multicond_sample_matches_reference(golden_dir):
                                   uc_context=uc_ctx, uc_img_context=uc_img, class_label=t("lab"), fs=t("fs"), cfg_scale=7.5,
                                   cfg_img=3.0, guidance_rescale=0.7, eta=1.0, noises=noises)
     assert float((out - t("samples")).abs().max()) < 1e-3
+
+
+def test_resampler_matches_reference(golden_dir):
+    """Resampler (next row f.3): oracle restatement vs the reference module's output; full-size key layout."""
+    g = np.load(os.path.join(golden_dir, "resampler_small.npz"))
+    cfg = dict(dim=128, depth=2, dim_head=64, heads=2, num_queries=4, embedding_dim=96, output_dim=128, ff_mult=4, video_length=4)
+    sd = O.seeded_state_dict(O.resampler_param_shapes(**cfg), seed=5)
+    y = O.resampler_forward(sd, torch.from_numpy(g["x"]), heads=2)
+    assert float((y - torch.from_numpy(g["y"])).abs().max()) < 1e-5
+    full = O.resampler_param_shapes()
+    assert len(full) == 51 and full["latents"] == (1, 256, 1024) and full["layers.3.0.to_kv.weight"] == (1536, 1024)
