@@ -377,3 +377,39 @@ def test_resampler_vs_reference_golden(golden_dir):
     # batch independence (size-independent property): sample 1 alone == sample 1 of the batch
     one = mf(x[1:2].cuda())
     assert float((one[0].float() - out[1].float()).abs().max()) < 2e-2
+
+
+def test_unet_full_size_properties():
+    """BASELINE full size (MDM1024: N=2 CFG batch, T=16, 72x128 latent, 1.44 B-parameter graph, random weights generated
+    on the GPU): size-independent properties of the forward through the C-ABI -- finite output of the right shape,
+    samples of a batch are independent (N=2 result == two N=1 results within fp16 re-rounding), and a replay of the
+    captured CUDA graph reproduces the eager result."""
+    import gpu_probe_full as PF
+    from mudg_b200.engine import Engine, MUDG_UNET
+    from mudg_b200.layout import unet_layout
+    eng = Engine(PF.UNET, PF.VAE)
+    eng.load_state_dict(PF.gpu_weights(unet_layout(**PF.UNET), 0), MUDG_UNET)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    N, T, h, w = 2, 16, 72, 128
+    x = torch.randn(N, 12, T, h, w, device="cuda", generator=g)
+    ctx = torch.randn(N, 77 + 16 * T, 1024, device="cuda", generator=g)
+    ts = torch.tensor([999, 499], device="cuda")
+    lab = torch.tensor([0, 500], device="cuda")
+    fs = torch.full((N,), 10, device="cuda", dtype=torch.long)
+    eng.set_context(ctx, T)
+    y_eager = eng.unet_forward(x, ts, lab, fs).clone()          # first call: eager
+    y_cap = eng.unet_forward(x, ts, lab, fs).clone()            # second: capture + launch
+    y_rep = eng.unet_forward(x, ts, lab, fs).clone()            # third: graph replay
+    torch.cuda.synchronize()
+    assert y_eager.shape == (N, 4, T, h, w) and bool(torch.isfinite(y_eager.float()).all())
+    assert float(y_eager.float().abs().max()) > 0.1
+    assert float((y_cap.float() - y_eager.float()).abs().max()) < 2e-2      # GroupNorm sums use atomics: not bitwise
+    assert float((y_rep.float() - y_cap.float()).abs().max()) < 2e-2
+    for i in range(N):
+        eng.set_context(ctx[i:i + 1].contiguous(), T)
+        one = eng.unet_forward(x[i:i + 1].contiguous(), ts[i:i + 1], lab[i:i + 1], fs[i:i + 1])
+        torch.cuda.synchronize()
+        d = (one[0].float() - y_eager[i].float()).abs()
+        assert float(d.max()) < 5e-2 and float(d.mean()) < 2e-3, (i, float(d.max()), float(d.mean()))
+    del eng
+    torch.cuda.empty_cache()
