@@ -184,6 +184,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     yaml_name, T, h, w, S, cfg_scale, g_rescale, unet_tf, vae_tf = CONFIGS[args.config]
     model = build_model(args.config, dev)
