@@ -573,10 +573,9 @@ Act Model::spatial_transformer(const Act& xin, const Layer& l) {   // attention.
   release_bytes(s1);
   Act a1 = alloc(xin.B, xin.T, xin.H, xin.W, C);
   const int hw_pad = round_up(HW, 8);
-  static const bool no_vt = [] { const char* e = getenv("MUDG_NO_VT"); return e && e[0] == '1'; }();   // debug (with MUDG_FLASH_V1=1)
-  __half* vt = static_cast<__half*>(alloc_bytes(no_vt ? 1024 : sizeof(__half) * (size_t)F * C * hw_pad));   // V^T [F][C][HW]
+  __half* vt = static_cast<__half*>(alloc_bytes(sizeof(__half) * (size_t)F * C * hw_pad));   // V^T [F][C][HW]
   if (live()) {
-    if (!no_vt) transpose_v(qkv.p + 2 * C, 3 * C, HW, F, l.heads, vt, hw_pad, st_);
+    transpose_v(qkv.p + 2 * C, 3 * C, HW, F, l.heads, vt, hw_pad, st_);
     FlashArgs fa;
     fa.Q = qkv.p; fa.q_pitch = 3 * C; fa.O = a1.p; fa.o_pitch = C; fa.F = F; fa.Nq = HW; fa.heads = l.heads;
     fa.nseg = 1;
