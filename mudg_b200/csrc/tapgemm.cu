@@ -716,6 +716,11 @@ __device__ __forceinline__ G2Tile g3_decode(const G3Params& p, int tile, int ran
   return t;
 }
 
+// EPI: epilogue specialisation.  -1 = everything decided at run time (and the only variant with the GEGLU path);
+// >= 0: bit 0 bias, bit 1 per-sample bias, bit 2 residual, bit 3 folded LayerNorm, alpha == 1, no GEGLU.  Tested from the
+// kernel-parameter bank, every `if (p.b.bias ...)` in the 32-column slice loop is a dependent LDCU -> UISETP -> BRA.U chain of
+// 60-80 clocks that a lone, latency-bound epilogue warp cannot overlap with anything (clock64 trace: ~500 clk per slice).
+template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G3_THREADS, 1)
 tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
                    const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmD,
@@ -835,7 +840,14 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int ih = r % p.b.bh; r /= p.b.bh;
     const int it_ = r % p.b.bt;
     const int ib_ = r / p.b.bt;
-    const int csh = p.b.geglu ? 7 : 6;          // accumulator columns per chunk: 64, or 128 (64 value + 64 gate)
+    constexpr bool kGeneric = EPI < 0;
+    const bool f_geglu = kGeneric && p.b.geglu;
+    const bool f_bias = kGeneric ? (p.b.bias != nullptr) : ((EPI & 1) != 0);
+    const bool f_bias2 = kGeneric ? (p.b.bias2 != nullptr) : ((EPI & 2) != 0);
+    const bool f_res = kGeneric ? (p.R != nullptr) : ((EPI & 4) != 0);
+    const bool f_ln = kGeneric ? (p.b.ln_stats != nullptr) : ((EPI & 8) != 0);
+    const bool f_alpha = kGeneric && !p.alpha_is_one;
+    const int csh = f_geglu ? 7 : 6;            // accumulator columns per chunk: 64, or 128 (64 value + 64 gate)
     auto arrive_empty = [&](uint32_t bar) {     // MUDG_GEMM_DBG bit 1: fall back to the (slow) release arrive
       if (p.dbg & 2) mbar_arrive_cluster(bar);
       else mbar_arrive_cluster_relaxed(bar);
@@ -860,8 +872,8 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const bool row_ok = pw < p.dimW && ph < p.dimH && pt < p.b.dimT && pb < p.dimB;
       const int64_t pix = (((int64_t)pb * p.b.dimT + pt) * p.dimH + ph) * p.dimW + pw;
       float2 ln_ms = make_float2(0.f, 1.f);
-      if (p.b.ln_stats != nullptr && row_ok) ln_ms = __ldg(p.b.ln_stats + pix);
-      if (p.b.geglu) {
+      if (f_ln && row_ok) ln_ms = __ldg(p.b.ln_stats + pix);
+      if (f_geglu) {
         mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
         __syncwarp();
         tc_fence_after();
@@ -932,13 +944,13 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         continue;
       }
       int sample = 0;
-      if (p.b.bias2 != nullptr) {
+      if (f_bias2) {
         sample = fd_div(p.b.fd_b2, pb * p.b.dimT + pt);
         if (sample >= p.b.nb2) sample = p.b.nb2 - 1;
       }
       // residual row of this thread: chunk ch covers 8 uint4 (64 columns) starting at rp + 8 ch
-      const uint4* rp = (p.R != nullptr && row_ok) ? reinterpret_cast<const uint4*>(p.R + pix * p.b.n_out + tl.n0) : nullptr;
-      if (p.R != nullptr && tile + n_clusters < p.total_tiles) {
+      const uint4* rp = (f_res && row_ok) ? reinterpret_cast<const uint4*>(p.R + pix * p.b.n_out + tl.n0) : nullptr;
+      if (f_res && tile + n_clusters < p.total_tiles) {
         // residual rows of this CTA's NEXT tile: pull them from HBM into L2 a whole mainloop ahead of their use
         // (128 B line = one chunk; the two groups take alternate lines)
         const G2Tile nx = g3_decode(p, tile + n_clusters, (int)rank);
@@ -960,8 +972,14 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tc_fence_after();
       if (q == 2 && lane == 0) G3_TRACE(2 + grp, lt, 1);       // accumulator complete
       const int nslices = mine * 2;          // my 32-column slices, two per chunk
-#pragma unroll 1
-      for (int sl = 0; sl < nslices; sl++) {
+      // Two register sets for the accumulator slices: the tcgen05.ld of slice s+1 is in flight while slice s is converted
+      // and staged (tcgen05.wait::ld covers every outstanding load, so the next one is issued right after the wait).
+      // Only where it fits the 168-register cap without spilling (measured: with the residual registers, or in the
+      // run-time variant that also carries the GEGLU path, the spills cost more than the overlap gains).
+      constexpr bool kPrefetchLd = EPI >= 0 && (EPI & 4) == 0;
+      uint32_t va[32], vb[32];
+      if (kPrefetchLd) tmem_ld32(t_row + first * 64, va);
+      auto do_slice = [&](int sl, uint32_t (&v)[32], uint32_t (&vn)[32]) {
         const int hf = sl & 1;
         const int ch = first + (sl >> 1) * 2;                  // chunk: accumulator / output columns [64 ch, 64 ch + 64)
         const int coff = ch * 64 + hf * 32;
@@ -976,21 +994,26 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             for (int j = 0; j < 4; j++) res_nxt[j] = __ldg(np4 + j);
           }
         }
-        uint32_t v[32];
-        tmem_ld32(t_row + coff, v);
         uint8_t* stg = stg_grp + (chunk_no & 1) * 16384;
         uint8_t* srow = stg + row * 128;
-        tmem_ld_wait();
-        if (sl == nslices - 1) tc_fence_before();   // last TMEM read of this accumulator (released at the next group_sync)
+        if (kPrefetchLd) {
+          tmem_ld_wait_regs(v);
+          if (sl + 1 < nslices) tmem_ld32(t_row + (first + ((sl + 1) >> 1) * 2) * 64 + ((sl + 1) & 1) * 32, vn);
+          else tc_fence_before();            // last TMEM read of this accumulator (released at the next group_sync)
+        } else {
+          tmem_ld32(t_row + coff, v);
+          tmem_ld_wait();
+          if (sl == nslices - 1) tc_fence_before();
+        }
         const int col0 = tl.n0 + coff;
         float f[32];
 #pragma unroll
         for (int i = 0; i < 32; i++) f[i] = __uint_as_float(v[i]);
-        if (!p.alpha_is_one) {
+        if (f_alpha) {
 #pragma unroll
           for (int i = 0; i < 32; i++) f[i] *= p.b.alpha;
         }
-        if (p.b.ln_stats != nullptr) {
+        if (f_ln) {
           const float4* cp = reinterpret_cast<const float4*>(p.b.ln_c1 + col0);
           const float k = -ln_ms.x * ln_ms.y;
 #pragma unroll
@@ -1000,7 +1023,7 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             f[4 * i4 + 2] = fmaf(f[4 * i4 + 2], ln_ms.y, k * c4.z); f[4 * i4 + 3] = fmaf(f[4 * i4 + 3], ln_ms.y, k * c4.w);
           }
         }
-        if (p.b.bias != nullptr) {
+        if (f_bias) {
           const float4* bp = reinterpret_cast<const float4*>(p.b.bias + col0);
 #pragma unroll
           for (int i4 = 0; i4 < 8; i4++) {
@@ -1008,7 +1031,7 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             f[4 * i4] += b4.x; f[4 * i4 + 1] += b4.y; f[4 * i4 + 2] += b4.z; f[4 * i4 + 3] += b4.w;
           }
         }
-        if (p.b.bias2 != nullptr) {
+        if (f_bias2) {
           const float4* bp = reinterpret_cast<const float4*>(p.b.bias2 + (size_t)sample * p.b.N + col0);
 #pragma unroll
           for (int i4 = 0; i4 < 8; i4++) {
@@ -1045,6 +1068,16 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           __syncwarp();
           chunk_no++;
           if (q == 2 && lane == 0) G3_TRACE(2 + grp, lt, 2 + (sl >> 1));   // chunk stored
+        }
+      };
+#pragma unroll 1
+      for (int ci = 0; ci < mine; ci++) {
+        if (kPrefetchLd) {
+          do_slice(2 * ci, va, vb);
+          do_slice(2 * ci + 1, vb, va);
+        } else {
+          do_slice(2 * ci, va, va);
+          do_slice(2 * ci + 1, va, va);
         }
       }
     }
@@ -1312,13 +1345,31 @@ void tapgemm_tc3(const TapGemm& g, cudaStream_t st) {
   const CUtensorMap* md = get_tmap(g.D, ddims, dstr, abox);
   static bool attr_set = false;
   if (!attr_set) {
-    MUDG_CUDA(cudaFuncSetAttribute(tapgemm_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM));
+    MUDG_CUDA(cudaFuncSetAttribute(tapgemm_tc3_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM));
+    MUDG_CUDA(cudaFuncSetAttribute(tapgemm_tc3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM));
+    MUDG_CUDA(cudaFuncSetAttribute(tapgemm_tc3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM));
+    MUDG_CUDA(cudaFuncSetAttribute(tapgemm_tc3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM));
+    MUDG_CUDA(cudaFuncSetAttribute(tapgemm_tc3_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM));
+    MUDG_CUDA(cudaFuncSetAttribute(tapgemm_tc3_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM));
     attr_set = true;
   }
   const int clusters = (int)std::min<int64_t>(total, sm_count() / 2);
   p.rot_div = FastDiv{0u, 0u, 0};
   if (p.nt > 1 && clusters % p.nt == 0) p.rot_div = make_fastdiv(clusters);
-  tapgemm_tc3_kernel<<<2 * clusters, G3_THREADS, G3_SMEM, st>>>(*ma, *mb0, *mb1, *md, p);
+  // epilogue specialisation (see the kernel's EPI comment); MUDG_GEMM_EPI=0 forces the run-time variant
+  static const bool epi_on = [] { const char* e = getenv("MUDG_GEMM_EPI"); return !(e && e[0] == '0'); }();
+  int epi = -1;
+  if (epi_on && !g.geglu && g.alpha == 1.f)
+    epi = (g.bias ? 1 : 0) | (g.bias2 ? 2 : 0) | (g.R ? 4 : 0) | (g.ln_stats ? 8 : 0);
+  const dim3 grid(2 * clusters);
+  switch (epi) {
+    case 0: tapgemm_tc3_kernel<0><<<grid, G3_THREADS, G3_SMEM, st>>>(*ma, *mb0, *mb1, *md, p); break;
+    case 1: tapgemm_tc3_kernel<1><<<grid, G3_THREADS, G3_SMEM, st>>>(*ma, *mb0, *mb1, *md, p); break;
+    case 3: tapgemm_tc3_kernel<3><<<grid, G3_THREADS, G3_SMEM, st>>>(*ma, *mb0, *mb1, *md, p); break;
+    case 5: tapgemm_tc3_kernel<5><<<grid, G3_THREADS, G3_SMEM, st>>>(*ma, *mb0, *mb1, *md, p); break;
+    case 9: tapgemm_tc3_kernel<9><<<grid, G3_THREADS, G3_SMEM, st>>>(*ma, *mb0, *mb1, *md, p); break;
+    default: tapgemm_tc3_kernel<-1><<<grid, G3_THREADS, G3_SMEM, st>>>(*ma, *mb0, *mb1, *md, p); break;
+  }
   MUDG_CUDA(cudaGetLastError());
 }
 
