@@ -24,3 +24,12 @@ def noise_like(shape, device, repeat=False):
     if repeat:
         return torch.randn((1, *shape[1:]), device=device).repeat(shape[0], *((1,) * (len(shape) - 1)))
     return torch.randn(shape, device=device)
+
+
+def autocast(f, enabled=True):
+    """Decorator with the semantics of the reference one (lvdm/common.py:16-22): run `f` under CUDA autocast with the ambient settings."""
+    def do_autocast(*args, **kwargs):
+        with torch.cuda.amp.autocast(enabled=enabled, dtype=torch.get_autocast_gpu_dtype(),
+                                     cache_enabled=torch.is_autocast_cache_enabled()):
+            return f(*args, **kwargs)
+    return do_autocast

@@ -71,6 +71,9 @@ def _megfile():
     import os
     mod.smart_exists = os.path.exists
     mod.smart_makedirs = lambda p, exist_ok=True: os.makedirs(p, exist_ok=exist_ok)
+    mod.smart_path_join = os.path.join           # virtual_render/data_tools.py:5 (local paths only)
+    mod.smart_listdir = os.listdir
+    mod.smart_isdir = os.path.isdir
     return mod
 
 

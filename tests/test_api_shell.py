@@ -149,3 +149,27 @@ def test_c_abi_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     lib.mudg_last_error.restype = ctypes.c_char_p
     assert lib.mudg_last_error() is not None
+
+
+def test_unchanged_reference_driver_imports_against_the_dropin_packages():
+    """B1: with this repo first and a reference checkout later on sys.path, the UNCHANGED driver module
+    (virtual_render/virtual_pose_render.py) imports, and its sampler / config / post-decode symbols are this repo's,
+    while modules not replaced here (data_tools) come from the reference.  Build container only (needs /root/reference)."""
+    import subprocess
+    import sys
+    ref = "/root/reference"
+    if not os.path.isdir(os.path.join(ref, "virtual_render")):
+        pytest.skip("reference checkout not present")
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from mudg_b200 import compat; compat.install()\n"
+        "import inspect, virtual_render.virtual_pose_render as V, virtual_render.data_tools as D\n"
+        "print(inspect.getsourcefile(V)); print(inspect.getsourcefile(V.DDIMSampler)); print(inspect.getsourcefile(V.DDIMSampler_multicond))\n"
+        "print(inspect.getsourcefile(V.instantiate_from_config)); print(inspect.getsourcefile(V.save_virtual_depth_results))\n"
+        "print(inspect.getsourcefile(D))\n" % (ref, ROOT))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp", timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.strip().splitlines()[-6:]
+    assert lines[0].startswith(ref) and lines[5].startswith(ref)
+    for ln in lines[1:5]:
+        assert ln.startswith(ROOT), lines
