@@ -33,10 +33,13 @@ __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.f + __ex
 // so partial sums stay in registers until one flush at the end.
 __global__ void gn_stats_kernel(const __half* __restrict__ x, double* __restrict__ sums, int64_t R, int C, int cpg,
                                 int rows_per_block) {
-  __shared__ float acc[32][2];
+  // fp64 accumulators: the ORDER of the shared / global atomics varies from run to run, and in fp32 that moved the statistics
+  // in the 7th digit -- enough to flip fp16 roundings downstream and make two identical forwards differ by a few fp16 ulps
+  // (6e-3 max on the UNet output).  With fp64 sums of per-thread fp32 partials (fixed order) the result is repeatable.
+  __shared__ double acc[32][2];
   const int vecs = C >> 3;
   const int v = threadIdx.x % vecs, r0 = threadIdx.x / vecs, rstep = blockDim.x / vecs;
-  if (threadIdx.x < 64) (&acc[0][0])[threadIdx.x] = 0.f;
+  if (threadIdx.x < 64) (&acc[0][0])[threadIdx.x] = 0.0;
   __syncthreads();
   const int s = blockIdx.y;
   const int64_t row_begin = (int64_t)blockIdx.x * rows_per_block;
@@ -79,21 +82,21 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, double* __restrict
     for (int i = 0; i < 8; i++) {
       const int g = (v * 8 + i) / cpg;
       if (g != g_cur) {
-        atomicAdd(&acc[g_cur][0], a);
-        atomicAdd(&acc[g_cur][1], b);
+        atomicAdd(&acc[g_cur][0], (double)a);
+        atomicAdd(&acc[g_cur][1], (double)b);
         a = b = 0.f;
         g_cur = g;
       }
       a += sm[i];
       b += sq[i];
     }
-    atomicAdd(&acc[g_cur][0], a);
-    atomicAdd(&acc[g_cur][1], b);
+    atomicAdd(&acc[g_cur][0], (double)a);
+    atomicAdd(&acc[g_cur][1], (double)b);
   }
   __syncthreads();
   if (threadIdx.x < 64) {
     const int g = threadIdx.x >> 1, k = threadIdx.x & 1;
-    atomicAdd(&sums[((int64_t)s * 32 + g) * 2 + k], (double)acc[g][k]);
+    atomicAdd(&sums[((int64_t)s * 32 + g) * 2 + k], acc[g][k]);
   }
 }
 
