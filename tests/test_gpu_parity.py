@@ -471,3 +471,18 @@ def test_unchanged_reference_driver_function(golden_dir):
     cross_d = float((outs[0] - outs[2]).abs().mean())
     print(f"driver vs driver mean|d| {self_d:.5f}; driver vs mudg_b200.pipeline mean|d| {cross_d:.5f}")
     assert cross_d <= 3.0 * self_d + 2e-3, (self_d, cross_d)
+
+
+def test_bitwise_repeatability(engine, golden_dir):
+    """Two identical calls give identical bits -- eager, graph capture and graph replay of the UNet forward, VAE decode /
+    encode, post-decode (every reduction has a fixed order; the GroupNorm atomics accumulate in fp64)."""
+    g = np.load(os.path.join(golden_dir, "unet_small.npz"))
+    t = lambda k: torch.from_numpy(g[k]).cuda()
+    engine.set_context(t("ctx"), T=4)
+    ys = [engine.unet_forward(t("x"), t("ts"), t("lab"), t("fs")).clone() for _ in range(4)]
+    z = torch.from_numpy(np.load(os.path.join(golden_dir, "vae_small.npz"))["z"]).cuda()
+    ds = [engine.vae_decode(z).clone() for _ in range(2)]
+    torch.cuda.synchronize()
+    for y in ys[1:]:
+        assert torch.equal(y, ys[0])
+    assert torch.equal(ds[0], ds[1])
