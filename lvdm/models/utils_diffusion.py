@@ -20,19 +20,23 @@ def timestep_embedding(timesteps, dim, max_period=10000, repeat_only=False):
 
 
 def make_beta_schedule(schedule, n_timestep, linear_start=1e-4, linear_end=2e-2, cosine_s=8e-3):
-    """utils_diffusion.py:31-53."""
+    """utils_diffusion.py:31-53.  float64 torch arithmetic in the reference's order (np.linspace / np.cos differ from
+    torch's in the last ulp, and the tables are compared bit for bit); returns a numpy array like the reference."""
+    f64 = torch.float64
     if schedule == "linear":
-        return np.linspace(linear_start ** 0.5, linear_end ** 0.5, n_timestep, dtype=np.float64) ** 2
-    if schedule == "cosine":
-        t = np.arange(n_timestep + 1, dtype=np.float64) / n_timestep + cosine_s
-        a = np.cos(t / (1 + cosine_s) * np.pi / 2) ** 2
+        betas = torch.linspace(linear_start ** 0.5, linear_end ** 0.5, n_timestep, dtype=f64) ** 2
+    elif schedule == "cosine":
+        t = torch.arange(n_timestep + 1, dtype=f64) / n_timestep + cosine_s
+        a = torch.cos(t / (1 + cosine_s) * np.pi / 2).pow(2)
         a = a / a[0]
-        return np.clip(1 - a[1:] / a[:-1], 0, 0.999)
-    if schedule == "sqrt_linear":
-        return np.linspace(linear_start, linear_end, n_timestep, dtype=np.float64)
-    if schedule == "sqrt":
-        return np.linspace(linear_start, linear_end, n_timestep, dtype=np.float64) ** 0.5
-    raise ValueError(f"schedule '{schedule}' unknown.")
+        betas = torch.from_numpy(np.clip((1 - a[1:] / a[:-1]).numpy(), 0, 0.999))
+    elif schedule == "sqrt_linear":
+        betas = torch.linspace(linear_start, linear_end, n_timestep, dtype=f64)
+    elif schedule == "sqrt":
+        betas = torch.linspace(linear_start, linear_end, n_timestep, dtype=f64) ** 0.5
+    else:
+        raise ValueError(f"schedule '{schedule}' unknown.")
+    return betas.numpy()
 
 
 def rescale_zero_terminal_snr(betas):

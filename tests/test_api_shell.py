@@ -173,3 +173,32 @@ def test_unchanged_reference_driver_imports_against_the_dropin_packages():
     assert lines[0].startswith(ref) and lines[5].startswith(ref)
     for ln in lines[1:5]:
         assert ln.startswith(ROOT), lines
+
+
+def test_schedule_helpers_match_reference_golden(golden_dir):
+    """lvdm.models.utils_diffusion (host side of a1 / a3 / a6): every beta schedule, DDIM spacing, eta, the timestep
+    embedding and rescale_noise_cfg against the reference's own outputs (oracle/make_golden_schedules.py)."""
+    from lvdm.models import utils_diffusion as U
+    g = np.load(os.path.join(golden_dir, "schedules.npz"))
+    for sched in ("linear", "cosine", "sqrt_linear", "sqrt"):
+        b = np.asarray(U.make_beta_schedule(sched, 1000, linear_start=0.00085, linear_end=0.012), dtype=np.float64)
+        assert np.array_equal(b, g[f"betas_{sched}"]), sched
+    betas = U.make_beta_schedule("linear", 1000, linear_start=0.00085, linear_end=0.012)
+    zs = np.asarray(U.rescale_zero_terminal_snr(betas), dtype=np.float64)
+    assert np.array_equal(zs, g["betas_zero_snr"])
+    ac = torch.tensor(np.cumprod(1.0 - zs, axis=0), dtype=torch.float32)
+    for method in ("uniform", "quad", "uniform_trailing"):
+        for S in (50, 25, 7):
+            ts = U.make_ddim_timesteps(method, S, 1000, verbose=False)
+            assert np.array_equal(np.asarray(ts), g[f"ts_{method}_{S}"]), (method, S)
+            for eta in (0.0, 1.0):
+                sig, a, ap = U.make_ddim_sampling_parameters(ac.cpu(), ts, eta, verbose=False)
+                assert np.array_equal(np.asarray(sig, dtype=np.float64), g[f"sig_{method}_{S}_{eta}"]), (method, S, eta)
+                assert np.array_equal(np.asarray(a, dtype=np.float64), g[f"a_{method}_{S}_{eta}"])
+                assert np.array_equal(np.asarray(ap, dtype=np.float64), g[f"ap_{method}_{S}_{eta}"])
+    t = torch.tensor([0, 1, 19, 500, 999], dtype=torch.long)
+    for dim in (320, 64, 7):
+        assert np.array_equal(U.timestep_embedding(t, dim).numpy(), g[f"temb_{dim}"]), dim
+    assert np.array_equal(U.timestep_embedding(t, 8, repeat_only=True).numpy(), g["temb_repeat"])
+    out = U.rescale_noise_cfg(torch.from_numpy(g["rescale_in_cfg"]), torch.from_numpy(g["rescale_in_txt"]), guidance_rescale=0.7)
+    assert np.array_equal(out.numpy(), g["rescale_out"])
