@@ -202,3 +202,19 @@ def test_schedule_helpers_match_reference_golden(golden_dir):
     assert np.array_equal(U.timestep_embedding(t, 8, repeat_only=True).numpy(), g["temb_repeat"])
     out = U.rescale_noise_cfg(torch.from_numpy(g["rescale_in_cfg"]), torch.from_numpy(g["rescale_in_txt"]), guidance_rescale=0.7)
     assert np.array_equal(out.numpy(), g["rescale_out"])
+
+
+def test_host_tensor_helpers_match_reference_golden(golden_dir):
+    """q_sample / predict_start_from_z_and_v / predict_eps_from_z_and_v of the drop-in model and the VAE posterior
+    (CPU-generator sampling, logvar clamp) against the reference's outputs (oracle/make_golden_host.py), bit for bit."""
+    from utils.utils import instantiate_from_config
+    from lvdm.distributions import DiagonalGaussianDistribution
+    g = np.load(os.path.join(golden_dir, "host_small.npz"))
+    model = instantiate_from_config(small_model_config())
+    t = lambda k: torch.from_numpy(g[k])
+    assert np.array_equal(model.q_sample(t("x0"), t("t"), t("noise")).numpy(), g["q_sample"])
+    assert np.array_equal(model.predict_start_from_z_and_v(t("x0"), t("t"), t("v")).numpy(), g["pred_start"])
+    assert np.array_equal(model.predict_eps_from_z_and_v(t("x0"), t("t"), t("v")).numpy(), g["pred_eps"])
+    d = DiagonalGaussianDistribution(t("moments"))
+    torch.manual_seed(5)
+    assert np.array_equal(d.sample().numpy(), g["sample"]) and np.array_equal(d.mode().numpy(), g["mode"])
