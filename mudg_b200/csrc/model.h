@@ -112,11 +112,11 @@ class Model {
   int T_real_ = 1;                // frames per sample of the current forward
   int N_ = 1;
   struct GraphSlot {
-    // Ring of executable graphs instantiated from ONE capture: a cudaGraphExec_t cannot run concurrently with itself and
-    // cudaGraphLaunch blocks the HOST until its previous launch has finished, which put the Python sampler loop in
-    // lock-step with the GPU (measured: 144 ms inside every unet_forward call) -- any host hiccup then idles the GPU.
-    // With a ring the host queues GRAPH_RING - 1 steps ahead.
-    static constexpr int GRAPH_RING = 8;
+    // Two executable graphs instantiated from ONE capture, launched alternately.  (Measured: cudaGraphLaunch of the
+    // 1 126-node forward blocks the host until the previous launch has drained -- 144 ms inside every unet_forward call --
+    // and a ring of 8 did not change that, so the launch queue, not the exec object, is the limit; two are kept so that a
+    // relaunch never has to wait for its own previous instance.)
+    static constexpr int GRAPH_RING = 2;
     cudaGraphExec_t exec = nullptr;          // == ring[0] once captured (non-null <=> captured)
     cudaGraphExec_t ring[GRAPH_RING] = {};
     int next = 0;
