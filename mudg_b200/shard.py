@@ -42,8 +42,14 @@ def scatter_items(items_on_rank0, key=None):
 
 
 def frames_to_uint8(frames: torch.Tensor) -> torch.Tensor:
-    """[-1,1] float frames -> uint8, the clamp + scale of virtual_pose_render.py:243 / eval_tools.py:24-27."""
-    return ((frames.float().clamp(-1.0, 1.0) + 1.0) * 127.5).round().to(torch.uint8)
+    """[-1,1] float frames -> uint8 with the reference's arithmetic (virtual_pose_render.py:243 clamp, eval_tools.py:24-27
+    `(x + 1) / 2 * 255` then truncation).  A decoded clip on the GPU ([B, 3, T, H, W]) goes through the post-decode kernel
+    (mudg_postdecode) and comes back as [B, T, 3, H, W]; anything else (host tensors in the plumbing tests) uses the same
+    fp32 formula in torch."""
+    if frames.is_cuda and frames.dim() == 5 and frames.shape[1] == 3:
+        from .engine import MUDG_POST_COLOR, postdecode
+        return postdecode(frames, [MUDG_POST_COLOR] * frames.shape[0])[0]
+    return ((frames.float().clamp(-1.0, 1.0) + 1.0) / 2.0 * 255).to(torch.uint8)
 
 
 def gather_frames(frames_u8: torch.Tensor, ids: torch.Tensor):

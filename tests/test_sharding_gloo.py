@@ -78,3 +78,13 @@ def test_assign_items_round_robin():
     assert shard.assign_items(items, 0, 4) == [0, 4, 8]
     assert shard.assign_items(items, 3, 4) == [3, 7]
     assert sum(len(shard.assign_items(items, r, 4)) for r in range(4)) == 10
+
+
+def test_frames_to_uint8_is_the_reference_conversion():
+    """Truncation, not rounding: bit for bit the conversion pinned in oracle/post_oracle.py against eval_tools.py:24-27."""
+    import numpy as np
+    from oracle import post_oracle as P
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 3, 4, 8, 8, generator=g)
+    x[0, 0, 0, 0, :4] = torch.tensor([-1.0, 1.0, 1.0 / 255 * 2 - 1, 0.5])
+    assert np.array_equal(shard.frames_to_uint8(x).numpy(), P.to_uint8(x.numpy()))
