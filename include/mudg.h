@@ -69,6 +69,14 @@ MUDG_EXPORT int mudg_set_context(MudgCtx* ctx, const void* context, int dtype, i
 MUDG_EXPORT int mudg_unet_forward(MudgCtx* ctx, const void* x, const int64_t* t, const int64_t* c_label,
                                   const int64_t* fs, int N, int T, int h, int w, void* out, void* stream);
 
+/* The classifier-free-guidance form of the same forward: the two (ddim.py:221-222) or three (ddim_multiplecond.py:213-
+ * 235) reference calls of one DDIM step differ only in `context`.  x / t / c_label / fs hold N / dup distinct samples tiled
+ * dup times (sample n == sample n % (N / dup)) -- a promise of the caller -- and the context set by mudg_set_context has N
+ * rows.  Everything before the first cross-attention (conv_in, init_attn, the first ResBlock, the first
+ * SpatialTransformer's self-attention) is evaluated once per distinct sample; results equal mudg_unet_forward's. */
+MUDG_EXPORT int mudg_unet_forward_shared(MudgCtx* ctx, const void* x, const int64_t* t, const int64_t* c_label,
+                                         const int64_t* fs, int N, int dup, int T, int h, int w, void* out, void* stream);
+
 /* DDIMSampler.p_sample_ddim after the UNet calls (ddim.py:226-277) + rescale_noise_cfg (utils_diffusion.py:147-158)
  * + predict_{eps,start}_from_z_and_v (ddpm3d.py:239-251).  x/noise/x_prev/pred_x0 fp32 [B, n]; v_* fp16 [B, n];
  * v_uncond may be NULL (no guidance).  Scalars are the per-step table entries. */
@@ -119,26 +127,6 @@ MUDG_EXPORT int64_t mudg_launch_count(MudgCtx* ctx);
 MUDG_EXPORT int mudg_profile_gemm(int enable);
 MUDG_EXPORT int mudg_profile_gemm_read(double* ms_total, double* flops_total, int64_t* launches);
 
-/* ---- single-kernel test hooks (tests/ only) ---- */
-MUDG_EXPORT int mudg_test_tapgemm(const void* A, int B, int T, int H, int W, int Cin, int mode, const void* Wt, int N,
-                                  void* D, const void* R, const float* bias, const float* bias2, int bias2_div, int nb2,
-                                  float alpha, int geglu, int backend, void* stream);
-MUDG_EXPORT int mudg_test_flash(const void* Q, int q_pitch, void* O, int o_pitch, int F, int Nq, int heads,
-                                const void* K0, const void* V0, int pitch0, int len0, int nbatch0, int div0,
-                                const void* K1, const void* V1, int pitch1, int len1, int nbatch1, int div1, float scale,
-                                int backend, void* stream);
-/* debug: device buffer [3][96][8] int64 receiving the clock64 time line of CTA 0 of the next flash launches (NULL = off) */
-MUDG_EXPORT int mudg_test_flash_trace(void* buf);
-/* debug: device buffer [4][64][8] int64 receiving the clock64 time line of CTA 0 of the next pair-GEMM launches */
-MUDG_EXPORT int mudg_test_gemm_trace(void* buf);
-/* debug: tcgen05.mma issue-rate probe; out = device int64 [ctas][2] (clocks until issued, until complete) */
-MUDG_EXPORT int mudg_test_mma_probe(int variant, int reps, int ctas, int mode, void* out, void* stream);
-MUDG_EXPORT int mudg_test_temporal_attn(const void* qkv, void* out, int B, int T, int HW, int heads, float scale,
-                                        void* stream);
-MUDG_EXPORT int mudg_test_groupnorm(const void* x, void* y, int S, int64_t rows_per_sample, int C, const float* gamma,
-                                    const float* beta, float eps, int silu, void* stream);
-MUDG_EXPORT int mudg_test_layernorm(const void* x, void* y, const float* gamma, const float* beta, int64_t rows, int C,
-                                    void* stream);
 #ifdef __cplusplus
 }
 #endif

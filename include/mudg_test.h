@@ -1,0 +1,50 @@
+/* libmudg_sm100_test.so -- TEST-ONLY companion of libmudg_sm100.so (tests/, bench diagnostics).
+ *
+ * The test library links its own copy of the product objects plus csrc/test/testhooks.cu: single-kernel entry points,
+ * CUDA-core checkers of the tcgen05 kernels' contracts, the tcgen05.mma issue-rate probe, clock64 traces and the tuning
+ * knobs.  None of these symbols exist in the product library, and the product library reads no tuning switches from
+ * the environment.  It also exports the whole product ABI (include/mudg.h), so a test can run the product path with a
+ * knob changed.
+ */
+#ifndef MUDG_TEST_H_
+#define MUDG_TEST_H_
+#include "mudg.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* knobs (csrc/common.h: struct Knobs): gemm_pair, gemm_sub, gemm_epi, gemm_dbg, flash_stagger, flash_poly, tattn_generic,
+ * gn_fuse; "reset" restores the shipped defaults */
+MUDG_EXPORT int mudg_test_set_knob(const char* name, int value);
+/* kernel the last tap-GEMM launch took: 2 = tapgemm_tc2<1>, 3 = tapgemm_tc2<2>, 4 = tapgemm_tc3; | (EPI + 1) << 8 */
+MUDG_EXPORT int mudg_test_last_gemm_path(void);
+
+/* backend 0 = product dispatch (tcgen05), 1 = CUDA-core checker.  mode 0 linear, 1 conv 3x3, 2 temporal conv (3,1,1).
+ * ln_stats ([rows] float2 mean,rstd) / ln_c1 ([N]): folded-LayerNorm epilogue (bias then carries W beta + bias), or NULL */
+MUDG_EXPORT int mudg_test_tapgemm(const void* A, int B, int T, int H, int W, int Cin, int mode, const void* Wt, int N,
+                                  void* D, const void* R, const float* bias, const float* bias2, int bias2_div, int nb2,
+                                  float alpha, int geglu, const void* ln_stats, const float* ln_c1, int backend,
+                                  void* stream);
+MUDG_EXPORT int mudg_test_flash(const void* Q, int q_pitch, void* O, int o_pitch, int F, int Nq, int heads,
+                                const void* K0, const void* V0, int pitch0, int len0, int nbatch0, int div0,
+                                const void* K1, const void* V1, int pitch1, int len1, int nbatch1, int div1, float scale,
+                                int backend, void* stream);
+/* debug: device buffer [3][96][8] int64 receiving the clock64 time line of CTA 0 of the next flash launches (NULL = off) */
+MUDG_EXPORT int mudg_test_flash_trace(void* buf);
+/* debug: device buffer [4][64][8] int64 receiving the clock64 time line of CTA 0 of the next pair-GEMM launches */
+MUDG_EXPORT int mudg_test_gemm_trace(void* buf);
+/* debug: tcgen05.mma issue-rate probe; out = device int64 [ctas][2] (clocks until issued, until complete) */
+MUDG_EXPORT int mudg_test_mma_probe(int variant, int reps, int ctas, int mode, void* out, void* stream);
+MUDG_EXPORT int mudg_test_temporal_attn(const void* qkv, void* out, int B, int T, int HW, int heads, float scale,
+                                        void* stream);
+MUDG_EXPORT int mudg_test_groupnorm(const void* x, void* y, int S, int64_t rows_per_sample, int C, const float* gamma,
+                                    const float* beta, float eps, int silu, void* stream);
+MUDG_EXPORT int mudg_test_layernorm(const void* x, void* y, const float* gamma, const float* beta, int64_t rows, int C,
+                                    void* stream);
+MUDG_EXPORT int mudg_test_ln_stats(const void* x, void* mean_rstd, int64_t rows, int C, void* stream);
+MUDG_EXPORT int mudg_test_ln_fold(void* W_f16, const float* gamma, const float* beta, const float* bias, float* c1,
+                                  float* c2, int N, int K, void* stream);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -253,22 +253,33 @@ class LatentDiffusion(DDPM):
         out = self.model(x_noisy, t, class_label, **cond, **kwargs)
         return out[0] if isinstance(out, tuple) else out
 
-    def apply_model_cfg(self, x_noisy, t, cond, uncond, **kwargs):
-        """cond + uncond evaluated as ONE batch of 2B (the two reference calls at ddim.py:221-222 differ only in the
-        context); returns (e_t_cond, e_t_uncond)."""
-        b = x_noisy.shape[0]
-        cache = getattr(self, "_cfg_cache", None)
-        key = tuple(id(v) for d in (cond, uncond) for k in sorted(d) for v in d[k]) + \
-            tuple(v._version for d in (cond, uncond) for k in sorted(d) for v in d[k])
+    def apply_model_multi(self, x_noisy, t, conds, **kwargs):
+        """The 2 (ddim.py:221-222) or 3 (ddim_multiplecond.py:213-235) UNet evaluations of one guided DDIM step as ONE
+        batch of len(conds)*B: the calls differ only in the conditioning.  When they differ only in the cross-attention
+        context (same c_concat: the driver's case) the copies also share the layers before the first cross-attention
+        (UNetModel.forward(mudg_shared_copies=...)).  Returns one output per conditioning."""
+        b, d = x_noisy.shape[0], len(conds)
+        tensors = [v for c in conds for k in sorted(c) for v in c[k]]
+        key = tuple(id(v) for v in tensors) + tuple(v._version for v in tensors)
+        cache = getattr(self, "_multi_cache", None)
         if cache is None or cache[0] != key:
-            both = {k: [torch.cat([c, u], dim=0) for c, u in zip(cond[k], uncond[k])] for k in cond}
-            cache = (key, both, (cond, uncond))
-            self._cfg_cache = cache
-        both = cache[1]
-        kw = {k: (torch.cat([v, v], dim=0) if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == b else v)
+            both = {k: [torch.cat(vs, dim=0) for vs in zip(*(c[k] for c in conds))] for k in conds[0]}
+            shared = all(k == "c_crossattn" or all(v is w or torch.equal(v, w) for c in conds[1:] for v, w in zip(c[k], conds[0][k]))
+                         for k in conds[0])
+            cache = (key, both, tuple(conds), shared)
+            self._multi_cache = cache
+        both, shared = cache[1], cache[3]
+        kw = {k: (torch.cat([v] * d, dim=0) if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == b else v)
               for k, v in kwargs.items()}
-        out = self.apply_model(torch.cat([x_noisy, x_noisy], dim=0), torch.cat([t, t], dim=0), both, **kw)
-        return out[:b], out[b:]
+        if shared and hasattr(self.model.diffusion_model, "engine"):
+            kw["mudg_shared_copies"] = d
+        out = self.apply_model(torch.cat([x_noisy] * d, dim=0), torch.cat([t] * d, dim=0), both, **kw)
+        return [out[i * b:(i + 1) * b] for i in range(d)]
+
+    def apply_model_cfg(self, x_noisy, t, cond, uncond, **kwargs):
+        """cond + uncond evaluated as ONE batch of 2B; returns (e_t_cond, e_t_uncond)."""
+        e_c, e_u = self.apply_model_multi(x_noisy, t, [cond, uncond], **kwargs)
+        return e_c, e_u
 
 
 class LatentVisualDiffusion(LatentDiffusion):

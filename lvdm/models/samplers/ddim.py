@@ -48,8 +48,9 @@ class DDIMSampler(object):
         self.ddim_sigmas, self.ddim_alphas, self.ddim_alphas_prev = sig, a, a_prev
         self.ddim_sqrt_one_minus_alphas = np.sqrt(1.0 - a)
         # host copies of the per-timestep scalars the fused step needs (no device sync inside the loop)
-        self._h_sqrt_ac = acc.sqrt().numpy()
-        self._h_sqrt_1mac = (1.0 - acc).sqrt().numpy()
+        # (the model's own buffers, derived in float64 as the reference indexes them: ddpm3d.py:239-251)
+        self._h_sqrt_ac = m.sqrt_alphas_cumprod.detach().cpu().numpy()
+        self._h_sqrt_1mac = m.sqrt_one_minus_alphas_cumprod.detach().cpu().numpy()
         if m.use_dynamic_rescale:
             self._h_scale = self.ddim_scale_arr.detach().cpu().numpy()
             self._h_scale_prev = self.ddim_scale_arr_prev.detach().cpu().numpy()

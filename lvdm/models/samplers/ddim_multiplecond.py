@@ -27,9 +27,13 @@ class DDIMSampler(_Base):
         if unconditional_conditioning is None or unconditional_guidance_scale == 1.0:
             out = m.apply_model(x, t, c, **kwargs)
         else:
-            v_c = m.apply_model(x, t, c, **kwargs)
-            v_u = m.apply_model(x, t, unconditional_conditioning, **kwargs)
-            v_ui = m.apply_model(x, t, uc_img, **kwargs)
+            if all(isinstance(d, dict) for d in (c, unconditional_conditioning, uc_img)) and hasattr(m, "apply_model_multi"):
+                # one 3B forward (cross-attention K/V of the three contexts cached together, shared prefix computed once)
+                v_c, v_u, v_ui = m.apply_model_multi(x, t, [c, unconditional_conditioning, uc_img], **kwargs)
+            else:
+                v_c = m.apply_model(x, t, c, **kwargs)
+                v_u = m.apply_model(x, t, unconditional_conditioning, **kwargs)
+                v_ui = m.apply_model(x, t, uc_img, **kwargs)
             out = v_u + cfg_img * (v_ui - v_u) + unconditional_guidance_scale * (v_c - v_ui)
             if guidance_rescale > 0.0:
                 out = rescale_noise_cfg(out, v_c, guidance_rescale=guidance_rescale)

@@ -38,6 +38,9 @@ class UNetModel(nn.Module):
             "fs_condition=False": not fs_condition, "class_label_condition=False": not class_label_condition,
             "domain_cross_attention": domain_cross_attention, "conv_resample=False": not conv_resample,
             "context_dim is None": context_dim is None,
+            # the reference's temporal transformers then cross-attend to the context (attention.py:504-505)
+            "temporal_selfatt_only=False": not temporal_selfatt_only,
+            "num_heads != -1": num_heads != -1,
         }
         bad = [k for k, v in unsupported.items() if v]
         if bad:
@@ -95,7 +98,11 @@ class UNetModel(nn.Module):
 
     # ------------------------------------------------------------------ reference signature (openaimodel3d.py:567)
     @torch.no_grad()
-    def forward(self, x, timesteps, c_label=None, context=None, features_adapter=None, fs=None, **kwargs):
+    def forward(self, x, timesteps, c_label=None, context=None, features_adapter=None, fs=None, mudg_shared_copies=1,
+                **kwargs):
+        """`mudg_shared_copies` = d > 1 (set by LatentDiffusion.apply_model_multi only): the batch is d copies of the same
+        latents / t / labels / fs that differ in `context` alone, so the library runs the layers before the first
+        cross-attention once per distinct sample (mudg_unet_forward_shared).  Everything else is the reference signature."""
         if features_adapter is not None:
             raise NotImplementedError("features_adapter is not part of the MuDG sampler path")
         if c_label is None:
@@ -104,6 +111,6 @@ class UNetModel(nn.Module):
         if fs is None:
             fs = torch.full((b,), self.default_fs, dtype=torch.long, device=x.device)
         eng = self.set_context(context, t)
-        y = eng.unet_forward(x, timesteps, c_label, fs)
+        y = eng.unet_forward(x, timesteps, c_label, fs, dup=int(mudg_shared_copies))
         # the reference returns fp16 under autocast (last conv) and the input dtype otherwise
         return y if (torch.is_autocast_enabled() or x.dtype == torch.float16) else y.to(x.dtype)

@@ -1,14 +1,11 @@
 // Attention kernels of the UNet (head dim 64 everywhere on the path: num_head_channels 64).
 //
-// flash_attention: spatial self-attention (N up to 9216 tokens/frame) and text/image cross-attention.
-//   One CTA = 128 queries of one (frame, head); 2 CTAs per SM.
-//   warp 0: TMA producer (Q once, then K/V 128-token blocks through a 2-stage ring)
-//   warp 1: tcgen05 issuer: S = Q K^T (M128 N128 K64) into TMEM, then O_blk = P V (M128 N64 K128,
-//           V consumed MN-major straight from its row-major TMA tile)
-//   warps 2-5: softmax, thread == query row == TMEM lane: two passes over S (max, then exp2/sum),
-//           P written as fp16 into a SWIZZLE_128B K-major smem tile, O rescaled/accumulated in registers.
+// flash2_kernel: spatial self-attention (up to 9216 tokens / frame) and text + image cross-attention on tcgen05
+//   (one CTA per SM, 256 queries = two 128-row tiles of one (frame, head); see the kernel's own comment).
 //   Two K/V segments keep separate softmax statistics and are summed at the end (attention.py:129-142).
-// temporal_attention: T<=64 tokens per (pixel, head); CUDA cores, K/V staged in smem (HBM-bound op).
+// temporal_attn16_kernel / temporal_attn_kernel: T <= 64 tokens per (pixel, head): HBM-bound, mma.sync / CUDA cores.
+// transpose_v_kernel: V -> V^T once per layer (the P V MMA wants a K-major B operand).
+// The CUDA-core checker and the tcgen05 issue-rate probes live in csrc/test/testhooks.cu (tests only).
 #include "ops.h"
 #include "ptx.cuh"
 
@@ -19,9 +16,7 @@ namespace mudg {
 
 namespace {
 
-constexpr int FA_THREADS = 192;
 constexpr int TILE = 128 * 64 * 2;                       // 16 KB: 128 rows x 64 fp16
-constexpr int FA_SMEM = TILE /*Q*/ + 2 * 2 * TILE /*K,V ring*/ + 2 * TILE /*P*/ + 1024 + 256;
 
 struct FaParams {
   long long* trace;   // debug (tests/gpu_trace_flash.py): clock64 time line of CTA 0, [3 roles][96 blocks][8 events]
@@ -31,217 +26,6 @@ struct FaParams {
   int kv_div[2];
   float scale_log2;   // scale * log2(e)
 };
-
-template <int NSEG>
-__global__ void __launch_bounds__(FA_THREADS, 2)
-flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmO,
-                const __grid_constant__ CUtensorMap tmK0, const __grid_constant__ CUtensorMap tmV0,
-                const __grid_constant__ CUtensorMap tmK1, const __grid_constant__ CUtensorMap tmV1, const FaParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sKV = smem + TILE;              // stage s: K at sKV + s*2*TILE, V at + TILE
-  uint8_t* sP = smem + 5 * TILE;           // 2 atoms of 64 kv columns
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * TILE);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;            // [2]
-  uint64_t* kv_empty = bars + 3;           // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_ready = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128, head = blockIdx.y, f = blockIdx.z;
-
-  if (threadIdx.x == 0) {
-    mbar_init(q_full, 1);
-    mbar_init(&kv_full[0], 1); mbar_init(&kv_full[1], 1);
-    mbar_init(&kv_empty[0], 1); mbar_init(&kv_empty[1], 1);
-    mbar_init(s_full, 1);
-    mbar_init(p_ready, 128);
-    mbar_init(o_full, 1);
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc<256>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
-
-  int nblk[2];
-  nblk[0] = (p.len[0] + 127) >> 7;
-  nblk[1] = NSEG > 1 ? (p.len[1] + 127) >> 7 : 0;
-  const int nb = nblk[0] + nblk[1];
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(q_full, TILE);
-      tma_load_5d(sQ, &tmQ, q_full, head * 64, q0, f, 0, 0);
-      int it = 0;
-      for (int sg = 0; sg < NSEG; sg++) {
-        const CUtensorMap* mk = sg ? &tmK1 : &tmK0;
-        const CUtensorMap* mv = sg ? &tmV1 : &tmV0;
-        const int kb = f / p.kv_div[sg];
-        for (int j = 0; j < nblk[sg]; j++, it++) {
-          const int s = it & 1;
-          mbar_wait(&kv_empty[s], ((it >> 1) & 1) ^ 1);
-          mbar_expect_tx(&kv_full[s], 2 * TILE);
-          uint8_t* k_s = sKV + s * 2 * TILE;
-          tma_load_5d(k_s, mk, &kv_full[s], head * 64, j * 128, kb, 0, 0);
-          tma_load_5d(k_s + TILE, mv, &kv_full[s], head * 64, j * 128, kb, 0, 0);
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_f16(128, 128, 0, 0);    // S = Q K^T : A,B K-major
-      constexpr uint32_t idesc_o = umma_idesc_f16(128, 64, 0, 1);     // O = P V   : B (V) MN-major
-      const uint64_t dq = umma_desc_sw128(smem_u32(sQ), 16, 1024);
-      const uint64_t dp = umma_desc_sw128(smem_u32(sP), 16, 1024);
-      mbar_wait(q_full, 0);
-      auto issue_s = [&](int it) {
-        const int s = it & 1;
-        mbar_wait(&kv_full[s], (it >> 1) & 1);
-        tc_fence_after();
-        const uint64_t dk = umma_desc_sw128(smem_u32(sKV + s * 2 * TILE), 16, 1024);
-#pragma unroll
-        for (int k = 0; k < 4; k++) umma_f16(tmem_S, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-        umma_commit(s_full);
-      };
-      issue_s(0);
-      for (int it = 0; it < nb; it++) {
-        const int s = it & 1;
-        mbar_wait(p_ready, it & 1);
-        tc_fence_after();
-        // V tile: 128 kv rows x 128 B, MN-major (d contiguous); 8-row groups 1024 B apart (SBO); K=16 -> +2048 B
-        const uint64_t dv = umma_desc_sw128(smem_u32(sKV + s * 2 * TILE + TILE), 1024, 1024);
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-          // P: two 64-column K-major atoms (16 KB apart); inside an atom +32 B per K=16
-          const uint64_t dpk = dp + (uint64_t)((k >> 2) * (TILE >> 4) + (k & 3) * 2);
-          umma_f16(tmem_O, dpk, dv + (uint64_t)(k * (2048 >> 4)), idesc_o, k != 0 ? 1u : 0u);
-        }
-        umma_commit(o_full);
-        umma_commit(&kv_empty[s]);
-        if (it + 1 < nb) issue_s(it + 1);
-      }
-    }
-    __syncwarp();
-  } else {
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    float O[64];
-    uint32_t acc[NSEG > 1 ? 32 : 1];       // fp16x2 running sum of the finished segments' outputs
-    if (NSEG > 1) {
-#pragma unroll
-      for (int i = 0; i < 32; i++) acc[i] = 0u;
-    }
-    int it = 0;
-#pragma unroll 1
-    for (int sg = 0; sg < NSEG; sg++) {
-      float m = -INFINITY, l = 0.f;
-#pragma unroll
-      for (int i = 0; i < 64; i++) O[i] = 0.f;
-#pragma unroll 1
-      for (int j = 0; j < nblk[sg]; j++, it++) {
-        const int valid = p.len[sg] - j * 128;          // columns >= valid are padding (TMA zero fill)
-        mbar_wait(s_full, it & 1);
-        __syncwarp();
-        tc_fence_after();
-        float mx = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < 4; c++) {
-          uint32_t v[32];
-          tmem_ld32(tmem_S + lane_off + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i++)
-            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-        }
-        const float m_new = fmaxf(m, mx * p.scale_log2);
-        const float alpha = exp2f(m - m_new);
-        float lsum = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < 4; c++) {
-          uint32_t v[32];
-          tmem_ld32(tmem_S + lane_off + c * 32, v);
-          tmem_ld_wait();
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float p0 = (c * 32 + i < valid) ? exp2f(__uint_as_float(v[i]) * p.scale_log2 - m_new) : 0.f;
-            float p1 = (c * 32 + i + 1 < valid) ? exp2f(__uint_as_float(v[i + 1]) * p.scale_log2 - m_new) : 0.f;
-            lsum += p0 + p1;
-            pk[i >> 1] = pack_half2(p0, p1);
-          }
-          uint8_t* atom = sP + (c >> 1) * TILE + row * 128;
-#pragma unroll
-          for (int jj = 0; jj < 4; jj++) {
-            const int chunk = (c & 1) * 4 + jj;
-            *reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) =
-                make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
-          }
-        }
-        l = l * alpha + lsum;
-        m = m_new;
-        fence_proxy_async_smem();          // P (generic-proxy writes) -> visible to the tensor core
-        tc_fence_before();                 // orders this thread's tcgen05.ld of S before the next S MMA
-        mbar_arrive(p_ready);
-        mbar_wait(o_full, it & 1);
-        __syncwarp();
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < 2; c++) {
-          uint32_t v[32];
-          tmem_ld32(tmem_O + lane_off + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i++) O[c * 32 + i] = O[c * 32 + i] * alpha + __uint_as_float(v[i]);
-        }
-      }
-      const float inv = 1.f / l;
-      if (NSEG > 1) {
-#pragma unroll
-        for (int i = 0; i < 32; i++) {
-          const float2 a = unpack_half2(acc[i]);
-          acc[i] = pack_half2(a.x + O[2 * i] * inv, a.y + O[2 * i + 1] * inv);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 64; i++) O[i] *= inv;
-      }
-    }
-    // ---- epilogue: fp16 tile -> swizzled smem (P buffer is free: the last PV MMA has retired) -> TMA store
-    uint8_t* stg = sP + row * 128;
-#pragma unroll
-    for (int jj = 0; jj < 8; jj++) {
-      uint4 val;
-      if (NSEG > 1) val = make_uint4(acc[4 * jj], acc[4 * jj + 1], acc[4 * jj + 2], acc[4 * jj + 3]);
-      else val = make_uint4(pack_half2(O[8 * jj], O[8 * jj + 1]), pack_half2(O[8 * jj + 2], O[8 * jj + 3]),
-                            pack_half2(O[8 * jj + 4], O[8 * jj + 5]), pack_half2(O[8 * jj + 6], O[8 * jj + 7]));
-      *reinterpret_cast<uint4*>(stg + ((jj ^ (row & 7)) << 4)) = val;
-    }
-    fence_proxy_async_smem();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (warp == 2 && lane == 0) {
-      tma_store_5d(&tmO, sP, head * 64, q0, f, 0, 0);
-      tma_store_commit();
-      tma_store_wait_read0();
-    }
-    __syncwarp();
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    tc_fence_after();
-    tmem_dealloc<256>(tmem_base);
-  }
-}
 
 // ================================================================ flash attention v2 (FA4-style schedule)
 // One CTA per SM, 256 queries (two 128-row tiles) of one (frame, head):
@@ -592,40 +376,6 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   }
 }
 
-// ---------------------------------------------------------------- SIMT checker: thread per (frame, head, query)
-__global__ void flash_simt_kernel(FlashArgs a) {
-  const int64_t total = (int64_t)a.F * a.heads * a.Nq;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int qi = idx % a.Nq;
-  const int head = (idx / a.Nq) % a.heads;
-  const int f = idx / ((int64_t)a.Nq * a.heads);
-  const __half* qp = a.Q + ((int64_t)f * a.Nq + qi) * a.q_pitch + head * 64;
-  float q[64], out[64];
-  for (int i = 0; i < 64; i++) { q[i] = __half2float(qp[i]); out[i] = 0.f; }
-  for (int sg = 0; sg < a.nseg; sg++) {
-    const FlashSeg& s = a.seg[sg];
-    const int kb = f / s.kv_div;
-    float m = -INFINITY, l = 0.f, o[64];
-    for (int i = 0; i < 64; i++) o[i] = 0.f;
-    for (int j = 0; j < s.len; j++) {
-      const __half* kp = s.K + ((int64_t)kb * s.len + j) * s.pitch + head * 64;
-      const __half* vp = s.V + ((int64_t)kb * s.len + j) * s.pitch + head * 64;
-      float d = 0.f;
-      for (int i = 0; i < 64; i++) d += q[i] * __half2float(kp[i]);
-      d *= a.scale;
-      const float mn = fmaxf(m, d);
-      const float al = expf(m - mn), pj = expf(d - mn);
-      l = l * al + pj;
-      for (int i = 0; i < 64; i++) o[i] = o[i] * al + pj * __half2float(vp[i]);
-      m = mn;
-    }
-    for (int i = 0; i < 64; i++) out[i] += o[i] / l;
-  }
-  __half* op = a.O + ((int64_t)f * a.Nq + qi) * a.o_pitch + head * 64;
-  for (int i = 0; i < 64; i++) op[i] = __float2half_rn(out[i]);
-}
-
 // ---------------------------------------------------------------- temporal attention
 // qkv rows are ordered (b, t, pixel); a warp handles `pairs` (pixel, head) problems at once: lane -> (pair, t)
 // for T <= 32, and lane -> t, t+32 for T in (32, 64].  K/V of the warp's pairs are staged in shared memory.
@@ -871,83 +621,6 @@ temporal_attn16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out,
   }
 }
 
-// ---------------------------------------------------------------- tcgen05.mma issue-rate probe (tests/gpu_probe_mma.py)
-// One thread issues `reps` MMAs of a given shape / operand source / accumulator pattern on garbage operands and times
-// issue -> completion with clock64.  Used to find out what actually paces the attention kernel's small MMAs.
-template <int variant>
-__device__ __forceinline__ void mma_probe_issue(int r, uint32_t tm, uint64_t da, uint64_t db, uint64_t dv) {
-  constexpr uint32_t i128 = umma_idesc_f16(128, 128, 0, 0), i256 = umma_idesc_f16(128, 256, 0, 0),
-                     i64 = umma_idesc_f16(128, 64, 0, 0), i64v = umma_idesc_f16(128, 64, 0, 1);
-  const uint32_t acc = r >= 4 ? 1u : 0u;
-  const uint64_t ko = 2 * (r & 3);
-  switch (variant) {
-    case 0: umma_f16(tm, da + ko, db + ko, i128, acc); break;                              // SS N128, one D
-    case 1: umma_f16(tm + (r & 1) * 128, da + ko, db + ko, i128, acc); break;              // SS N128, 2 D
-    case 2: umma_f16(tm, da + ko, db + ko, i256, acc); break;                              // SS N256, one D
-    case 3: umma_f16(tm, da + ko, db + ko, i64, acc); break;                               // SS N64, one D
-    case 4: umma_f16(tm + (r & 3) * 64, da + ko, db + ko, i64, acc); break;                // SS N64, 4 D
-    case 5: umma_f16_ts(tm, tm + 384 + (r & 7) * 8, dv + (uint64_t)((r & 7) * 128), i64v, acc); break;          // TS N64 MN-major B
-    case 6: umma_f16_ts(tm + (r & 1) * 64, tm + 384 + (r & 7) * 8, dv + (uint64_t)((r & 7) * 128), i64v, acc); break;
-    case 7: umma_f16_ts(tm + (r & 3) * 64, tm + 384 + (r & 7) * 8, dv + (uint64_t)((r & 7) * 128), i64v, acc); break;
-    case 8: umma_f16(tm + (r & 3) * 128, da + ko, db + ko, i128, acc); break;              // SS N128, 4 D
-    case 9: umma_f16_ts(tm, tm + 384 + (r & 7) * 8, db + ko, i64, acc); break;             // TS N64 K-major B
-    case 10: umma_f16_ts(tm, tm + 256 + (r & 7) * 8, db + ko, i128, acc); break;           // TS N128 K-major B
-    case 11: umma_f16_ts(tm, tm + 256 + (r & 7) * 8, db + ko, i256, acc); break;           // TS N256
-    default: break;
-  }
-}
-
-// mode 0: a single diverged thread issues (if (threadIdx.x == 0) ...); mode 1: the whole warp runs the loop and one
-// elected lane issues (uniform control flow, operands in uniform registers)
-template <int VARIANT>
-__global__ void __launch_bounds__(128, 1) mma_probe_kernel(int reps, int mode, long long* out) {
-  extern __shared__ __align__(1024) uint8_t psm[];
-  __shared__ uint64_t bar;
-  __shared__ uint32_t slot;
-  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(psm)[i] = 0x3c003c00u;   // 1.0h
-  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
-  if (threadIdx.x < 32) tmem_alloc<512>(&slot);
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tm = slot;
-  const uint64_t da = umma_desc_sw128(smem_u32(psm), 16, 1024);                 // K-major 128 x 64
-  const uint64_t db = umma_desc_sw128(smem_u32(psm) + 32768, 16, 1024);         // K-major up to 256 x 64
-  const uint64_t dv = umma_desc_sw128(smem_u32(psm) + 65536, 1024, 1024);       // MN-major 128 x 64
-  if (mode == 0) {
-    if (threadIdx.x == 0) {
-      const long long t0 = clock64();
-      for (int r = 0; r < reps; r++) mma_probe_issue<VARIANT>(r, tm, da, db, dv);
-      const long long t1 = clock64();
-      umma_commit(&bar);
-      mbar_wait(&bar, 0);
-      const long long t2 = clock64();
-      out[blockIdx.x * 2] = t1 - t0;
-      out[blockIdx.x * 2 + 1] = t2 - t0;
-    }
-  } else if (threadIdx.x < 32) {
-    const long long t0 = clock64();
-    for (int r = 0; r < reps; r++) {
-      if (elect_one()) mma_probe_issue<VARIANT>(r, tm, da, db, dv);
-      __syncwarp();
-    }
-    const long long t1 = clock64();
-    if (elect_one()) umma_commit(&bar);
-    __syncwarp();
-    mbar_wait(&bar, 0);
-    const long long t2 = clock64();
-    if (threadIdx.x == 0) {
-      out[blockIdx.x * 2] = t1 - t0;
-      out[blockIdx.x * 2 + 1] = t2 - t0;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (threadIdx.x < 32) tmem_dealloc<512>(tm);
-}
-
 // ---------------------------------------------------------------- V -> V^T (the P V MMA wants its B operand K-major)
 // V rows [nbatch][len] of pitch elements, head h at columns [h*64, h*64+64)  ->  VT [nbatch][heads*64][len_pad], kv contiguous.
 __global__ void __launch_bounds__(256) transpose_v_kernel(const __half* __restrict__ V, int pitch, int len, int heads,
@@ -1008,42 +681,12 @@ void transpose_v(const __half* V, int pitch, int len, int nbatch, int heads, __h
   MUDG_CUDA(cudaGetLastError());
 }
 
-void flash_attention_simt(const FlashArgs& a, cudaStream_t st) {
-  const int64_t total = (int64_t)a.F * a.heads * a.Nq;
-  flash_simt_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(a);
-  MUDG_CUDA(cudaGetLastError());
-}
-
-void mma_probe(int variant, int reps, int ctas, int mode, long long* out, cudaStream_t st) {
-#define MUDG_PROBE_CASE(V)                                                                                         \
-  case V:                                                                                                           \
-    MUDG_CUDA(cudaFuncSetAttribute(mma_probe_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));  \
-    mma_probe_kernel<V><<<ctas, 128, 96 * 1024, st>>>(reps, mode, out);                                            \
-    break;
-  switch (variant) {
-    MUDG_PROBE_CASE(0) MUDG_PROBE_CASE(1) MUDG_PROBE_CASE(2) MUDG_PROBE_CASE(3) MUDG_PROBE_CASE(4) MUDG_PROBE_CASE(5)
-    MUDG_PROBE_CASE(6) MUDG_PROBE_CASE(7) MUDG_PROBE_CASE(8) MUDG_PROBE_CASE(9) MUDG_PROBE_CASE(10) MUDG_PROBE_CASE(11)
-    default: MUDG_REQUIRE(false, "mma_probe: variant %d", variant);
-  }
-#undef MUDG_PROBE_CASE
-  MUDG_CUDA(cudaGetLastError());
-}
-
 static long long* g_flash_trace = nullptr;
 void flash_set_trace(long long* buf) { g_flash_trace = buf; }
 
 void flash_attention(const FlashArgs& a, cudaStream_t st) {
-  static const bool force_simt = [] {
-    const char* e = getenv("MUDG_FORCE_SIMT");
-    return e && e[0] == '1';
-  }();
-  if (force_simt) return flash_attention_simt(a, st);
   MUDG_REQUIRE(a.nseg == 1 || a.nseg == 2, "nseg");
   MUDG_REQUIRE(a.q_pitch % 8 == 0 && a.o_pitch % 8 == 0, "pitch alignment");
-  static const bool use_v1 = [] {
-    const char* e = getenv("MUDG_FLASH_V1");
-    return e && e[0] == '1';
-  }();
   const int width = a.heads * 64;
   const CUtensorMap* mq = rows_map(a.Q, width, a.q_pitch, a.Nq, a.F);
   const CUtensorMap* mo = rows_map(a.O, width, a.o_pitch, a.Nq, a.F);
@@ -1052,59 +695,37 @@ void flash_attention(const FlashArgs& a, cudaStream_t st) {
   FaParams p{};
   p.nseg = a.nseg;
   p.scale_log2 = a.scale * 1.4426950408889634f;
-  static const int stagger_env = [] {
-    const char* e = getenv("MUDG_FLASH_STAGGER");   // 0 off, 1 hand over after all exponentials, 2 / 3 / 4 after 3/4, 1/2, 1/4
-    return e ? atoi(e) : 3;
-  }();
-  p.stagger = stagger_env;
+  p.stagger = knobs().flash_stagger;
   p.trace = g_flash_trace;
   for (int i = 0; i < 2; i++) {
     const FlashSeg& s = a.seg[i < a.nseg ? i : 0];
     MUDG_REQUIRE(s.pitch % 8 == 0 && s.len > 0, "kv segment");
     mk[i] = rows_map(s.K, width, s.pitch, s.len, s.nbatch);
-    if (use_v1) {
-      mv[i] = rows_map(s.V, width, s.pitch, s.len, s.nbatch);
-    } else {
-      MUDG_REQUIRE(s.VT != nullptr && s.vt_pitch % 8 == 0 && s.vt_pitch >= s.len, "flash attention needs V^T (transpose_v) of every kv segment");
-      mv[i] = vt_map(s.VT, s.len, s.vt_pitch, width, s.nbatch);
-    }
+    MUDG_REQUIRE(s.VT != nullptr && s.vt_pitch % 8 == 0 && s.vt_pitch >= s.len, "flash attention needs V^T (transpose_v) of every kv segment");
+    mv[i] = vt_map(s.VT, s.len, s.vt_pitch, width, s.nbatch);
     p.len[i] = s.len;
     p.kv_div[i] = s.kv_div > 0 ? s.kv_div : 1;
   }
   static bool attr = false;
   if (!attr) {
-    MUDG_CUDA(cudaFuncSetAttribute(flash_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-    MUDG_CUDA(cudaFuncSetAttribute(flash_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
     MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
     MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
     MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
     attr = true;
   }
   // Polynomial exp2 offload (FA4 trick).  Measured on B200 (tests/gpu_bench_flash.py): 5.49 ms vs 4.99 ms without it at
-  // 9216 tokens -- the kernel is not MUFU-bound at this occupancy, so it stays off unless MUDG_FLASH_POLY=1.
-  static const bool poly = [] {
-    const char* e = getenv("MUDG_FLASH_POLY");
-    return e && e[0] == '1';
-  }();
-  if (use_v1) {
-    dim3 grid((a.Nq + 127) / 128, a.heads, a.F);
-    if (a.nseg == 1) flash_tc_kernel<1><<<grid, FA_THREADS, FA_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
-    else flash_tc_kernel<2><<<grid, FA_THREADS, FA_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
-  } else {
-    dim3 grid((a.Nq + 255) / 256, a.heads, a.F);
-    if (a.nseg == 1 && poly) flash2_kernel<1, true><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
-    else if (a.nseg == 1) flash2_kernel<1, false><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
-    else flash2_kernel<2, false><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
-  }
+  // 9216 tokens -- the exponent phase is latency-bound at this occupancy, so it stays off (knob flash_poly).
+  const bool poly = knobs().flash_poly != 0;
+  dim3 grid((a.Nq + 255) / 256, a.heads, a.F);
+  if (a.nseg == 1 && poly) flash2_kernel<1, true><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
+  else if (a.nseg == 1) flash2_kernel<1, false><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
+  else flash2_kernel<2, false><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
   MUDG_CUDA(cudaGetLastError());
 }
 
 void temporal_attention(const __half* qkv, __half* out, int B, int T, int HW, int heads, float scale, cudaStream_t st) {
   MUDG_REQUIRE(T >= 1 && T <= 64, "temporal attention supports T <= 64 (T=%d)", T);
-  static const bool generic_only = [] {
-    const char* e = getenv("MUDG_TATTN_GENERIC");
-    return e && e[0] == '1';
-  }();
+  const bool generic_only = knobs().tattn_generic != 0;
   if (T == 16 && !generic_only) {
     static bool attr16 = false;
     if (!attr16) {

@@ -20,6 +20,11 @@ std::string fmt(const char* f, ...) {
 void set_last_error(const std::string& s) { g_last_error = s; }
 const char* last_error_cstr() { return g_last_error.c_str(); }
 
+Knobs& knobs() {
+  static Knobs k;
+  return k;
+}
+
 int sm_count() {
   static int n = 0;
   if (!n) {

@@ -198,13 +198,14 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, __half* __restric
 
 // ---------------------------------------------------------------- layout helpers
 __global__ void concat_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ o,
-                              int64_t rows, int va, int vb) {
+                              int64_t rows, int64_t rows_b, int va, int vb) {
   const int vo = va + vb;
   const int64_t total = rows * vo;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / vo;
     const int v = i - r * vo;
-    o[i] = v < va ? __ldg(a + r * va + v) : __ldg(b + r * vb + (v - va));
+    const int64_t rb = r < rows_b ? r : r % rows_b;
+    o[i] = v < va ? __ldg(a + r * va + v) : __ldg(b + rb * vb + (v - va));
   }
 }
 
@@ -486,11 +487,12 @@ void layernorm(const __half* x, __half* y, const float* gamma, const float* beta
   MUDG_CUDA(cudaGetLastError());
 }
 
-void concat_channels(const __half* a, int Ca, const __half* b, int Cb, __half* out, int64_t rows, cudaStream_t st) {
+void concat_channels(const __half* a, int Ca, const __half* b, int Cb, __half* out, int64_t rows, int64_t rows_b,
+                     cudaStream_t st) {
   MUDG_REQUIRE(Ca % 8 == 0 && Cb % 8 == 0, "concat needs C %% 8 == 0");
   const int64_t total = rows * ((Ca + Cb) / 8);
   concat_kernel<<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b),
-                                                      reinterpret_cast<uint4*>(out), rows, Ca / 8, Cb / 8);
+                                                      reinterpret_cast<uint4*>(out), rows, rows_b, Ca / 8, Cb / 8);
   MUDG_CUDA(cudaGetLastError());
 }
 

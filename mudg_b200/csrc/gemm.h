@@ -52,12 +52,9 @@ struct TapGemmGeneric {
 };
 
 bool tapgemm_tc_eligible(const TapGemm& g);
-void tapgemm_tc(const TapGemm& g, cudaStream_t st);        // tcgen05 + TMA path, v1: one tile per CTA
-void tapgemm_tc2(const TapGemm& g, cudaStream_t st);       // v2: persistent CTAs, double-buffered TMEM, 64..192-wide tiles
-void tapgemm_tc_auto(const TapGemm& g, cudaStream_t st);   // v2 unless MUDG_GEMM_V1=1
-void tapgemm_simt(const TapGemm& g, cudaStream_t st);      // CUDA-core checker of the same contract (debug)
+void tapgemm_tc2(const TapGemm& g, cudaStream_t st);       // persistent single-CTA kernel, or the CTA-pair kernel for large problems
 void tapgemm_generic(const TapGemmGeneric& g, cudaStream_t st);
-// dispatch: tensor cores unless MUDG_FORCE_SIMT=1 (debug) or the layer is not eligible
+// The product entry: tcgen05 path (+ optional per-launch timing); throws when the layer is not eligible (no fallback).
 void tapgemm(const TapGemm& g, cudaStream_t st);
 
 void gemm_set_trace(long long* buf);   // debug: clock64 time line of the pair GEMM's CTA 0 ([4][64][8] int64), null = off

@@ -68,6 +68,15 @@ void WeightStore::drop(const std::string& key) {
   }
 }
 
+void WeightStore::clear() {
+  for (auto& kv : w_) cudaFree(kv.second.w);
+  for (auto& kv : v_) cudaFree(kv.second.p);
+  w_.clear();
+  v_.clear();
+  bytes_ = 0;
+  finalized = false;
+}
+
 void WeightStore::stack_rows(const std::string& out_key, const std::vector<std::string>& keys, cudaStream_t st) {
   if (hasW(out_key)) return;   // already fused
   Weight o;
@@ -251,7 +260,26 @@ void Model::build_plan() {
   n_res_ = res_count;
 }
 
+void Model::begin_load(int which) {
+  WeightStore& ws = which == MUDG_VAE ? vae_w : (which == MUDG_RESAMPLER ? res_w : unet_w);
+  if (!ws.finalized) return;
+  MUDG_CUDA(cudaDeviceSynchronize());      // kernels of earlier forwards may still read the old set
+  ws.clear();
+  clear_tmap_cache();                      // tensor maps are keyed by weight pointers
+  if (which == MUDG_UNET) {
+    unet_ready_ = false;
+    drop_graphs();                         // captured kernel arguments / tensor maps point at the freed weights
+    ctx_N_ = ctx_L_ = ctx_T_ = 0;          // the K/V cache was projected with the old weights: set_context must run again
+    ctx_version_++;
+  } else if (which == MUDG_VAE) {
+    vae_ready_ = vae_enc_ready_ = false;
+  } else {
+    res_ready_ = false;
+  }
+}
+
 void Model::finalize(int which, cudaStream_t st) {
+  (which == MUDG_VAE ? vae_w : (which == MUDG_RESAMPLER ? res_w : unet_w)).finalized = true;
   if (which == MUDG_RESAMPLER) {
     // touch every key Resampler.forward needs and derive the dimensions from the shapes (resampler.py:104-129)
     WeightStore& w = res_w;
@@ -491,10 +519,24 @@ Act Model::conv_t3(const Act& x, const std::string& p, const Act* residual) {
 }
 
 Act Model::concat(const Act& a, const Act& b) {
+  // b may hold fewer samples than a (a skip tensor from the shared CFG prefix): its rows then repeat with period b.rows()
   Act y = alloc(a.B, a.T, a.H, a.W, a.C + b.C);
   if (live()) {
-    concat_channels(a.p, a.C, b.p, b.C, y.p, a.rows(), st_);
+    MUDG_REQUIRE(a.rows() % b.rows() == 0, "concat: %lld rows vs %lld", (long long)a.rows(), (long long)b.rows());
+    concat_channels(a.p, a.C, b.p, b.C, y.p, a.rows(), b.rows(), st_);
     launches++;
+  }
+  return y;
+}
+
+// x [B0, ...] -> [n, ...]: the samples tiled n / B0 times (sample i of the result = sample i % B0 of x)
+Act Model::tile_batch(const Act& x, int n) {
+  Act y = alloc(n, x.T, x.H, x.W, x.C);
+  if (live()) {
+    MUDG_REQUIRE(n % x.B == 0, "tile_batch: %d samples from %d", n, x.B);
+    for (int i = 0; i < n / x.B; i++)
+      MUDG_CUDA(cudaMemcpyAsync(y.p + (size_t)i * x.numel(), x.p, x.bytes(), cudaMemcpyDeviceToDevice, st_));
+    launches += n / x.B;
   }
   return y;
 }
@@ -563,7 +605,7 @@ Act Model::transformer_block_tail(Act x, const std::string& tb) {
 Act Model::spatial_transformer(const Act& xin, const Layer& l) {   // attention.py:451-467, use_linear=True
   const std::string& p = l.prefix;
   const std::string tb = p + ".transformer_blocks.0";
-  const int C = l.ch, F = xin.B * xin.T, HW = xin.H * xin.W;
+  const int C = l.ch, HW = xin.H * xin.W;
   Act g = group_norm(xin, p + ".norm", 1e-6f, false, false);
   Act x = linear(g, p + ".proj_in.weight", p + ".proj_in.bias", nullptr);
   release(g);
@@ -573,15 +615,16 @@ Act Model::spatial_transformer(const Act& xin, const Layer& l) {   // attention.
   release_bytes(s1);
   Act a1 = alloc(xin.B, xin.T, xin.H, xin.W, C);
   const int hw_pad = round_up(HW, 8);
-  __half* vt = static_cast<__half*>(alloc_bytes(sizeof(__half) * (size_t)F * C * hw_pad));   // V^T [F][C][HW]
+  const int F1 = xin.B * xin.T;
+  __half* vt = static_cast<__half*>(alloc_bytes(sizeof(__half) * (size_t)F1 * C * hw_pad));   // V^T [F][C][HW]
   if (live()) {
-    transpose_v(qkv.p + 2 * C, 3 * C, HW, F, l.heads, vt, hw_pad, st_);
+    transpose_v(qkv.p + 2 * C, 3 * C, HW, F1, l.heads, vt, hw_pad, st_);
     FlashArgs fa;
-    fa.Q = qkv.p; fa.q_pitch = 3 * C; fa.O = a1.p; fa.o_pitch = C; fa.F = F; fa.Nq = HW; fa.heads = l.heads;
+    fa.Q = qkv.p; fa.q_pitch = 3 * C; fa.O = a1.p; fa.o_pitch = C; fa.F = F1; fa.Nq = HW; fa.heads = l.heads;
     fa.nseg = 1;
     fa.seg[0].K = qkv.p + C; fa.seg[0].V = qkv.p + 2 * C; fa.seg[0].pitch = 3 * C; fa.seg[0].len = HW;
     fa.seg[0].VT = vt; fa.seg[0].vt_pitch = hw_pad;
-    fa.seg[0].nbatch = F; fa.seg[0].kv_div = 1;
+    fa.seg[0].nbatch = F1; fa.seg[0].kv_div = 1;
     fa.scale = 0.125f;
     flash_attention(fa, st_);
     launches += 2;
@@ -591,11 +634,22 @@ Act Model::spatial_transformer(const Act& xin, const Layer& l) {   // attention.
   Act x1 = linear(a1, tb + ".attn1.to_out.0.weight", tb + ".attn1.to_out.0.bias", &x);
   release(a1);
   release(x);
+  // Shared CFG prefix ends here: up to this point the `dup` copies of a sample (same latent, same t / label / fs) are
+  // identical, from the first cross-attention on they differ.  Tile x1 and the block input (residual of proj_out).
+  Act xin_full = xin;
+  const bool split = xin.B < N_;
+  if (split) {
+    Act t1 = tile_batch(x1, N_);
+    release(x1);
+    x1 = t1;
+    xin_full = tile_batch(xin, N_);
+  }
+  const int F = xin_full.B * xin_full.T;
   // attn2: text (77 tokens, shared by the frames of a sample) + image tokens, separate softmaxes summed
   float2* s2 = layer_norm_stats(x1);
   Act q = linear(x1, tb + ".attn2.to_q.weight", "", nullptr, false, 1.f, s2);
   release_bytes(s2);
-  Act a2 = alloc(xin.B, xin.T, xin.H, xin.W, C);
+  Act a2 = alloc(xin_full.B, xin.T, xin.H, xin.W, C);
   if (live()) {
     auto it = kv_.find(p);
     MUDG_REQUIRE(it != kv_.end() && ctx_N_ == N_ && ctx_T_ == T_real_, "mudg_set_context(N=%d, T=%d) must precede the forward",
@@ -620,8 +674,9 @@ Act Model::spatial_transformer(const Act& xin, const Layer& l) {   // attention.
   release(a2);
   release(x1);
   Act x3 = transformer_block_tail(x2, tb);
-  Act y = linear(x3, p + ".proj_out.weight", p + ".proj_out.bias", &xin);
+  Act y = linear(x3, p + ".proj_out.weight", p + ".proj_out.bias", &xin_full);
   release(x3);
+  if (split) release(xin_full);
   return y;
 }
 
@@ -711,16 +766,22 @@ void Model::compute_embeddings(const int64_t* t, const int64_t* label, const int
   release_bytes(emb);
 }
 
-void Model::unet_body(const void* x, const int64_t* t, const int64_t* label, const int64_t* fs, int N, int T, int h, int w,
-                      void* out) {
+void Model::unet_body(const void* x, const int64_t* t, const int64_t* label, const int64_t* fs, int N, int dup, int T, int h,
+                      int w, void* out) {
   ws_ = &unet_w;
   N_ = N; T_real_ = T;
   arena_.reset();
   compute_embeddings(t, label, fs, N);
   const int cpad = round_up(ucfg_.in_channels, 8);
-  Act xin = alloc(N, T, h, w, cpad);
+  // Shared prefix (classifier-free guidance batches): x / t / label / fs hold N / dup distinct samples tiled dup times and
+  // only the context differs, so everything before the first cross-attention runs on the N / dup distinct samples
+  // (spatial_transformer tiles the batch back to N where the copies start to differ).
+  bool has_spatial = false;
+  for (auto& b : in_blocks_) for (auto& l : b.layers) has_spatial |= (l.kind == "spatial");
+  const int B0 = (dup > 1 && has_spatial) ? N / dup : N;
+  Act xin = alloc(B0, T, h, w, cpad);
   if (live()) {
-    to_channels_last(x, true, xin.p, N, ucfg_.in_channels, (int64_t)T * h * w, cpad, st_);
+    to_channels_last(x, true, xin.p, B0, ucfg_.in_channels, (int64_t)T * h * w, cpad, st_);
     launches++;
   }
   std::vector<Act> hs;
@@ -839,12 +900,12 @@ void Model::set_context(const void* ctx, int dtype, int N, int L, int T, cudaStr
 }
 
 // ================================================================ entry points
-size_t Model::plan_unet(int N, int T, int h, int w) {
+size_t Model::plan_unet(int N, int dup, int T, int h, int w) {
   MUDG_REQUIRE(unet_ready_, "weights not finalized");
   arena_.planning = true;
   planning_ = true;
   arena_.reset_high();
-  unet_body(nullptr, nullptr, nullptr, nullptr, N, T, h, w, nullptr);
+  unet_body(nullptr, nullptr, nullptr, nullptr, N, dup, T, h, w, nullptr);
   const size_t need = arena_.high_water();
   arena_.planning = false;
   planning_ = false;
@@ -854,12 +915,13 @@ size_t Model::plan_unet(int N, int T, int h, int w) {
 
 // The ~1300 launches of one forward are captured once per shape into a CUDA graph (inputs/outputs go through fixed
 // staging buffers so the captured pointers stay valid); later steps replay it.  MUDG_GRAPH=0 disables the capture.
-void Model::unet_forward(const void* x, const int64_t* t, const int64_t* label, const int64_t* fs, int N, int T, int h, int w,
-                         void* out, cudaStream_t st) {
+void Model::unet_forward(const void* x, const int64_t* t, const int64_t* label, const int64_t* fs, int N, int dup, int T, int h,
+                         int w, void* out, cudaStream_t st) {
   MUDG_REQUIRE(unet_ready_, "weights not finalized");
-  std::array<int, 4> key{N, T, h, w};
+  MUDG_REQUIRE(dup >= 1 && N % dup == 0, "unet_forward: N = %d is not a multiple of dup = %d", N, dup);
+  std::array<int, 5> key{N, dup, T, h, w};
   auto it = unet_plans_.find(key);
-  if (it == unet_plans_.end()) it = unet_plans_.emplace(key, plan_unet(N, T, h, w)).first;
+  if (it == unet_plans_.end()) it = unet_plans_.emplace(key, plan_unet(N, dup, T, h, w)).first;
   ensure_arena(it->second);
   st_ = st;
   static const bool graphs_on = [] {
@@ -867,7 +929,7 @@ void Model::unet_forward(const void* x, const int64_t* t, const int64_t* label, 
     return !(e && e[0] == '0');
   }();
   if (!graphs_on || gemm_profile_active()) {
-    unet_body(x, t, label, fs, N, T, h, w, out);
+    unet_body(x, t, label, fs, N, dup, T, h, w, out);
     return;
   }
   // Capture is illegal on the legacy default stream (what PyTorch uses unless told otherwise): run on an own
@@ -903,13 +965,13 @@ void Model::unet_forward(const void* x, const int64_t* t, const int64_t* label, 
   } else if (g.runs == 0) {
     // first call: eager (sets kernel attributes, fills the tensor-map cache)
     const int64_t l0 = launches;
-    unet_body(g.in_x, g.in_idx, g.in_idx + N, g.in_idx + 2 * N, N, T, h, w, g.out);
+    unet_body(g.in_x, g.in_idx, g.in_idx + N, g.in_idx + 2 * N, N, dup, T, h, w, g.out);
     g.launches = launches - l0;
   } else {
     cudaGraph_t graph = nullptr;
     MUDG_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     try {
-      unet_body(g.in_x, g.in_idx, g.in_idx + N, g.in_idx + 2 * N, N, T, h, w, g.out);
+      unet_body(g.in_x, g.in_idx, g.in_idx + N, g.in_idx + 2 * N, N, dup, T, h, w, g.out);
     } catch (...) {
       cudaStreamEndCapture(st, &graph);
       if (graph) cudaGraphDestroy(graph);

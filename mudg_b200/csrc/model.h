@@ -50,6 +50,8 @@ class WeightStore {
   void make_geglu(const std::string& proj_prefix, cudaStream_t st);
   void fold_ln(const std::string& wkey, const std::string& bkey, const std::string& ln, cudaStream_t st);   // "<p>.weight"/".bias" -> "<p>.geglu.weight"/".bias"
   void drop(const std::string& key);
+  void clear();                      // free every tensor (raw and derived)
+  bool finalized = false;            // set by Model::finalize; the next load() then starts a fresh set (Model::begin_load)
   size_t bytes() const { return bytes_; }
 
  private:
@@ -73,15 +75,22 @@ class Model {
   ~Model();
 
   WeightStore unet_w, vae_w, res_w;   // res_w: Resampler (image_proj_model), "next" row f.3
+  // A load after finalize() replaces the WHOLE weight set: the fused / folded tensors (qkv, kv_text, kv_img, GEGLU
+  // interleave, LayerNorm folds, padded rows) are derived from raw tensors that finalize() released, so nothing of the
+  // old set may survive.  Also drops the captured CUDA graphs and the cross-attention K/V cache (both hold weight data).
+  void begin_load(int which);
   void finalize(int which, cudaStream_t st);
+  int device() const { return device_; }
   void set_context(const void* ctx, int dtype, int N, int L, int T, cudaStream_t st);
-  void unet_forward(const void* x, const int64_t* t, const int64_t* label, const int64_t* fs, int N, int T, int h, int w,
-                    void* out, cudaStream_t st);
+  // dup > 1: x / t / label / fs hold N / dup distinct samples tiled dup times (sample n == sample n % (N / dup)); only the
+  // context differs (classifier-free guidance).  The layers before the first cross-attention then run once per distinct sample.
+  void unet_forward(const void* x, const int64_t* t, const int64_t* label, const int64_t* fs, int N, int dup, int T, int h,
+                    int w, void* out, cudaStream_t st);
   void vae_decode(const void* z, int F, int h, int w, void* out, cudaStream_t st);
   void vae_encode(const void* x, int F, int H, int W, void* moments, cudaStream_t st);
   // Resampler.forward (resampler.py:131-144): x [B, L, embedding_dim] -> out [B, num_queries*video_length, output_dim] fp32
   void resampler_forward(const void* x, int dtype, int B, int L, void* out, cudaStream_t st);
-  size_t plan_unet(int N, int T, int h, int w);
+  size_t plan_unet(int N, int dup, int T, int h, int w);
   size_t plan_vae(int h, int w);
   int64_t launches = 0;
 
@@ -127,11 +136,11 @@ class Model {
     int64_t launches = 0;
     int64_t ctx_version = -1;
   };
-  std::map<std::array<int, 4>, GraphSlot> graphs_;
+  std::map<std::array<int, 5>, GraphSlot> graphs_;
   int64_t ctx_version_ = 0;
   cudaStream_t own_stream_ = nullptr;
   void drop_graphs();
-  std::map<std::array<int, 4>, size_t> unet_plans_;
+  std::map<std::array<int, 5>, size_t> unet_plans_;
   std::map<std::array<int, 2>, size_t> vae_plans_;
 
   void ensure_arena(size_t bytes);
@@ -151,6 +160,7 @@ class Model {
   Act conv_t3(const Act& x, const std::string& p, const Act* residual);
   Act gemm_raw(const __half* A, int M, int K, const __half* Wt, int N, const float* bias, const Act* residual, float alpha);
   Act concat(const Act& a, const Act& b);
+  Act tile_batch(const Act& x, int n);
   Act upsample(const Act& x);
   Act downsample(const Act& x, const std::string& p, int pad);
 
@@ -160,7 +170,7 @@ class Model {
   Act temporal_transformer(const Act& x, const Layer& l);
   Act run_block(Act h, const Block& b, bool owns_input);
   void compute_embeddings(const int64_t* t, const int64_t* label, const int64_t* fs, int N);
-  void unet_body(const void* x, const int64_t* t, const int64_t* label, const int64_t* fs, int N, int T, int h, int w,
+  void unet_body(const void* x, const int64_t* t, const int64_t* label, const int64_t* fs, int N, int dup, int T, int h, int w,
                  void* out);
   Act vae_res(const Act& x, const std::string& p);
   Act vae_attn(const Act& x, const std::string& p);

@@ -14,7 +14,9 @@ void layernorm(const __half* x, __half* y, const float* gamma, const float* beta
 void ln_stats(const __half* x, float2* out, int64_t rows, int C, float eps, cudaStream_t st);
 void ln_fold(__half* W, const float* gamma, const float* beta, const float* bias, float* c1, float* c2, int N, int K,
              cudaStream_t st);
-void concat_channels(const __half* a, int Ca, const __half* b, int Cb, __half* out, int64_t rows, cudaStream_t st);
+// out[r] = [a[r] | b[r % rows_b]] (rows_b divides rows: a skip tensor shared by the copies of a CFG batch)
+void concat_channels(const __half* a, int Ca, const __half* b, int Cb, __half* out, int64_t rows, int64_t rows_b,
+                     cudaStream_t st);
 void upsample2x(const __half* x, __half* y, int F, int H, int W, int C, cudaStream_t st);
 void im2col_s2(const __half* x, __half* y, int F, int H, int W, int C, int pad, cudaStream_t st);   // Ho = (H + pad - 2) / 2 + 1
 void softmax_rows(__half* x, int64_t rows, int n, cudaStream_t st);
@@ -57,9 +59,7 @@ struct FlashArgs {
 };
 void flash_attention(const FlashArgs& a, cudaStream_t st);
 void transpose_v(const __half* V, int pitch, int len, int nbatch, int heads, __half* VT, int len_pad, cudaStream_t st);
-void flash_attention_simt(const FlashArgs& a, cudaStream_t st);
-void mma_probe(int variant, int reps, int ctas, int mode, long long* out, cudaStream_t st);   // debug: tcgen05.mma issue-rate probe
-void flash_set_trace(long long* buf);   // debug: clock64 time line of CTA 0 ([3][96][8] int64), null = off   // CUDA-core checker (debug / MUDG_FORCE_SIMT)
+void flash_set_trace(long long* buf);   // debug: clock64 time line of CTA 0 ([3][96][8] int64), null = off
 
 // Temporal self-attention over T for every (b, h, w, head): qkv rows [B*T*HW][3*inner] (q | k | v), out [rows][inner]
 void temporal_attention(const __half* qkv, __half* out, int B, int T, int HW, int heads, float scale, cudaStream_t st);

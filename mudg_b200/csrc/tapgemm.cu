@@ -1,13 +1,15 @@
-// Tap GEMM kernels (see gemm.h).  tcgen05/TMA implementation + SIMT checkers.
+// Tap GEMM kernels (see gemm.h): tcgen05 / TMA implementations of the one contraction every Linear / Conv2d 3x3 /
+// Conv3d (3,1,1) / 1x1 conv of the path maps to.
 //
-// tcgen05 kernel, one 128x128 output tile per CTA, 2 CTAs resident per SM:
-//   warp 0 : TMA producer   -- per k-step one 5-D box of A (64 ch x 128 pixels, shifted by the tap offset,
-//                              OOB -> zeros == conv padding) and one 2-D box of W (64 x 128 rows), SWIZZLE_128B
-//   warp 1 : MMA issuer     -- 4 x tcgen05.mma (M128 N128 K16, fp16 -> fp32 in TMEM) per stage
-//   warps 2-5 : epilogue    -- tcgen05.ld (lane == tile row), bias / per-sample bias / residual / GEGLU,
-//                              fp16 pack into swizzled smem, TMA store (clips partial tiles)
-// Ring of 3 x 32 KB stages; the first stage is reused as the epilogue staging buffer once the
-// accumulator is complete (all operand reads are done by then).
+//   tapgemm_tc2_kernel<SUB>  persistent single-CTA kernel (128 x <=128 tiles, SUB M sub-tiles per weight tile)
+//   tapgemm_tc3_kernel<EPI>  CTA pair (cta_group::2), 256 x <=256 tiles: the large problems
+//   tapgemm_generic_kernel   CUDA cores, arbitrary strides / dtypes: the three irregular layers (< 0.1 % of the FLOPs)
+//
+// Common structure: warp 0 = TMA producer (per k-step one 5-D box of A: 64 channels x 128 pixels, shifted by the tap
+// offset, OOB -> zeros == conv padding; and one box of W), warp 1 = tcgen05.mma issuer (fp16 -> fp32 in TMEM), the other
+// warps = epilogue (tcgen05.ld with lane == tile row; bias / per-sample bias / residual / folded LayerNorm / GEGLU /
+// GroupNorm partial sums; fp16 pack into swizzled smem; TMA store, which clips partial tiles).
+// The CUDA-core checker of the same contract lives in csrc/test/testhooks.cu (tests only).
 #include "gemm.h"
 #include "ptx.cuh"
 
@@ -22,10 +24,7 @@ namespace mudg {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
-constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int TC_THREADS = 192;
-constexpr int TC_SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int BM = 128, BK = 64;
 
 // Division by a runtime constant without the ~40-instruction IDIV sequence (Granlund-Montgomery, dividends < 2^31):
 // the tile decode runs once per tile in EVERY role of the persistent kernels, on their critical path.
@@ -67,215 +66,6 @@ struct TcParams {
   const float* ln_c1;       // [N]
   int8_t taps[9][4];
 };
-
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
-
-__global__ void __launch_bounds__(TC_THREADS, 2)
-tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
-                  const TcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* full = bars;                 // [STAGES]
-  uint64_t* empty = bars + STAGES;       // [STAGES]
-  uint64_t* tmem_full = bars + 2 * STAGES;
-  uint64_t* res_full = bars + 2 * STAGES + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // tile coordinates: N tiles fastest so the CTAs sharing an A tile run together (A read once from HBM)
-  int tile = blockIdx.x;
-  const int nt = tile % p.tiles_n; tile /= p.tiles_n;
-  const int tw = tile % p.tiles_w; tile /= p.tiles_w;
-  const int th = tile % p.tiles_h; tile /= p.tiles_h;
-  const int tt = tile % p.tiles_t;
-  const int tb = tile / p.tiles_t;
-  const int n0 = nt * BN, w0 = tw * p.bw, h0 = th * p.bh, t0 = tt * p.bt, b0 = tb * p.bb;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; i++) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
-    }
-    mbar_init(tmem_full, 1);
-    mbar_init(res_full, 1);
-    fence_mbar_init();
-  }
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    tma_prefetch_desc(&tmD);
-  }
-  if (warp == 1) tmem_alloc<128>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int ktotal = p.ntaps * p.kchunks;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      for (int it = 0; it < ktotal; it++) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], STAGE_BYTES);
-        const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
-        uint8_t* a_s = smem + s * STAGE_BYTES;
-        tma_load_5d(a_s, &tmA, &full[s], kc * BK, w0 + p.taps[tap][0], h0 + p.taps[tap][1], t0 + p.taps[tap][2], b0);
-        tma_load_5d(a_s + A_BYTES, &tmB, &full[s], tap * p.cin + kc * BK, n0, 0, 0, 0);   // all maps are rank 5
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 0, 0);
-      for (int it = 0; it < ktotal; it++) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-        const uint64_t da = umma_desc_sw128(a_addr, 16, 1024);
-        const uint64_t db = umma_desc_sw128(a_addr + A_BYTES, 16, 1024);
-#pragma unroll
-        for (int k = 0; k < BK / 16; k++)   // +32 B per K=16 step inside the 128 B swizzle atom
-          umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
-        umma_commit(&empty[s]);             // frees the smem stage when these MMAs retire
-      }
-      umma_commit(tmem_full);
-    }
-    __syncwarp();
-  } else {
-    // ---------------- epilogue: 128 threads, thread <-> tile row (TMEM lane)
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    uint8_t* stg0 = smem;                   // 16 KB: output columns [0,64) of the tile
-    uint8_t* stg1 = smem + A_BYTES;         // 16 KB: output columns [64,128)
-    const bool issuer = (warp == 2 && lane == 0);
-
-    mbar_wait(tmem_full, 0);
-    __syncwarp();                           // lanes may leave the spin loop apart; .sync.aligned ops follow
-    tc_fence_after();
-
-    // box row -> (iw, ih, it, ib) for the per-sample bias
-    int sample = 0;
-    if (p.bias2 != nullptr) {
-      int r = row;
-      r /= p.bw;
-      r /= p.bh;
-      const int it_ = r % p.bt;
-      const int ib_ = r / p.bt;
-      sample = ((b0 + ib_) * p.dimT + (t0 + it_)) / p.bias2_div;
-      if (sample >= p.nb2) sample = p.nb2 - 1;
-    }
-
-    if (p.geglu) {
-      // TMEM columns [0,64) = value rows, [64,128) = gate rows of the interleaved weight
-#pragma unroll 1
-      for (int c = 0; c < 2; c++) {
-        uint32_t v[32], g[32];
-        tmem_ld32(t_row + c * 32, v);
-        tmem_ld32(t_row + 64 + c * 32, g);
-        tmem_ld_wait();
-        uint32_t o[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float v0 = __uint_as_float(v[i]) * p.alpha, v1 = __uint_as_float(v[i + 1]) * p.alpha;
-          float g0 = __uint_as_float(g[i]) * p.alpha, g1 = __uint_as_float(g[i + 1]) * p.alpha;
-          if (p.bias != nullptr) {
-            const float* bp = p.bias + n0 + c * 32 + i;
-            v0 += __ldg(bp); v1 += __ldg(bp + 1);
-            g0 += __ldg(bp + 64); g1 += __ldg(bp + 65);
-          }
-          o[i >> 1] = pack_half2(v0 * gelu_erf(g0), v1 * gelu_erf(g1));
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int chunk = c * 4 + j;
-          uint4 val = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-          *reinterpret_cast<uint4*>(stg0 + row * 128 + ((chunk ^ (row & 7)) << 4)) = val;
-        }
-      }
-      fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (issuer) {
-        tma_store_5d(&tmD, stg0, nt * 64, w0, h0, t0, b0);
-        tma_store_commit();
-      }
-      __syncwarp();
-    } else {
-      const int nhalf = (n0 + 64 < p.N) ? 2 : 1;
-      if (p.has_res) {
-        if (issuer) {
-          mbar_expect_tx(res_full, nhalf * A_BYTES);
-          tma_load_5d(stg0, &tmR, res_full, n0, w0, h0, t0, b0);
-          if (nhalf == 2) tma_load_5d(stg1, &tmR, res_full, n0 + 64, w0, h0, t0, b0);
-        }
-        __syncwarp();
-        mbar_wait(res_full, 0);
-        __syncwarp();
-      }
-#pragma unroll 1
-      for (int hf = 0; hf < nhalf; hf++) {
-        uint8_t* stg = hf ? stg1 : stg0;
-#pragma unroll 1
-        for (int c = 0; c < 2; c++) {
-          uint32_t v[32];
-          tmem_ld32(t_row + hf * 64 + c * 32, v);
-          tmem_ld_wait();
-          const int col0 = n0 + hf * 64 + c * 32;
-          float f[32];
-#pragma unroll
-          for (int i = 0; i < 32; i++) f[i] = __uint_as_float(v[i]) * p.alpha;
-          if (p.bias != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 32; i++) f[i] += __ldg(p.bias + col0 + i);
-          }
-          if (p.bias2 != nullptr) {
-            const float* b2 = p.bias2 + (size_t)sample * p.N + col0;
-#pragma unroll
-            for (int i = 0; i < 32; i++) f[i] += __ldg(b2 + i);
-          }
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const int chunk = c * 4 + j;
-            uint4* sp = reinterpret_cast<uint4*>(stg + row * 128 + ((chunk ^ (row & 7)) << 4));
-            if (p.has_res) {
-              const uint4 r4 = *sp;
-              const float2 r0 = unpack_half2(r4.x), r1 = unpack_half2(r4.y), r2 = unpack_half2(r4.z),
-                           r3 = unpack_half2(r4.w);
-              f[8 * j + 0] += r0.x; f[8 * j + 1] += r0.y; f[8 * j + 2] += r1.x; f[8 * j + 3] += r1.y;
-              f[8 * j + 4] += r2.x; f[8 * j + 5] += r2.y; f[8 * j + 6] += r3.x; f[8 * j + 7] += r3.y;
-            }
-            *sp = make_uint4(pack_half2(f[8 * j + 0], f[8 * j + 1]), pack_half2(f[8 * j + 2], f[8 * j + 3]),
-                             pack_half2(f[8 * j + 4], f[8 * j + 5]), pack_half2(f[8 * j + 6], f[8 * j + 7]));
-          }
-        }
-        fence_proxy_async_smem();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (issuer) {
-          tma_store_5d(&tmD, stg, n0 + hf * 64, w0, h0, t0, b0);
-          tma_store_commit();
-        }
-        __syncwarp();
-      }
-    }
-    if (issuer) tma_store_wait_read0();     // smem must stay valid until the bulk stores have read it
-    __syncwarp();
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    tc_fence_after();
-    tmem_dealloc<128>(tmem_base);
-  }
-}
 
 // ================================================================ tap GEMM v2: persistent, double-buffered accumulators
 // Two persistent CTAs per SM loop over output tiles (N tiles fastest so co-resident CTAs share A in L2):
@@ -1093,61 +883,6 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// SIMT checker of the same contract: one thread per output element, fp32 accumulate.
-__global__ void tapgemm_simt_kernel(const __half* __restrict__ A, const __half* __restrict__ Wt, __half* __restrict__ D,
-                                    const __half* __restrict__ R, int B, int T, int H, int W, int Cin, int ntaps,
-                                    TcParams p) {
-  const int n_out = p.n_out;
-  const int64_t total = (int64_t)B * T * H * W * n_out;
-  const int Ktot = ntaps * Cin;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int n = idx % n_out;
-    int64_t m = idx / n_out;
-    const int w = m % W; m /= W;
-    const int h = m % H; m /= H;
-    const int t = m % T;
-    const int b = m / T;
-    // geglu: value row / gate row inside the 64/64 interleaved weight
-    const int nv = p.geglu ? ((n / 64) * 128 + (n % 64)) : n;
-    const int ng = nv + 64;
-    float acc = 0.f, accg = 0.f;
-    for (int tap = 0; tap < ntaps; tap++) {
-      const int ww = w + p.taps[tap][0], hh = h + p.taps[tap][1], tt = t + p.taps[tap][2];
-      if (ww < 0 || ww >= W || hh < 0 || hh >= H || tt < 0 || tt >= T) continue;
-      const __half* a = A + ((((int64_t)b * T + tt) * H + hh) * W + ww) * Cin;
-      const __half* wv = Wt + (int64_t)nv * Ktot + tap * Cin;
-      const __half* wg = Wt + (int64_t)ng * Ktot + tap * Cin;
-      for (int c = 0; c < Cin; c++) {
-        const float av = __half2float(a[c]);
-        acc += av * __half2float(wv[c]);
-        if (p.geglu) accg += av * __half2float(wg[c]);
-      }
-    }
-    if (p.ln_stats != nullptr) {           // folded LayerNorm (rows == pixels here: linear layers only)
-      const float2 ms = p.ln_stats[idx / n_out];
-      acc = ms.y * (acc - ms.x * p.ln_c1[nv]);
-      accg = ms.y * (accg - ms.x * p.ln_c1[ng < p.N ? ng : nv]);
-    }
-    float out;
-    if (p.geglu) {
-      float v = acc * p.alpha, g = accg * p.alpha;
-      if (p.bias) { v += p.bias[nv]; g += p.bias[ng]; }
-      out = v * gelu_erf(g);
-    } else {
-      out = acc * p.alpha;
-      if (p.bias) out += p.bias[n];
-      if (p.bias2) {
-        int s = (b * T + t) / p.bias2_div;
-        if (s >= p.nb2) s = p.nb2 - 1;
-        out += p.bias2[(size_t)s * p.N + n];
-      }
-      if (R) out += __half2float(R[idx]);
-    }
-    D[idx] = __float2half_rn(out);
-  }
-}
-
 template <typename TA, typename TD>
 __global__ void tapgemm_generic_kernel(TapGemmGeneric g) {
   const int64_t total = (int64_t)g.B * g.T * g.H * g.W * g.N;
@@ -1234,56 +969,12 @@ bool tapgemm_tc_eligible(const TapGemm& g) {
   return true;
 }
 
-void tapgemm_tc(const TapGemm& g, cudaStream_t st) {
-  MUDG_REQUIRE(tapgemm_tc_eligible(g), "layer not eligible for the tcgen05 path (Cin=%d N=%d)", g.Cin, g.N);
-  MUDG_REQUIRE(g.ln_stats == nullptr, "the v1 GEMM kernel has no folded-LayerNorm epilogue");
-  TcParams p = make_params(g);
-  // box: 128 pixels = bw*bh*bt*bb
-  int budget = BM;
-  p.bw = pick_box(g.W, budget); budget /= p.bw;
-  p.bh = pick_box(g.H, budget); budget /= p.bh;
-  p.bt = pick_box(g.T, budget); budget /= p.bt;
-  p.bb = budget;                                   // whatever is left goes to the batch dim (may overhang)
-  p.tiles_n = (g.N + BN - 1) / BN;
-  p.tiles_w = (g.W + p.bw - 1) / p.bw;
-  p.tiles_h = (g.H + p.bh - 1) / p.bh;
-  p.tiles_t = (g.T + p.bt - 1) / p.bt;
-  const int tiles_b = (g.B + p.bb - 1) / p.bb;
-  const int64_t grid = (int64_t)p.tiles_n * p.tiles_w * p.tiles_h * p.tiles_t * tiles_b;
-  MUDG_REQUIRE(grid > 0 && grid < (int64_t(1) << 31), "grid too large");
-
-  const uint64_t C = g.Cin, No = p.n_out, Ktot = (uint64_t)g.ntaps * g.Cin;
-  const uint64_t adims[5] = {C, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.T, (uint64_t)g.B};
-  const uint64_t astr[4] = {C * 2, C * 2 * g.W, C * 2 * g.W * g.H, C * 2 * g.W * g.H * g.T};
-  const uint32_t abox[5] = {BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bt, (uint32_t)p.bb};
-  const uint64_t ddims[5] = {No, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.T, (uint64_t)g.B};
-  const uint64_t dstr[4] = {No * 2, No * 2 * g.W, No * 2 * g.W * g.H, No * 2 * g.W * g.H * g.T};
-  const uint64_t bdims[5] = {Ktot, (uint64_t)g.N, 1, 1, 1};
-  const uint64_t bstr[4] = {Ktot * 2, Ktot * 2 * g.N, Ktot * 2 * g.N, Ktot * 2 * g.N};
-  const uint32_t bbox[5] = {BK, BN, 1, 1, 1};
-  const CUtensorMap* ma = get_tmap(g.A, adims, astr, abox);
-  const CUtensorMap* mb = get_tmap(g.Wt, bdims, bstr, bbox);
-  const CUtensorMap* md = get_tmap(g.D, ddims, dstr, abox);
-  const CUtensorMap* mr = g.R ? get_tmap(g.R, ddims, dstr, abox) : md;
-
-  static bool attr_set = false;
-  if (!attr_set) {
-    MUDG_CUDA(cudaFuncSetAttribute(tapgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    attr_set = true;
-  }
-  tapgemm_tc_kernel<<<(unsigned)grid, TC_THREADS, TC_SMEM, st>>>(*ma, *mb, *md, *mr, p);
-  MUDG_CUDA(cudaGetLastError());
-}
-
 // CTA-pair kernel (tapgemm_tc3_kernel): large problems only (several waves of 256 x 256 tiles over the 74 TPCs)
 static long long* g_gemm_trace = nullptr;
 void gemm_set_trace(long long* buf) { g_gemm_trace = buf; }
 
 bool tapgemm_pair_wanted(const TapGemm& g, int64_t m_tiles, int nt128) {
-  static const int mode = [] {
-    const char* e = getenv("MUDG_GEMM_PAIR");
-    return e ? atoi(e) : -1;
-  }();
+  const int mode = knobs().gemm_pair;
   if (mode == 0) return false;
   if (mode == 1) return true;
   const int ktot_steps = g.ntaps * ((g.Cin + BK - 1) / BK);
@@ -1323,11 +1014,7 @@ void tapgemm_tc3(const TapGemm& g, cudaStream_t st) {
   p.R = g.R;
   p.alpha_is_one = g.alpha == 1.f ? 1 : 0;
   p.trace = g_gemm_trace;
-  static const int dbg_env = [] {
-    const char* e = getenv("MUDG_GEMM_DBG");
-    return e ? atoi(e) : 0;
-  }();
-  p.dbg = dbg_env;
+  p.dbg = knobs().gemm_dbg;
 
   const uint64_t C = g.Cin, No = p.b.n_out, Ktot = (uint64_t)g.ntaps * g.Cin;
   const uint64_t adims[5] = {C, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.T, (uint64_t)g.B};
@@ -1356,8 +1043,8 @@ void tapgemm_tc3(const TapGemm& g, cudaStream_t st) {
   const int clusters = (int)std::min<int64_t>(total, sm_count() / 2);
   p.rot_div = FastDiv{0u, 0u, 0};
   if (p.nt > 1 && clusters % p.nt == 0) p.rot_div = make_fastdiv(clusters);
-  // epilogue specialisation (see the kernel's EPI comment); MUDG_GEMM_EPI=0 forces the run-time variant
-  static const bool epi_on = [] { const char* e = getenv("MUDG_GEMM_EPI"); return !(e && e[0] == '0'); }();
+  // epilogue specialisation (see the kernel's EPI comment); knob gemm_epi = 0 forces the run-time variant
+  const bool epi_on = knobs().gemm_epi != 0;
   int epi = -1;
   if (epi_on && !g.geglu && g.alpha == 1.f)
     epi = (g.bias ? 1 : 0) | (g.bias2 ? 2 : 0) | (g.R ? 4 : 0) | (g.ln_stats ? 8 : 0);
@@ -1368,8 +1055,9 @@ void tapgemm_tc3(const TapGemm& g, cudaStream_t st) {
     case 3: tapgemm_tc3_kernel<3><<<grid, G3_THREADS, G3_SMEM, st>>>(*ma, *mb0, *mb1, *md, p); break;
     case 5: tapgemm_tc3_kernel<5><<<grid, G3_THREADS, G3_SMEM, st>>>(*ma, *mb0, *mb1, *md, p); break;
     case 9: tapgemm_tc3_kernel<9><<<grid, G3_THREADS, G3_SMEM, st>>>(*ma, *mb0, *mb1, *md, p); break;
-    default: tapgemm_tc3_kernel<-1><<<grid, G3_THREADS, G3_SMEM, st>>>(*ma, *mb0, *mb1, *md, p); break;
+    default: epi = -1; tapgemm_tc3_kernel<-1><<<grid, G3_THREADS, G3_SMEM, st>>>(*ma, *mb0, *mb1, *md, p); break;
   }
+  knobs().last_gemm_path = 4 | ((epi + 1) << 8);
   MUDG_CUDA(cudaGetLastError());
 }
 
@@ -1404,11 +1092,8 @@ void tapgemm_tc2(const TapGemm& g, cudaStream_t st) {
   const int64_t m_tiles = (int64_t)p.b.tiles_w * p.b.tiles_h * p.b.tiles_t * p.tiles_b;
   MUDG_REQUIRE(m_tiles * p.nt < (int64_t(1) << 30), "grid too large");
   p.m_tiles = (int)m_tiles;
-  // 256-row super tiles when there is enough work to fill the machine several times over (MUDG_GEMM_SUB=1|2 forces)
-  static const int force_sub = [] {
-    const char* e = getenv("MUDG_GEMM_SUB");
-    return e ? atoi(e) : 0;
-  }();
+  // 256-row super tiles when there is enough work to fill the machine several times over (knob gemm_sub = 1|2 forces)
+  const int force_sub = knobs().gemm_sub;
   const int ktot_steps = g.ntaps * ((g.Cin + BK - 1) / BK);
   int sub = (m_tiles * p.nt >= 8 * (int64_t)sm_count() && ktot_steps >= 8) ? 2 : 1;
   if (force_sub == 1 || force_sub == 2) sub = force_sub;
@@ -1443,14 +1128,7 @@ void tapgemm_tc2(const TapGemm& g, cudaStream_t st) {
     const int grid = (int)std::min<int64_t>(total, sm_count());
     tapgemm_tc2_kernel<2><<<grid, G2Cfg<2>::THREADS, G2Cfg<2>::SMEM, st>>>(*ma, *mb, *md, p);
   }
-  MUDG_CUDA(cudaGetLastError());
-}
-
-void tapgemm_simt(const TapGemm& g, cudaStream_t st) {
-  TcParams p = make_params(g);
-  const int64_t total = (int64_t)g.B * g.T * g.H * g.W * p.n_out;
-  const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 64);
-  tapgemm_simt_kernel<<<blocks, 256, 0, st>>>(g.A, g.Wt, g.D, g.R, g.B, g.T, g.H, g.W, g.Cin, g.ntaps, p);
+  knobs().last_gemm_path = sub == 1 ? 2 : 3;
   MUDG_CUDA(cudaGetLastError());
 }
 
@@ -1462,15 +1140,6 @@ void tapgemm_generic(const TapGemmGeneric& g, cudaStream_t st) {
   else if (g.d_fp32) tapgemm_generic_kernel<__half, float><<<blocks, 256, 0, st>>>(g);
   else tapgemm_generic_kernel<__half, __half><<<blocks, 256, 0, st>>>(g);
   MUDG_CUDA(cudaGetLastError());
-}
-
-void tapgemm_tc_auto(const TapGemm& g, cudaStream_t st) {
-  static const bool use_v1 = [] {
-    const char* e = getenv("MUDG_GEMM_V1");
-    return e && e[0] == '1';
-  }();
-  if (use_v1) tapgemm_tc(g, st);
-  else tapgemm_tc2(g, st);
 }
 
 // ---- optional per-launch timing of the tcgen05 GEMM (bench.py's roofline leg): CUDA events on the launching stream
@@ -1527,11 +1196,9 @@ void gemm_profile_read(double* ms_total, double* flops_total, int64_t* launches)
 }
 
 void tapgemm(const TapGemm& g, cudaStream_t st) {
-  static const bool force_simt = [] {
-    const char* e = getenv("MUDG_FORCE_SIMT");
-    return e && e[0] == '1';
-  }();
-  if (!force_simt && tapgemm_tc_eligible(g)) {
+  MUDG_REQUIRE(tapgemm_tc_eligible(g), "layer not eligible for the tcgen05 path (Cin=%d N=%d, 16 B alignment): there is no "
+               "CUDA-core fallback in the product library", g.Cin, g.N);
+  {
     if (g_prof.on) {
       if (g_prof.ev.size() < 2 * (g_prof.used + 1)) {
         cudaEvent_t a, b;
@@ -1541,7 +1208,7 @@ void tapgemm(const TapGemm& g, cudaStream_t st) {
         g_prof.ev.push_back(b);
       }
       MUDG_CUDA(cudaEventRecord(g_prof.ev[2 * g_prof.used], st));
-      tapgemm_tc_auto(g, st);
+      tapgemm_tc2(g, st);
       MUDG_CUDA(cudaEventRecord(g_prof.ev[2 * g_prof.used + 1], st));
       // algorithmic work of the layer: 2 * rows * N * (taps * Cin), padding and tile overhang not counted
       g_prof.flops.push_back(2.0 * (double)g.B * g.T * g.H * g.W * (double)g.N * (double)g.ntaps * g.Cin);
@@ -1553,10 +1220,8 @@ void tapgemm(const TapGemm& g, cudaStream_t st) {
       }
       g_prof.used++;
     } else {
-      tapgemm_tc_auto(g, st);
+      tapgemm_tc2(g, st);
     }
-  } else {
-    tapgemm_simt(g, st);
   }
 }
 

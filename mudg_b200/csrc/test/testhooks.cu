@@ -1,0 +1,402 @@
+// libmudg_sm100_test.so only (tests/): single-kernel entry points, CUDA-core checkers of the tcgen05 kernels' contracts,
+// the tcgen05.mma issue-rate probes and the tuning knobs.  None of this is part of the product library
+// (libmudg_sm100.so): the test library links its own copy of the product objects plus this file.
+#include <cmath>
+#include <cstring>
+
+#include "../gemm.h"
+#include "../model.h"
+#include "../ops.h"
+#include "../ptx.cuh"
+#include "mudg.h"
+#include "mudg_test.h"
+
+namespace mudg {
+const char* last_error_cstr();
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// CUDA-core checker of the tap-GEMM contract (gemm.h): one thread per output element, fp32 accumulate.
+struct SimtGemm {
+  const __half* A; const __half* Wt; __half* D; const __half* R;
+  int B, T, H, W, Cin, ntaps, N, n_out, geglu;
+  const float* bias; const float* bias2; int bias2_div, nb2;
+  float alpha;
+  const float2* ln_stats; const float* ln_c1;
+  int8_t taps[9][4];
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+
+__global__ void tapgemm_simt_kernel(const SimtGemm p) {
+  const int64_t total = (int64_t)p.B * p.T * p.H * p.W * p.n_out;
+  const int Ktot = p.ntaps * p.Cin;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int n = idx % p.n_out;
+    int64_t m = idx / p.n_out;
+    const int w = m % p.W; m /= p.W;
+    const int h = m % p.H; m /= p.H;
+    const int t = m % p.T;
+    const int b = m / p.T;
+    // geglu: value row / gate row inside the 64/64 interleaved weight
+    const int nv = p.geglu ? ((n / 64) * 128 + (n % 64)) : n;
+    const int ng = nv + 64;
+    float acc = 0.f, accg = 0.f;
+    for (int tap = 0; tap < p.ntaps; tap++) {
+      const int ww = w + p.taps[tap][0], hh = h + p.taps[tap][1], tt = t + p.taps[tap][2];
+      if (ww < 0 || ww >= p.W || hh < 0 || hh >= p.H || tt < 0 || tt >= p.T) continue;
+      const __half* a = p.A + ((((int64_t)b * p.T + tt) * p.H + hh) * p.W + ww) * p.Cin;
+      const __half* wv = p.Wt + (int64_t)nv * Ktot + tap * p.Cin;
+      const __half* wg = p.Wt + (int64_t)ng * Ktot + tap * p.Cin;
+      for (int c = 0; c < p.Cin; c++) {
+        const float av = __half2float(a[c]);
+        acc += av * __half2float(wv[c]);
+        if (p.geglu) accg += av * __half2float(wg[c]);
+      }
+    }
+    float al = p.alpha;
+    if (p.ln_stats != nullptr) {           // folded LayerNorm: rstd * (acc - mean * c1[n]); c2 arrives as the bias
+      const float2 ms = p.ln_stats[idx / p.n_out];
+      acc = ms.y * (acc - ms.x * p.ln_c1[nv]);
+      if (p.geglu) accg = ms.y * (accg - ms.x * p.ln_c1[ng]);
+      al = 1.f;
+    }
+    float out;
+    if (p.geglu) {
+      float v = acc * al, g = accg * al;
+      if (p.bias) { v += p.bias[nv]; g += p.bias[ng]; }
+      out = v * gelu_erf(g);
+    } else {
+      out = acc * al;
+      if (p.bias) out += p.bias[n];
+      if (p.bias2) {
+        int s = (b * p.T + t) / p.bias2_div;
+        if (s >= p.nb2) s = p.nb2 - 1;
+        out += p.bias2[(size_t)s * p.N + n];
+      }
+      if (p.R) out += __half2float(p.R[idx]);
+    }
+    p.D[idx] = __float2half_rn(out);
+  }
+}
+
+void tapgemm_simt(const TapGemm& g, cudaStream_t st) {
+  SimtGemm p{};
+  p.A = g.A; p.Wt = g.Wt; p.D = g.D; p.R = g.R;
+  p.B = g.B; p.T = g.T; p.H = g.H; p.W = g.W; p.Cin = g.Cin; p.ntaps = g.ntaps; p.N = g.N;
+  p.geglu = g.geglu ? 1 : 0;
+  p.n_out = g.geglu ? g.N / 2 : g.N;
+  p.bias = g.bias; p.bias2 = g.bias2; p.bias2_div = g.bias2_div > 0 ? g.bias2_div : 1; p.nb2 = g.nb2;
+  p.alpha = g.alpha; p.ln_stats = g.ln_stats; p.ln_c1 = g.ln_c1;
+  for (int i = 0; i < g.ntaps; i++)
+    for (int j = 0; j < 3; j++) p.taps[i][j] = g.taps[i][j];
+  const int64_t total = (int64_t)g.B * g.T * g.H * g.W * p.n_out;
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 64);
+  tapgemm_simt_kernel<<<blocks, 256, 0, st>>>(p);
+  MUDG_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------- SIMT checker: thread per (frame, head, query)
+__global__ void flash_simt_kernel(FlashArgs a) {
+  const int64_t total = (int64_t)a.F * a.heads * a.Nq;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int qi = idx % a.Nq;
+  const int head = (idx / a.Nq) % a.heads;
+  const int f = idx / ((int64_t)a.Nq * a.heads);
+  const __half* qp = a.Q + ((int64_t)f * a.Nq + qi) * a.q_pitch + head * 64;
+  float q[64], out[64];
+  for (int i = 0; i < 64; i++) { q[i] = __half2float(qp[i]); out[i] = 0.f; }
+  for (int sg = 0; sg < a.nseg; sg++) {
+    const FlashSeg& s = a.seg[sg];
+    const int kb = f / s.kv_div;
+    float m = -INFINITY, l = 0.f, o[64];
+    for (int i = 0; i < 64; i++) o[i] = 0.f;
+    for (int j = 0; j < s.len; j++) {
+      const __half* kp = s.K + ((int64_t)kb * s.len + j) * s.pitch + head * 64;
+      const __half* vp = s.V + ((int64_t)kb * s.len + j) * s.pitch + head * 64;
+      float d = 0.f;
+      for (int i = 0; i < 64; i++) d += q[i] * __half2float(kp[i]);
+      d *= a.scale;
+      const float mn = fmaxf(m, d);
+      const float al = expf(m - mn), pj = expf(d - mn);
+      l = l * al + pj;
+      for (int i = 0; i < 64; i++) o[i] = o[i] * al + pj * __half2float(vp[i]);
+      m = mn;
+    }
+    for (int i = 0; i < 64; i++) out[i] += o[i] / l;
+  }
+  __half* op = a.O + ((int64_t)f * a.Nq + qi) * a.o_pitch + head * 64;
+  for (int i = 0; i < 64; i++) op[i] = __float2half_rn(out[i]);
+}
+
+
+// ---------------------------------------------------------------- tcgen05.mma issue-rate probe (tests/gpu_probe_mma.py)
+// One thread issues `reps` MMAs of a given shape / operand source / accumulator pattern on garbage operands and times
+// issue -> completion with clock64.  Used to find out what actually paces the attention kernel's small MMAs.
+template <int variant>
+__device__ __forceinline__ void mma_probe_issue(int r, uint32_t tm, uint64_t da, uint64_t db, uint64_t dv) {
+  constexpr uint32_t i128 = umma_idesc_f16(128, 128, 0, 0), i256 = umma_idesc_f16(128, 256, 0, 0),
+                     i64 = umma_idesc_f16(128, 64, 0, 0), i64v = umma_idesc_f16(128, 64, 0, 1);
+  const uint32_t acc = r >= 4 ? 1u : 0u;
+  const uint64_t ko = 2 * (r & 3);
+  switch (variant) {
+    case 0: umma_f16(tm, da + ko, db + ko, i128, acc); break;                              // SS N128, one D
+    case 1: umma_f16(tm + (r & 1) * 128, da + ko, db + ko, i128, acc); break;              // SS N128, 2 D
+    case 2: umma_f16(tm, da + ko, db + ko, i256, acc); break;                              // SS N256, one D
+    case 3: umma_f16(tm, da + ko, db + ko, i64, acc); break;                               // SS N64, one D
+    case 4: umma_f16(tm + (r & 3) * 64, da + ko, db + ko, i64, acc); break;                // SS N64, 4 D
+    case 5: umma_f16_ts(tm, tm + 384 + (r & 7) * 8, dv + (uint64_t)((r & 7) * 128), i64v, acc); break;          // TS N64 MN-major B
+    case 6: umma_f16_ts(tm + (r & 1) * 64, tm + 384 + (r & 7) * 8, dv + (uint64_t)((r & 7) * 128), i64v, acc); break;
+    case 7: umma_f16_ts(tm + (r & 3) * 64, tm + 384 + (r & 7) * 8, dv + (uint64_t)((r & 7) * 128), i64v, acc); break;
+    case 8: umma_f16(tm + (r & 3) * 128, da + ko, db + ko, i128, acc); break;              // SS N128, 4 D
+    case 9: umma_f16_ts(tm, tm + 384 + (r & 7) * 8, db + ko, i64, acc); break;             // TS N64 K-major B
+    case 10: umma_f16_ts(tm, tm + 256 + (r & 7) * 8, db + ko, i128, acc); break;           // TS N128 K-major B
+    case 11: umma_f16_ts(tm, tm + 256 + (r & 7) * 8, db + ko, i256, acc); break;           // TS N256
+    default: break;
+  }
+}
+
+// mode 0: a single diverged thread issues (if (threadIdx.x == 0) ...); mode 1: the whole warp runs the loop and one
+// elected lane issues (uniform control flow, operands in uniform registers)
+template <int VARIANT>
+__global__ void __launch_bounds__(128, 1) mma_probe_kernel(int reps, int mode, long long* out) {
+  extern __shared__ __align__(1024) uint8_t psm[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(psm)[i] = 0x3c003c00u;   // 1.0h
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (threadIdx.x < 32) tmem_alloc<512>(&slot);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = slot;
+  const uint64_t da = umma_desc_sw128(smem_u32(psm), 16, 1024);                 // K-major 128 x 64
+  const uint64_t db = umma_desc_sw128(smem_u32(psm) + 32768, 16, 1024);         // K-major up to 256 x 64
+  const uint64_t dv = umma_desc_sw128(smem_u32(psm) + 65536, 1024, 1024);       // MN-major 128 x 64
+  if (mode == 0) {
+    if (threadIdx.x == 0) {
+      const long long t0 = clock64();
+      for (int r = 0; r < reps; r++) mma_probe_issue<VARIANT>(r, tm, da, db, dv);
+      const long long t1 = clock64();
+      umma_commit(&bar);
+      mbar_wait(&bar, 0);
+      const long long t2 = clock64();
+      out[blockIdx.x * 2] = t1 - t0;
+      out[blockIdx.x * 2 + 1] = t2 - t0;
+    }
+  } else if (threadIdx.x < 32) {
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; r++) {
+      if (elect_one()) mma_probe_issue<VARIANT>(r, tm, da, db, dv);
+      __syncwarp();
+    }
+    const long long t1 = clock64();
+    if (elect_one()) umma_commit(&bar);
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    const long long t2 = clock64();
+    if (threadIdx.x == 0) {
+      out[blockIdx.x * 2] = t1 - t0;
+      out[blockIdx.x * 2 + 1] = t2 - t0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (threadIdx.x < 32) tmem_dealloc<512>(tm);
+}
+
+
+void flash_attention_simt(const FlashArgs& a, cudaStream_t st) {
+  const int64_t total = (int64_t)a.F * a.heads * a.Nq;
+  flash_simt_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(a);
+  MUDG_CUDA(cudaGetLastError());
+}
+
+void mma_probe(int variant, int reps, int ctas, int mode, long long* out, cudaStream_t st) {
+#define MUDG_PROBE_CASE(V)                                                                                         \
+  case V:                                                                                                           \
+    MUDG_CUDA(cudaFuncSetAttribute(mma_probe_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));  \
+    mma_probe_kernel<V><<<ctas, 128, 96 * 1024, st>>>(reps, mode, out);                                            \
+    break;
+  switch (variant) {
+    MUDG_PROBE_CASE(0) MUDG_PROBE_CASE(1) MUDG_PROBE_CASE(2) MUDG_PROBE_CASE(3) MUDG_PROBE_CASE(4) MUDG_PROBE_CASE(5)
+    MUDG_PROBE_CASE(6) MUDG_PROBE_CASE(7) MUDG_PROBE_CASE(8) MUDG_PROBE_CASE(9) MUDG_PROBE_CASE(10) MUDG_PROBE_CASE(11)
+    default: MUDG_REQUIRE(false, "mma_probe: variant %d", variant);
+  }
+#undef MUDG_PROBE_CASE
+  MUDG_CUDA(cudaGetLastError());
+}
+
+
+}  // namespace
+}  // namespace mudg
+
+using namespace mudg;
+
+#define MUDG_API_BEGIN try {
+#define MUDG_API_END                          \
+  return 0;                                   \
+  }                                           \
+  catch (const std::exception& e) {           \
+    mudg::set_last_error(e.what());           \
+    return -1;                                \
+  }                                           \
+  catch (...) {                               \
+    mudg::set_last_error("unknown exception"); \
+    return -2;                                \
+  }
+
+static cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+MUDG_EXPORT int mudg_test_set_knob(const char* name, int value) {
+  MUDG_API_BEGIN
+  Knobs& k = knobs();
+  const std::string n = name ? name : "";
+  if (n == "gemm_pair") k.gemm_pair = value;
+  else if (n == "gemm_sub") k.gemm_sub = value;
+  else if (n == "gemm_epi") k.gemm_epi = value;
+  else if (n == "gemm_dbg") k.gemm_dbg = value;
+  else if (n == "flash_stagger") k.flash_stagger = value;
+  else if (n == "flash_poly") k.flash_poly = value;
+  else if (n == "tattn_generic") k.tattn_generic = value;
+  else if (n == "gn_fuse") k.gn_fuse = value;
+  else if (n == "reset") k = Knobs{};
+  else MUDG_REQUIRE(false, "unknown knob %s", n.c_str());
+  MUDG_API_END
+}
+
+MUDG_EXPORT int mudg_test_last_gemm_path(void) { return knobs().last_gemm_path; }
+
+MUDG_EXPORT int mudg_test_tapgemm(const void* A, int B, int T, int H, int W, int Cin, int mode, const void* Wt, int N,
+                                  void* D, const void* R, const float* bias, const float* bias2, int bias2_div, int nb2,
+                                  float alpha, int geglu, const void* ln_stats, const float* ln_c1, int backend,
+                                  void* stream) {
+  MUDG_API_BEGIN
+  TapGemm g;
+  g.A = static_cast<const __half*>(A);
+  g.B = B; g.T = T; g.H = H; g.W = W; g.Cin = Cin;
+  if (mode == 0) { g.ntaps = 1; g.taps[0][0] = g.taps[0][1] = g.taps[0][2] = 0; }
+  else if (mode == 1) { g.ntaps = 9; set_taps_3x3(g.taps); }
+  else { g.ntaps = 3; set_taps_t3(g.taps); }
+  g.Wt = static_cast<const __half*>(Wt);
+  g.N = N;
+  g.D = static_cast<__half*>(D);
+  g.R = static_cast<const __half*>(R);
+  g.bias = bias; g.bias2 = bias2; g.bias2_div = bias2_div; g.nb2 = nb2;
+  g.alpha = alpha; g.geglu = geglu != 0;
+  g.ln_stats = static_cast<const float2*>(ln_stats);
+  g.ln_c1 = ln_c1;
+  knobs().last_gemm_path = 0;
+  if (backend == 0) tapgemm(g, S(stream));          // the product dispatch (tcgen05)
+  else tapgemm_simt(g, S(stream));
+  MUDG_API_END
+}
+
+MUDG_EXPORT int mudg_test_flash(const void* Q, int q_pitch, void* O, int o_pitch, int F, int Nq, int heads,
+                                const void* K0, const void* V0, int pitch0, int len0, int nbatch0, int div0,
+                                const void* K1, const void* V1, int pitch1, int len1, int nbatch1, int div1, float scale,
+                                int backend, void* stream) {
+  MUDG_API_BEGIN
+  FlashArgs a;
+  a.Q = static_cast<const __half*>(Q); a.q_pitch = q_pitch;
+  a.O = static_cast<__half*>(O); a.o_pitch = o_pitch;
+  a.F = F; a.Nq = Nq; a.heads = heads; a.scale = scale;
+  a.nseg = K1 ? 2 : 1;
+  a.seg[0].K = static_cast<const __half*>(K0); a.seg[0].V = static_cast<const __half*>(V0);
+  a.seg[0].pitch = pitch0; a.seg[0].len = len0; a.seg[0].nbatch = nbatch0; a.seg[0].kv_div = div0;
+  a.seg[1].K = static_cast<const __half*>(K1); a.seg[1].V = static_cast<const __half*>(V1);
+  a.seg[1].pitch = pitch1; a.seg[1].len = len1; a.seg[1].nbatch = nbatch1; a.seg[1].kv_div = div1;
+  if (backend == 0) {
+    // the tcgen05 kernel reads V transposed: build V^T of each segment in a (grow-only) scratch buffer of the test hook
+    static __half* scratch[2] = {nullptr, nullptr};
+    static size_t scratch_bytes[2] = {0, 0};
+    for (int i = 0; i < a.nseg; i++) {
+      FlashSeg& sg = a.seg[i];
+      const int pad = (sg.len + 7) / 8 * 8;
+      const size_t need = sizeof(__half) * (size_t)sg.nbatch * heads * 64 * pad;
+      if (scratch_bytes[i] < need) {
+        MUDG_CUDA(cudaDeviceSynchronize());
+        cudaFree(scratch[i]);
+        MUDG_CUDA(cudaMalloc(&scratch[i], need));
+        scratch_bytes[i] = need;
+      }
+      transpose_v(sg.V, sg.pitch, sg.len, sg.nbatch, heads, scratch[i], pad, S(stream));
+      sg.VT = scratch[i];
+      sg.vt_pitch = pad;
+    }
+    flash_attention(a, S(stream));
+  } else {
+    flash_attention_simt(a, S(stream));
+  }
+  MUDG_API_END
+}
+
+MUDG_EXPORT int mudg_test_gemm_trace(void* buf) {
+  MUDG_API_BEGIN
+  gemm_set_trace(static_cast<long long*>(buf));
+  MUDG_API_END
+}
+
+MUDG_EXPORT int mudg_test_mma_probe(int variant, int reps, int ctas, int mode, void* out, void* stream) {
+  MUDG_API_BEGIN
+  mma_probe(variant, reps, ctas, mode, static_cast<long long*>(out), S(stream));
+  MUDG_API_END
+}
+
+MUDG_EXPORT int mudg_test_flash_trace(void* buf) {
+  MUDG_API_BEGIN
+  flash_set_trace(static_cast<long long*>(buf));
+  MUDG_API_END
+}
+
+MUDG_EXPORT int mudg_test_temporal_attn(const void* qkv, void* out, int B, int T, int HW, int heads, float scale,
+                                        void* stream) {
+  MUDG_API_BEGIN
+  temporal_attention(static_cast<const __half*>(qkv), static_cast<__half*>(out), B, T, HW, heads, scale, S(stream));
+  MUDG_API_END
+}
+
+MUDG_EXPORT int mudg_test_groupnorm(const void* x, void* y, int Sn, int64_t rows_per_sample, int C, const float* gamma,
+                                    const float* beta, float eps, int silu, void* stream) {
+  MUDG_API_BEGIN
+  double* sums = nullptr;
+  float* ss = nullptr;
+  MUDG_CUDA(cudaMalloc(&sums, sizeof(double) * Sn * 64));
+  MUDG_CUDA(cudaMalloc(&ss, sizeof(float) * Sn * C * 2));
+  gn_scale_shift(static_cast<const __half*>(x), Sn, rows_per_sample, C, gamma, beta, eps, sums, ss, ss + (size_t)Sn * C,
+                 S(stream));
+  gn_apply(static_cast<const __half*>(x), static_cast<__half*>(y), ss, ss + (size_t)Sn * C, (int64_t)Sn * rows_per_sample, C,
+           rows_per_sample, silu != 0, S(stream));
+  MUDG_CUDA(cudaStreamSynchronize(S(stream)));
+  cudaFree(sums);
+  cudaFree(ss);
+  MUDG_API_END
+}
+
+MUDG_EXPORT int mudg_test_layernorm(const void* x, void* y, const float* gamma, const float* beta, int64_t rows, int C,
+                                    void* stream) {
+  MUDG_API_BEGIN
+  layernorm(static_cast<const __half*>(x), static_cast<__half*>(y), gamma, beta, rows, C, 1e-5f, S(stream));
+  MUDG_API_END
+}
+
+MUDG_EXPORT int mudg_test_ln_stats(const void* x, void* mean_rstd, int64_t rows, int C, void* stream) {
+  MUDG_API_BEGIN
+  ln_stats(static_cast<const __half*>(x), static_cast<float2*>(mean_rstd), rows, C, 1e-5f, S(stream));
+  MUDG_API_END
+}
+
+MUDG_EXPORT int mudg_test_ln_fold(void* W, const float* gamma, const float* beta, const float* bias, float* c1, float* c2,
+                                  int N, int K, void* stream) {
+  MUDG_API_BEGIN
+  ln_fold(static_cast<__half*>(W), gamma, beta, bias, c1, c2, N, K, S(stream));
+  MUDG_API_END
+}
+
+}  // extern "C"

@@ -167,8 +167,10 @@ class Engine:
                                      cur_stream()))
 
     def unet_forward(self, x: torch.Tensor, t: torch.Tensor, c_label: torch.Tensor, fs: torch.Tensor,
-                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """x [N, Cin, T, h, w] fp32; t/c_label/fs [N] int64; returns [N, Cout, T, h, w] fp16."""
+                     out: Optional[torch.Tensor] = None, dup: int = 1) -> torch.Tensor:
+        """x [N, Cin, T, h, w] fp32; t/c_label/fs [N] int64; returns [N, Cout, T, h, w] fp16.
+        dup > 1 (mudg_unet_forward_shared): the caller promises that x / t / c_label / fs are N / dup distinct samples
+        tiled dup times (a classifier-free-guidance batch: only the context rows differ)."""
         N, C, T, h, w = x.shape
         assert C == self.in_channels, (C, self.in_channels)
         x = x.detach().float().contiguous()
@@ -177,7 +179,13 @@ class Engine:
         fs = fs.to(device=x.device, dtype=torch.long).contiguous()
         if out is None:
             out = torch.empty((N, self.out_channels, T, h, w), device=x.device, dtype=torch.float16)
-        check(lib().mudg_unet_forward(self._h, ptr(x), ptr(t), ptr(c_label), ptr(fs), N, T, h, w, ptr(out), cur_stream()))
+        if dup > 1:
+            if N % dup:
+                raise MudgError(f"unet_forward: batch {N} is not a multiple of dup={dup}")
+            check(lib().mudg_unet_forward_shared(self._h, ptr(x), ptr(t), ptr(c_label), ptr(fs), N, int(dup), T, h, w, ptr(out),
+                                                 cur_stream()))
+        else:
+            check(lib().mudg_unet_forward(self._h, ptr(x), ptr(t), ptr(c_label), ptr(fs), N, T, h, w, ptr(out), cur_stream()))
         return out
 
     def vae_decode(self, z: torch.Tensor) -> torch.Tensor:

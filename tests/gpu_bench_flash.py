@@ -3,10 +3,10 @@ import ctypes, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from mudg_b200._lib import lib, check, ptr, cur_stream   # noqa: E402
+from mudg_b200._lib import test_lib, check, ptr, cur_stream   # noqa: E402
 
 def main():
-    L = lib()
+    L = test_lib()
     for name, F, Nq, heads in (("L0 9216x5", 32, 9216, 5), ("L1 2304x10", 32, 2304, 10), ("L2 576x20", 32, 576, 20)):
         C = heads * 64
         qkv = torch.randn(F, Nq, 3 * C, device="cuda").half()

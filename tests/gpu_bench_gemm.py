@@ -7,7 +7,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from mudg_b200._lib import lib, check, ptr, cur_stream   # noqa: E402
+from mudg_b200._lib import test_lib, check, ptr, cur_stream   # noqa: E402
 
 # (name, B, T, H, W, Cin, N, mode, res, geglu)
 SHAPES = [
@@ -37,8 +37,8 @@ SHAPES = [
 
 def main():
     dev = "cuda"
-    L = lib()
-    backends = [(0, "v2")] if os.environ.get("BENCH_V2_ONLY") else [(2, "v1"), (0, "v2")]
+    L = test_lib()
+    backends = [(0, "tc")]
     print(f"{'shape':28s} " + " ".join(f"{n:>8s}us {n:>6s}TF" for _, n in backends))
     only = sys.argv[1] if len(sys.argv) > 1 else None
     for name, B, T, H, W, Cin, N, mode, res, geglu in SHAPES:
@@ -56,7 +56,7 @@ def main():
         for backend, bn in backends:
             def run():
                 check(L.mudg_test_tapgemm(ptr(A), B, T, H, W, Cin, mode, ptr(Wt), N, ptr(D), ptr(R), ptr(bias), None,
-                                          ctypes.c_int(1), ctypes.c_int(0), ctypes.c_float(1.0), int(geglu), backend, cur_stream()))
+                                          ctypes.c_int(1), ctypes.c_int(0), ctypes.c_float(1.0), int(geglu), None, None, backend, cur_stream()))
             for _ in range(3):
                 run()
             torch.cuda.synchronize()

@@ -3,7 +3,7 @@ import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from mudg_b200._lib import lib, check, ptr, cur_stream   # noqa: E402
+from mudg_b200._lib import test_lib, check, ptr, cur_stream   # noqa: E402
 
 NAMES = {0: "SS N128 one D", 1: "SS N128 two D", 2: "SS N256 one D", 3: "SS N64 one D", 4: "SS N64 four D",
          5: "TS N64 MN-B one D", 6: "TS N64 MN-B two D", 7: "TS N64 MN-B four D", 8: "SS N128 four D",
@@ -11,7 +11,7 @@ NAMES = {0: "SS N128 one D", 1: "SS N128 two D", 2: "SS N256 one D", 3: "SS N64 
 
 
 def main():
-    L = lib()
+    L = test_lib()
     ctas = 148
     out = torch.zeros(ctas, 2, dtype=torch.int64, device="cuda")
     for mode in (0, 1):

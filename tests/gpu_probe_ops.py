@@ -41,10 +41,10 @@ def report(name, label, out, ref):
 def run_case(name):
     import torch
     import torch.nn.functional as Fn
-    from mudg_b200._lib import lib, check, ptr, cur_stream
+    from mudg_b200._lib import test_lib, check, ptr, cur_stream
     torch.manual_seed(0)
     dev = "cuda"
-    L = lib()
+    L = test_lib()
     f32 = ctypes.c_float
     if name.startswith("flash_self"):
         F, Nq, heads = {"flash_self_small": (2, 256, 1), "flash_self_l1": (3, 2304, 10), "flash_self_ragged": (2, 200, 2)}[name]

@@ -3,11 +3,11 @@ import ctypes, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from mudg_b200._lib import lib, check, ptr, cur_stream   # noqa: E402
+from mudg_b200._lib import test_lib, check, ptr, cur_stream   # noqa: E402
 
 
 def main():
-    L = lib()
+    L = test_lib()
     F, Nq, heads = 2, 9216, 5
     C = heads * 64
     qkv = torch.randn(F, Nq, 3 * C, device="cuda").half()

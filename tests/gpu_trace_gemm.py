@@ -3,14 +3,14 @@ import ctypes, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from mudg_b200._lib import lib, check, ptr, cur_stream   # noqa: E402
+from mudg_b200._lib import test_lib, check, ptr, cur_stream   # noqa: E402
 
 SHAPES = {"res320": (294912, 320, 320, 1, 0), "qkv": (294912, 320, 960, 0, 0), "geglu": (294912, 320, 2560, 0, 1),
           "res1280": (294912, 1280, 320, 1, 0)}
 
 
 def main():
-    L = lib()
+    L = test_lib()
     for name in (sys.argv[1:] or list(SHAPES)):
         M, Cin, N, res, geglu = SHAPES[name]
         A = torch.randn(1, 1, 1, M, Cin, device="cuda").half()
@@ -21,7 +21,7 @@ def main():
         bias = torch.randn(N, device="cuda")
         def run():
             check(L.mudg_test_tapgemm(ptr(A), 1, 1, 1, M, Cin, 0, ptr(Wt), N, ptr(D), ptr(R), ptr(bias), None,
-                                      ctypes.c_int(1), ctypes.c_int(0), ctypes.c_float(1.0), int(geglu), 0, cur_stream()))
+                                      ctypes.c_int(1), ctypes.c_int(0), ctypes.c_float(1.0), int(geglu), None, None, 0, cur_stream()))
         run(); torch.cuda.synchronize()
         tr = torch.zeros(4, 64, 8, dtype=torch.int64, device="cuda")
         check(L.mudg_test_gemm_trace(ptr(tr)))

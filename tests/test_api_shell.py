@@ -151,6 +151,26 @@ def test_c_abi_exports_every_declared_symbol():
     assert lib.mudg_last_error() is not None
 
 
+def test_test_hooks_live_only_in_the_test_library():
+    """libmudg_sm100_test.so (include/mudg_test.h) carries the single-kernel hooks, checkers and knobs; the product
+    library exports none of them and reads no tuning switch from the environment."""
+    from mudg_b200._lib import LIB_PATH, TEST_LIB_PATH
+    if not (os.path.exists(LIB_PATH) and os.path.exists(TEST_LIB_PATH)):
+        from mudg_b200.build import build
+        build()
+    header = open(os.path.join(ROOT, "include", "mudg_test.h")).read()
+    declared = set(re.findall(r"MUDG_EXPORT[^;(]*?\b(mudg_\w+)\s*\(", header))
+    assert {"mudg_test_tapgemm", "mudg_test_flash", "mudg_test_set_knob", "mudg_test_last_gemm_path"} <= declared
+    prod, test = ctypes.CDLL(LIB_PATH), ctypes.CDLL(TEST_LIB_PATH)
+    for name in declared:
+        assert hasattr(test, name), name
+        assert not hasattr(prod, name), name
+    assert hasattr(test, "mudg_unet_forward")        # the test library is a superset of the product ABI
+    blob = open(LIB_PATH, "rb").read()
+    for env in (b"MUDG_GEMM_PAIR", b"MUDG_FORCE_SIMT", b"MUDG_GEMM_V1", b"MUDG_GEMM_DBG", b"MUDG_FLASH_V1", b"MUDG_FLASH_POLY"):
+        assert env not in blob, env
+
+
 def test_unchanged_reference_driver_imports_against_the_dropin_packages():
     """B1: with this repo first and a reference checkout later on sys.path, the UNCHANGED driver module
     (virtual_render/virtual_pose_render.py) imports, and its sampler / config / post-decode symbols are this repo's,

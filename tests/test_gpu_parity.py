@@ -27,11 +27,23 @@ def engine():
     return eng
 
 
-@pytest.mark.parametrize("case", ["lin_small", "lin_k320", "lin_geglu", "conv3x3", "conv3x3_l0", "conv3x3_odd", "tconv",
-                                  "tconv_l0", "cin16", "lin_persist", "lin_n960", "lin_n64", "geglu_big", "conv_emb"])
+def _gemm_cases():
+    import gpu_probe_gemm as P
+    return list(P.CASES)
+
+
+@pytest.mark.parametrize("case", _gemm_cases())
 def test_tapgemm(case):
+    """Every tap-GEMM variant (single-CTA tc2, CTA-pair tc3 with each compile-time epilogue, GEGLU, folded LayerNorm)
+    against fp32 torch, at the BASELINE level-0 shapes for the pair kernel; the launch must really take the expected
+    kernel (mudg_test_last_gemm_path), so a dispatch change cannot silently leave the pair path untested."""
     import gpu_probe_gemm as P
     out = P.run_case(case)
+    path, want = out.pop("_path")
+    if want is not None:
+        assert (path & 255) == (want & 255), (case, "kernel", path & 255, "expected", want & 255)
+        if want >> 8:
+            assert (path >> 8) == (want >> 8), (case, "epilogue variant", (path >> 8) - 1, "expected", (want >> 8) - 1)
     for label, (err, nans) in out.items():
         assert nans == 0 and err < 0.02, (case, label, err, nans)
 
