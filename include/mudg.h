@@ -122,10 +122,12 @@ MUDG_EXPORT size_t mudg_workspace_bytes(MudgCtx* ctx, int N, int T, int h, int w
 /* Kernels launched by this context since creation (bench.py's gpu_launches). */
 MUDG_EXPORT int64_t mudg_launch_count(MudgCtx* ctx);
 
-/* Per-launch CUDA-event timing of the tcgen05 GEMM kernel on its launching stream (bench.py roofline leg):
- * enable, run, then read {sum of launch durations in ms, sum of algorithmic FLOPs, launches}; read() synchronises. */
-MUDG_EXPORT int mudg_profile_gemm(int enable);
-MUDG_EXPORT int mudg_profile_gemm_read(double* ms_total, double* flops_total, int64_t* launches);
+/* Per-launch profiler (bench.py's roofline leg): while enabled, every kernel family of the path is bracketed by a
+ * CUDA-event pair on its launching stream (forwards run eagerly instead of replaying their CUDA graph).
+ * mudg_profile_report(NULL, 0) synchronises, builds the report and returns its size; a second call with a buffer copies
+ * it out.  CSV rows: family,shape,launches,ms,flops,bytes (algorithmic FLOPs / HBM bytes of the launches, summed). */
+MUDG_EXPORT int mudg_profile(int enable);
+MUDG_EXPORT size_t mudg_profile_report(char* buf, size_t cap);
 
 #ifdef __cplusplus
 }

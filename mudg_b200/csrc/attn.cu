@@ -50,7 +50,7 @@ constexpr float F2_LAZY = 8.0f;
       p.trace[((role) * 96 + (blk)) * 8 + (ev)] = clock64();                                            \
   } while (0)
 
-template <int NSEG, bool F2_POLY>
+template <int NSEG, int F2_POLY>
 __global__ void __launch_bounds__(F2_THREADS, 1)
 flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmO,
               const __grid_constant__ CUtensorMap tmK0, const __grid_constant__ CUtensorMap tmV0,
@@ -266,9 +266,11 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
               // (optional) every 4th exponential on the FMA pipe (polynomial), the rest on the MUFU unit
-              const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c][i]), p.scale_log2, -m_used));
               const float a1 = fmaf(__uint_as_float(sr[c][i + 1]), p.scale_log2, -m_used);
-              const float p1 = ((i & 2) && F2_POLY) ? ex2_poly(a1) : ex2_approx(a1);
+              // F2_POLY: 0 all on the MUFU, 1 every 4th / 2 every 2nd / 3 three of four exponentials on the FMA pipe
+              const float a0 = fmaf(__uint_as_float(sr[c][i]), p.scale_log2, -m_used);
+              const float p0 = (F2_POLY == 3 && (i & 2)) ? ex2_poly(a0) : ex2_approx(a0);
+              const float p1 = ((F2_POLY == 1 && (i & 2)) || F2_POLY >= 2) ? ex2_poly(a1) : ex2_approx(a1);
               l4[(i >> 1) & 3] += p0 + p1;
               sr[c][i >> 1] = pack_half2(p0, p1);
               // early hand-over of the MUFU turn: the partner group may start its exponentials when 3/4 (or 1/2) of
@@ -708,18 +710,22 @@ void flash_attention(const FlashArgs& a, cudaStream_t st) {
   }
   static bool attr = false;
   if (!attr) {
-    MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
-    MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
-    MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
+    MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
+    MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
+    MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
+    MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
+    MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
     attr = true;
   }
   // Polynomial exp2 offload (FA4 trick).  Measured on B200 (tests/gpu_bench_flash.py): 5.49 ms vs 4.99 ms without it at
   // 9216 tokens -- the exponent phase is latency-bound at this occupancy, so it stays off (knob flash_poly).
-  const bool poly = knobs().flash_poly != 0;
+  const int poly = a.nseg == 1 ? knobs().flash_poly : 0;
   dim3 grid((a.Nq + 255) / 256, a.heads, a.F);
-  if (a.nseg == 1 && poly) flash2_kernel<1, true><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
-  else if (a.nseg == 1) flash2_kernel<1, false><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
-  else flash2_kernel<2, false><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
+  if (a.nseg == 2) flash2_kernel<2, 0><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
+  else if (poly == 1) flash2_kernel<1, 1><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
+  else if (poly == 2) flash2_kernel<1, 2><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
+  else if (poly == 3) flash2_kernel<1, 3><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
+  else flash2_kernel<1, 0><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
   MUDG_CUDA(cudaGetLastError());
 }
 

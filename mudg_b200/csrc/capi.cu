@@ -1,5 +1,6 @@
 // extern "C" surface of libmudg_sm100.so (see include/mudg.h).  No exceptions cross the ABI.
 #include <cmath>
+#include <cstring>
 
 #include "model.h"
 #include "mudg.h"
@@ -131,6 +132,7 @@ MUDG_EXPORT int mudg_ddim_step(const void* x, const void* v_cond, const void* v_
   a.sqrt_a_prev = sqrtf(a_prev);
   a.dir_coef = sqrtf(1.f - a_prev - sigma_t * sigma_t);
   a.sigma = sigma_t;
+  ProfScope ps(PF_SAMPLER, 0.0, (double)B * (double)n * (v_uncond ? 20.0 : 18.0), S(stream), "ddim_step");
   ddim_step(a, S(stream));
   MUDG_API_END
 }
@@ -157,6 +159,7 @@ MUDG_EXPORT int mudg_postdecode(const void* frames, int dtype, int B, int T, int
   MUDG_REQUIRE(frames && modes && rgb_u8, "null argument");
   MUDG_REQUIRE(dtype == MUDG_F32 || dtype == MUDG_F16 || dtype == MUDG_U8, "postdecode: dtype %d", dtype);
   MUDG_REQUIRE(H >= 1 && W >= 1, "postdecode: empty frame");
+  ProfScope ps(PF_POST, 0.0, (double)B * T * H * W * 3.0 * ((dtype == MUDG_F32 ? 4.0 : dtype == MUDG_F16 ? 2.0 : 1.0) + 1.0), S(stream), "postdecode");
   postdecode(frames, dtype, static_cast<uint8_t*>(rgb_u8), static_cast<float*>(depth_f32),
              static_cast<uint8_t*>(class_u8), B, T, (int64_t)H * W, modes, S(stream));
   MUDG_API_END
@@ -189,16 +192,27 @@ MUDG_EXPORT size_t mudg_workspace_bytes(MudgCtx* ctx, int N, int T, int h, int w
 
 MUDG_EXPORT int64_t mudg_launch_count(MudgCtx* ctx) { return ctx ? ctx->model.launches : 0; }
 
-MUDG_EXPORT int mudg_profile_gemm(int enable) {
+MUDG_EXPORT int mudg_profile(int enable) {
   MUDG_API_BEGIN
-  gemm_profile_enable(enable != 0);
+  prof_enable(enable != 0);
   MUDG_API_END
 }
 
-MUDG_EXPORT int mudg_profile_gemm_read(double* ms_total, double* flops_total, int64_t* launches) {
-  MUDG_API_BEGIN
-  gemm_profile_read(ms_total, flops_total, launches);
-  MUDG_API_END
+MUDG_EXPORT size_t mudg_profile_report(char* buf, size_t cap) {
+  try {
+    static thread_local std::string last;
+    if (buf == nullptr || cap == 0) {      // first call: build the report, return the size needed (incl. the NUL)
+      last = prof_report();
+      return last.size() + 1;
+    }
+    const size_t n = last.size() < cap - 1 ? last.size() : cap - 1;
+    memcpy(buf, last.data(), n);
+    buf[n] = 0;
+    return n + 1;
+  } catch (const std::exception& e) {
+    mudg::set_last_error(e.what());
+    return 0;
+  }
 }
 
 }  // extern "C"

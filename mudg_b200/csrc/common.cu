@@ -25,6 +25,65 @@ Knobs& knobs() {
   return k;
 }
 
+// ---------------------------------------------------------------- profiler
+namespace {
+struct ProfRec {
+  int fam;
+  double flops, bytes;
+  std::string shape;
+};
+struct Profiler {
+  bool on = false, paused = false;
+  std::vector<cudaEvent_t> ev;      // pairs, grow-only
+  std::vector<ProfRec> rec;
+} g_profiler;
+const char* kFamNames[PF_COUNT] = {"gemm", "flash_self", "flash_cross", "temporal_attn", "groupnorm", "ln_stats", "layernorm",
+                                   "transpose_v", "concat", "resample", "layout", "embed", "softmax", "generic_conv",
+                                   "ddim_step", "postdecode"};
+}  // namespace
+
+void prof_enable(bool on) {
+  g_profiler.on = on;
+  g_profiler.rec.clear();
+}
+bool prof_active() { return g_profiler.on && !g_profiler.paused; }
+void prof_pause(bool paused) { g_profiler.paused = paused; }
+
+ProfScope::ProfScope(int fam, double flops, double bytes, cudaStream_t s, const char* shape) : st(s) {
+  Profiler& p = g_profiler;
+  if (!p.on || p.paused) return;
+  idx = (int)p.rec.size();
+  while (p.ev.size() < 2 * (size_t)(idx + 1)) {
+    cudaEvent_t e;
+    MUDG_CUDA(cudaEventCreate(&e));
+    p.ev.push_back(e);
+  }
+  p.rec.push_back(ProfRec{fam, flops, bytes, shape ? shape : ""});
+  cudaEventRecord(p.ev[2 * idx], st);
+}
+ProfScope::~ProfScope() {
+  if (idx >= 0) cudaEventRecord(g_profiler.ev[2 * idx + 1], st);
+}
+
+std::string prof_report() {
+  Profiler& p = g_profiler;
+  MUDG_CUDA(cudaDeviceSynchronize());
+  struct Agg { double n = 0, ms = 0, flops = 0, bytes = 0; };
+  std::map<std::pair<int, std::string>, Agg> agg;
+  for (size_t i = 0; i < p.rec.size(); i++) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, p.ev[2 * i], p.ev[2 * i + 1]) != cudaSuccess) continue;
+    Agg& a = agg[{p.rec[i].fam, p.rec[i].shape}];
+    a.n += 1; a.ms += t; a.flops += p.rec[i].flops; a.bytes += p.rec[i].bytes;
+  }
+  std::string out = "family,shape,launches,ms,flops,bytes\n";
+  for (auto& kv : agg)
+    out += fmt("%s,%s,%.0f,%.5f,%.6e,%.6e\n", kFamNames[kv.first.first], kv.first.second.c_str(), kv.second.n, kv.second.ms,
+               kv.second.flops, kv.second.bytes);
+  p.rec.clear();
+  return out;
+}
+
 int sm_count() {
   static int n = 0;
   if (!n) {

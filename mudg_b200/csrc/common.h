@@ -95,4 +95,23 @@ struct Knobs {
 };
 Knobs& knobs();
 
+// ---------------------------------------------------------------- per-launch profiler (bench.py's roofline leg)
+// When enabled every kernel family of the path is bracketed by a CUDA-event pair on its launching stream (forwards then
+// run eagerly, not as a graph replay); the report gives launches, device time, algorithmic FLOPs and algorithmic HBM
+// bytes per (family, shape).  Off (the default) it costs one branch per launch.
+enum ProfFam {
+  PF_GEMM = 0, PF_FLASH_SELF, PF_FLASH_CROSS, PF_TATTN, PF_GN, PF_LN_STATS, PF_LAYERNORM, PF_TRANSPOSE_V, PF_CONCAT,
+  PF_RESAMPLE, PF_LAYOUT, PF_EMBED, PF_SOFTMAX, PF_GENERIC_CONV, PF_SAMPLER, PF_POST, PF_COUNT
+};
+void prof_enable(bool on);
+bool prof_active();
+void prof_pause(bool paused);  // planning passes walk the graph without launching: nothing may be booked
+std::string prof_report();     // CSV: family,shape,launches,ms,flops,bytes  (synchronises the device, clears the records)
+struct ProfScope {
+  ProfScope(int fam, double flops, double bytes, cudaStream_t st, const char* shape = "");
+  ~ProfScope();
+  int idx = -1;
+  cudaStream_t st = nullptr;
+};
+
 }  // namespace mudg

@@ -58,9 +58,6 @@ void tapgemm_generic(const TapGemmGeneric& g, cudaStream_t st);
 void tapgemm(const TapGemm& g, cudaStream_t st);
 
 void gemm_set_trace(long long* buf);   // debug: clock64 time line of the pair GEMM's CTA 0 ([4][64][8] int64), null = off
-void gemm_profile_enable(bool on);
-bool gemm_profile_active();
-void gemm_profile_read(double* ms_total, double* flops_total, int64_t* launches);
 
 void set_taps_3x3(int8_t taps[9][3]);      // (dw,dh) in {-1,0,1}^2, tap index = kh*3+kw (weight layout [N][kh][kw][Cin])
 void set_taps_t3(int8_t taps[9][3]);       // dt in {-1,0,1}

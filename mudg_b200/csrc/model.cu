@@ -425,6 +425,7 @@ Act Model::group_norm(const Act& x, const std::string& p, float eps, bool silu, 
     const Vec& g = ws_->V(p + ".weight");
     const Vec& b = ws_->V(p + ".bias");
     MUDG_REQUIRE(g.n == x.C, "GroupNorm %s: %d channels vs activation %d", p.c_str(), g.n, x.C);
+    ProfScope ps(PF_GN, 0.0, 4.0 * (double)x.numel(), st_, fmt("%lldx%d", (long long)x.rows(), x.C).c_str());   // ideal: 1 read + 1 write
     gn_scale_shift(x.p, S, rps, x.C, g.p, b.p, eps, sums, scale, scale + (size_t)S * x.C, st_);
     gn_apply(x.p, y.p, scale, scale + (size_t)S * x.C, x.rows(), x.C, rps, silu, st_);
     launches += 4;
@@ -437,6 +438,7 @@ Act Model::group_norm(const Act& x, const std::string& p, float eps, bool silu, 
 Act Model::layer_norm(const Act& x, const std::string& p) {
   Act y = alloc(x.B, x.T, x.H, x.W, x.C);
   if (live()) {
+    ProfScope ps(PF_LAYERNORM, 0.0, 4.0 * (double)x.numel(), st_, fmt("%lldx%d", (long long)x.rows(), x.C).c_str());
     layernorm(x.p, y.p, ws_->V(p + ".weight").p, ws_->V(p + ".bias").p, x.rows(), x.C, 1e-5f, st_);
     launches++;
   }
@@ -447,6 +449,7 @@ Act Model::layer_norm(const Act& x, const std::string& p) {
 float2* Model::layer_norm_stats(const Act& x) {
   float2* st = static_cast<float2*>(alloc_bytes(sizeof(float2) * (size_t)x.rows()));
   if (live()) {
+    ProfScope ps(PF_LN_STATS, 0.0, 2.0 * (double)x.numel() + 8.0 * (double)x.rows(), st_, fmt("%lldx%d", (long long)x.rows(), x.C).c_str());
     ln_stats(x.p, st, x.rows(), x.C, 1e-5f, st_);
     launches++;
   }
@@ -523,6 +526,7 @@ Act Model::concat(const Act& a, const Act& b) {
   Act y = alloc(a.B, a.T, a.H, a.W, a.C + b.C);
   if (live()) {
     MUDG_REQUIRE(a.rows() % b.rows() == 0, "concat: %lld rows vs %lld", (long long)a.rows(), (long long)b.rows());
+    ProfScope ps(PF_CONCAT, 0.0, 4.0 * (double)y.numel(), st_, fmt("%lldx%d", (long long)y.rows(), y.C).c_str());
     concat_channels(a.p, a.C, b.p, b.C, y.p, a.rows(), b.rows(), st_);
     launches++;
   }
@@ -534,6 +538,7 @@ Act Model::tile_batch(const Act& x, int n) {
   Act y = alloc(n, x.T, x.H, x.W, x.C);
   if (live()) {
     MUDG_REQUIRE(n % x.B == 0, "tile_batch: %d samples from %d", n, x.B);
+    ProfScope ps(PF_CONCAT, 0.0, 2.0 * (double)(x.numel() + y.numel()), st_, "tile_batch");
     for (int i = 0; i < n / x.B; i++)
       MUDG_CUDA(cudaMemcpyAsync(y.p + (size_t)i * x.numel(), x.p, x.bytes(), cudaMemcpyDeviceToDevice, st_));
     launches += n / x.B;
@@ -544,6 +549,7 @@ Act Model::tile_batch(const Act& x, int n) {
 Act Model::upsample(const Act& x) {
   Act y = alloc(x.B, x.T, 2 * x.H, 2 * x.W, x.C);
   if (live()) {
+    ProfScope ps(PF_RESAMPLE, 0.0, 2.0 * (double)(x.numel() + y.numel()), st_, "upsample2x");
     upsample2x(x.p, y.p, x.B * x.T, x.H, x.W, x.C, st_);
     launches++;
   }
@@ -556,6 +562,7 @@ Act Model::downsample(const Act& x, const std::string& p, int pad) {
   const int Ho = (x.H + pad - 2) / 2 + 1, Wo = (x.W + pad - 2) / 2 + 1;
   Act col = alloc(x.B, x.T, Ho, Wo, 9 * x.C);
   if (live()) {
+    ProfScope ps(PF_RESAMPLE, 0.0, 2.0 * (double)(x.numel() + col.numel()), st_, "im2col_s2");
     im2col_s2(x.p, col.p, x.B * x.T, x.H, x.W, x.C, pad, st_);
     launches++;
   }
@@ -618,7 +625,13 @@ Act Model::spatial_transformer(const Act& xin, const Layer& l) {   // attention.
   const int F1 = xin.B * xin.T;
   __half* vt = static_cast<__half*>(alloc_bytes(sizeof(__half) * (size_t)F1 * C * hw_pad));   // V^T [F][C][HW]
   if (live()) {
-    transpose_v(qkv.p + 2 * C, 3 * C, HW, F1, l.heads, vt, hw_pad, st_);
+    {
+      ProfScope ps(PF_TRANSPOSE_V, 0.0, 4.0 * (double)F1 * HW * C, st_, fmt("%dx%dx%d", F1, HW, C).c_str());
+      transpose_v(qkv.p + 2 * C, 3 * C, HW, F1, l.heads, vt, hw_pad, st_);
+    }
+    // algorithmic: 4 * Nq * Nkv * 64 FLOPs per (frame, head); Q, K, V read and O written once
+    ProfScope ps(PF_FLASH_SELF, 4.0 * (double)HW * HW * 64.0 * l.heads * F1, 8.0 * (double)F1 * HW * C, st_,
+                 fmt("%dx%dx%d", F1, HW, l.heads).c_str());
     FlashArgs fa;
     fa.Q = qkv.p; fa.q_pitch = 3 * C; fa.O = a1.p; fa.o_pitch = C; fa.F = F1; fa.Nq = HW; fa.heads = l.heads;
     fa.nseg = 1;
@@ -655,6 +668,9 @@ Act Model::spatial_transformer(const Act& xin, const Layer& l) {   // attention.
     MUDG_REQUIRE(it != kv_.end() && ctx_N_ == N_ && ctx_T_ == T_real_, "mudg_set_context(N=%d, T=%d) must precede the forward",
                  N_, T_real_);
     const KvCache& kc = it->second;
+    const int lkv = ucfg_.text_context_len + (ctx_per_frame_ ? 16 : ctx_Limg_);
+    ProfScope ps(PF_FLASH_CROSS, 4.0 * (double)HW * lkv * 64.0 * l.heads * F, 4.0 * (double)F * HW * C, st_,
+                 fmt("%dx%dx%dx%d", F, HW, lkv, l.heads).c_str());
     FlashArgs fa;
     fa.Q = q.p; fa.q_pitch = C; fa.O = a2.p; fa.o_pitch = C; fa.F = F; fa.Nq = HW; fa.heads = l.heads;
     fa.nseg = 2;
@@ -694,6 +710,8 @@ Act Model::temporal_transformer(const Act& xin, const Layer& l) {   // attention
     release_bytes(sk);
     Act a = alloc(xin.B, xin.T, xin.H, xin.W, l.inner);
     if (live()) {
+      ProfScope ps(PF_TATTN, 4.0 * (double)xin.T * xin.T * 64.0 * l.heads * xin.B * HW, 8.0 * (double)a.numel(), st_,
+                   fmt("%dx%dx%dx%d", xin.B, xin.T, HW, l.heads).c_str());
       temporal_attention(qkv.p, a.p, xin.B, xin.T, HW, l.heads, 0.125f, st_);
       launches++;
     }
@@ -738,6 +756,7 @@ void Model::compute_embeddings(const int64_t* t, const int64_t* label, const int
   float* emb = static_cast<float*>(alloc_bytes(sizeof(float) * N * ted));
   const char* names[3] = {"time_embed", "class_embed", "fps_embedding"};
   const int64_t* idx[3] = {t, label, fs};
+  ProfScope ps_embed(PF_EMBED, 0.0, 0.0, st_, "time/class/fps MLPs + emb_layers");
   if (live()) {
     for (int i = 0; i < 3; i++) {
       const std::string n = names[i];
@@ -781,6 +800,7 @@ void Model::unet_body(const void* x, const int64_t* t, const int64_t* label, con
   const int B0 = (dup > 1 && has_spatial) ? N / dup : N;
   Act xin = alloc(B0, T, h, w, cpad);
   if (live()) {
+    ProfScope ps(PF_LAYOUT, 0.0, 0.0, st_, "to_channels_last");
     to_channels_last(x, true, xin.p, B0, ucfg_.in_channels, (int64_t)T * h * w, cpad, st_);
     launches++;
   }
@@ -819,6 +839,7 @@ void Model::unet_body(const void* x, const int64_t* t, const int64_t* label, con
     g.Wt = wt.w; g.N = wt.O; g.D = y64.p;
     g.bias = ws_->V("out.2.bias.pad").p;
     tapgemm(g, st_);
+    ProfScope ps(PF_LAYOUT, 0.0, 0.0, st_, "from_channels_last");
     from_channels_last(y64.p, static_cast<__half*>(out), N, ucfg_.out_channels, (int64_t)T * h * w, 64, st_);
     launches += 2;
   }
@@ -904,11 +925,13 @@ size_t Model::plan_unet(int N, int dup, int T, int h, int w) {
   MUDG_REQUIRE(unet_ready_, "weights not finalized");
   arena_.planning = true;
   planning_ = true;
+  prof_pause(true);
   arena_.reset_high();
   unet_body(nullptr, nullptr, nullptr, nullptr, N, dup, T, h, w, nullptr);
   const size_t need = arena_.high_water();
   arena_.planning = false;
   planning_ = false;
+  prof_pause(false);
   arena_.reset();
   return need;
 }
@@ -928,7 +951,7 @@ void Model::unet_forward(const void* x, const int64_t* t, const int64_t* label, 
     const char* e = getenv("MUDG_GRAPH");
     return !(e && e[0] == '0');
   }();
-  if (!graphs_on || gemm_profile_active()) {
+  if (!graphs_on || prof_active()) {
     unet_body(x, t, label, fs, N, dup, T, h, w, out);
     return;
   }
@@ -1040,6 +1063,7 @@ Act Model::vae_attn(const Act& x, const std::string& p) {
   release(q);
   release(k);
   if (live()) {
+    ProfScope ps(PF_SOFTMAX, 0.0, 4.0 * (double)M * M, st_, "vae_attn");
     softmax_rows(s.p, M, M, st_);
     launches++;
   }
@@ -1113,11 +1137,13 @@ size_t Model::plan_vae(int h, int w) {
   MUDG_REQUIRE(vae_ready_, "VAE weights not finalized");
   arena_.planning = true;
   planning_ = true;
+  prof_pause(true);
   arena_.reset_high();
   vae_body(nullptr, h, w, nullptr);
   const size_t need = arena_.high_water();
   arena_.planning = false;
   planning_ = false;
+  prof_pause(false);
   arena_.reset();
   return need;
 }
@@ -1191,7 +1217,9 @@ void Model::vae_encode(const void* x, int F, int H, int W, void* moments, cudaSt
   auto it = vae_plans_.find(key);
   if (it == vae_plans_.end()) {
     arena_.planning = true; planning_ = true; arena_.reset_high();
+    prof_pause(true);
     vae_encode_body(nullptr, H, W, nullptr);
+    prof_pause(false);
     const size_t need = arena_.high_water();
     arena_.planning = false; planning_ = false; arena_.reset();
     it = vae_plans_.emplace(key, need).first;
@@ -1296,7 +1324,9 @@ void Model::resampler_forward(const void* x, int dtype, int B, int L, void* out,
   MUDG_REQUIRE(B >= 1 && L >= 1, "Resampler: empty input");
   arena_.planning = true; planning_ = true;
   arena_.reset_high();
+  prof_pause(true);
   resampler_body(nullptr, dtype, B, L, nullptr);
+  prof_pause(false);
   const size_t need = arena_.high_water();
   arena_.planning = false; planning_ = false;
   arena_.reset();

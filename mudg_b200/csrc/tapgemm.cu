@@ -16,6 +16,7 @@
 #include <array>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <string>
 #include <vector>
@@ -1142,87 +1143,38 @@ void tapgemm_generic(const TapGemmGeneric& g, cudaStream_t st) {
   MUDG_CUDA(cudaGetLastError());
 }
 
-// ---- optional per-launch timing of the tcgen05 GEMM (bench.py's roofline leg): CUDA events on the launching stream
-namespace {
-struct GemmProfiler {
-  bool on = false;
-  std::vector<cudaEvent_t> ev;      // pairs
-  std::vector<double> flops;
-  std::vector<std::string> shape;   // "rows,N,taps,Cin,geglu,res,ln" of each timed launch (per-shape dump)
-  size_t used = 0;
-} g_prof;
-}  // namespace
-
-bool gemm_profile_active() { return g_prof.on; }
-
-void gemm_profile_enable(bool on) {
-  g_prof.on = on;
-  g_prof.used = 0;
-  g_prof.flops.clear();
-  g_prof.shape.clear();
-}
-
-void gemm_profile_read(double* ms_total, double* flops_total, int64_t* launches) {
-  MUDG_CUDA(cudaDeviceSynchronize());
-  double ms = 0, fl = 0;
-  // MUDG_GEMM_PROFILE_DUMP=<file>: per-shape table (launches, total ms, total FLOP) of the timed launches
-  const char* dump = getenv("MUDG_GEMM_PROFILE_DUMP");
-  std::map<std::string, std::array<double, 3>> by_shape;
-  for (size_t i = 0; i < g_prof.used; i++) {
-    float t = 0.f;
-    MUDG_CUDA(cudaEventElapsedTime(&t, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]));
-    ms += t;
-    fl += g_prof.flops[i];
-    if (dump) {
-      auto& a = by_shape[g_prof.shape[i]];
-      a[0] += 1; a[1] += t; a[2] += g_prof.flops[i];
-    }
-  }
-  if (dump && !by_shape.empty()) {
-    if (FILE* f = fopen(dump, "w")) {
-      fprintf(f, "rows,N,taps,Cin,geglu,res,ln,launches,ms_total,tflop_total,tflops\n");
-      for (auto& kv : by_shape)
-        fprintf(f, "%s,%.0f,%.4f,%.4f,%.1f\n", kv.first.c_str(), kv.second[0], kv.second[1], kv.second[2] / 1e12,
-                kv.second[1] > 0 ? kv.second[2] / 1e9 / kv.second[1] : 0.0);
-      fclose(f);
-    }
-  }
-  *ms_total = ms;
-  *flops_total = fl;
-  *launches = (int64_t)g_prof.used;
-  g_prof.used = 0;
-  g_prof.flops.clear();
-  g_prof.shape.clear();
-}
-
+// The product entry.  With the profiler on (bench.py's roofline leg) the launch is bracketed by a CUDA-event pair and
+// booked with its algorithmic work: 2 * rows * N * taps * Cin FLOPs (padding and tile overhang not counted) and the HBM
+// bytes an ideal kernel moves (A once, W once, D once, residual once, LayerNorm statistics).
 void tapgemm(const TapGemm& g, cudaStream_t st) {
-  MUDG_REQUIRE(tapgemm_tc_eligible(g), "layer not eligible for the tcgen05 path (Cin=%d N=%d, 16 B alignment): there is no "
-               "CUDA-core fallback in the product library", g.Cin, g.N);
-  {
-    if (g_prof.on) {
-      if (g_prof.ev.size() < 2 * (g_prof.used + 1)) {
-        cudaEvent_t a, b;
-        MUDG_CUDA(cudaEventCreate(&a));
-        MUDG_CUDA(cudaEventCreate(&b));
-        g_prof.ev.push_back(a);
-        g_prof.ev.push_back(b);
-      }
-      MUDG_CUDA(cudaEventRecord(g_prof.ev[2 * g_prof.used], st));
-      tapgemm_tc2(g, st);
-      MUDG_CUDA(cudaEventRecord(g_prof.ev[2 * g_prof.used + 1], st));
-      // algorithmic work of the layer: 2 * rows * N * (taps * Cin), padding and tile overhang not counted
-      g_prof.flops.push_back(2.0 * (double)g.B * g.T * g.H * g.W * (double)g.N * (double)g.ntaps * g.Cin);
-      {
-        char buf[96];
-        snprintf(buf, sizeof buf, "%lld,%d,%d,%d,%d,%d,%d", (long long)g.B * g.T * g.H * g.W, g.N, g.ntaps, g.Cin,
-                 g.geglu ? 1 : 0, g.R ? 1 : 0, g.ln_stats ? 1 : 0);
-        g_prof.shape.push_back(buf);
-      }
-      g_prof.used++;
-    } else {
-      tapgemm_tc2(g, st);
-    }
+  if (!tapgemm_tc_eligible(g)) {
+    // Irregular plain GEMMs (N not a multiple of 64: the VAE mid-block attention at latent sizes whose token count is
+    // not, e.g. 8 x 12) run on the arbitrary-stride CUDA-core kernel like the other irregular layers; anything with a
+    // fused epilogue must be eligible.
+    MUDG_REQUIRE(!g.geglu && g.ln_stats == nullptr && g.bias2 == nullptr && g.R == nullptr,
+                 "layer not eligible for the tcgen05 path (Cin=%d N=%d, 16 B alignment) and it needs a fused epilogue", g.Cin, g.N);
+    TapGemmGeneric q;
+    q.A = g.A; q.B = g.B; q.T = g.T; q.H = g.H; q.W = g.W; q.Cin = g.Cin;
+    q.a_sc = 1; q.a_sw = g.Cin; q.a_sh = (int64_t)g.W * g.Cin; q.a_st = q.a_sh * g.H; q.a_sb = q.a_st * g.T;
+    q.ntaps = g.ntaps;
+    memcpy(q.taps, g.taps, sizeof(q.taps));
+    q.Wt = g.Wt; q.CinW = g.Cin; q.N = g.N;
+    q.D = g.D; q.d_sn = 1; q.d_sw = g.N; q.d_sh = (int64_t)g.W * g.N; q.d_st = q.d_sh * g.H; q.d_sb = q.d_st * g.T;
+    q.bias = g.bias; q.alpha = g.alpha;
+    ProfScope ps(PF_GENERIC_CONV, 0.0, 0.0, st, "irregular gemm");
+    return tapgemm_generic(q, st);
   }
+  if (!prof_active()) return tapgemm_tc2(g, st);
+  const double rows = (double)g.B * g.T * g.H * g.W;
+  const int n_out = g.geglu ? g.N / 2 : g.N;
+  const double flops = 2.0 * rows * (double)g.N * (double)g.ntaps * g.Cin;
+  const double bytes = 2.0 * (rows * g.Cin + (double)g.N * g.ntaps * g.Cin + rows * n_out * (g.R ? 2.0 : 1.0)) +
+                       (g.ln_stats ? 8.0 * rows : 0.0);
+  char buf[96];
+  snprintf(buf, sizeof buf, "%.0fx%dx%dx%d:g%dr%dl%db%d", rows, g.N, g.ntaps, g.Cin, g.geglu ? 1 : 0, g.R ? 1 : 0,
+           g.ln_stats ? 1 : 0, g.bias2 ? 1 : 0);
+  ProfScope ps(PF_GEMM, flops, bytes, st, buf);
+  tapgemm_tc2(g, st);
 }
 
 }  // namespace mudg

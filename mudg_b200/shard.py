@@ -79,6 +79,28 @@ def gather_frames(frames_u8: torch.Tensor, ids: torch.Tensor):
     return f[order], i[order]
 
 
+def gather_frames_to(frames_u8: torch.Tensor, ids: torch.Tensor, dst: int = 0):
+    """Gather the SAME number of clips from every rank onto rank `dst` only (the rank that writes the files,
+    virtual_pose_render.py:243-274): returns (frames [n_total, ...], ids [n_total]) sorted by id on `dst`, (None, None)
+    elsewhere.  One NCCL gather per call; 28 MB per 16x576x1024 uint8 clip and rank."""
+    rank, ws = world()
+    if ws == 1:
+        order = torch.argsort(ids)
+        return frames_u8[order], ids[order]
+    frames_u8, ids = frames_u8.contiguous(), ids.contiguous()
+    if rank == dst:
+        fb = [torch.empty_like(frames_u8) for _ in range(ws)]
+        ib = [torch.empty_like(ids) for _ in range(ws)]
+        dist.gather(frames_u8, fb, dst=dst)
+        dist.gather(ids, ib, dst=dst)
+        f, i = torch.cat(fb), torch.cat(ib)
+        order = torch.argsort(i)
+        return f[order], i[order]
+    dist.gather(frames_u8, None, dst=dst)
+    dist.gather(ids, None, dst=dst)
+    return None, None
+
+
 def max_over_ranks(value: float, device=None) -> float:
     rank, ws = world()
     if ws == 1:

@@ -342,17 +342,31 @@ def _mlp(sd: SD, p: str, x: Tensor) -> Tensor:
     return _lin(sd, f"{p}.2", F.silu(_lin(sd, f"{p}.0", x)))
 
 
+# Scores of one attention call are materialised like the reference's einsum path does; above this many bytes the batch
+# (frames) is processed in slices -- same arithmetic per (frame, head), only the peak memory changes (a full-size level-0
+# call is 32 frames x 5 heads x 9216^2 fp32 = 54 GB at once).  tests/test_oracle_golden.py pins sliced == unsliced.
+ATTN_SCORE_BYTES_MAX = 2 << 30
+
+
 def _softmax_attend(q: Tensor, k: Tensor, v: Tensor, heads: int) -> Tensor:
     """einsum path of CrossAttention.forward (attention.py:101-125): (b h) n d split, scale d^-0.5."""
     b, n, c = q.shape
     d = c // heads
 
     def split(t):
-        return t.reshape(b, t.shape[1], heads, d).permute(0, 2, 1, 3)
-    qh, kh, vh = split(q), split(k), split(v)
-    sim = torch.matmul(qh, kh.transpose(-1, -2)) * (d ** -0.5)
-    o = torch.matmul(sim.softmax(dim=-1), vh)
-    return o.permute(0, 2, 1, 3).reshape(b, n, c)
+        return t.reshape(t.shape[0], t.shape[1], heads, d).permute(0, 2, 1, 3)
+
+    def attend(qq, kk, vv):
+        qh, kh, vh = split(qq), split(kk), split(vv)
+        sim = torch.matmul(qh, kh.transpose(-1, -2)) * (d ** -0.5)
+        o = torch.matmul(sim.softmax(dim=-1), vh)
+        return o.permute(0, 2, 1, 3).reshape(qq.shape[0], n, c)
+
+    per_frame = heads * n * k.shape[1] * q.element_size()
+    step = max(1, int(ATTN_SCORE_BYTES_MAX // max(1, per_frame)))
+    if step >= b:
+        return attend(q, k, v)
+    return torch.cat([attend(q[i:i + step], k[i:i + step], v[i:i + step]) for i in range(0, b, step)], dim=0)
 
 
 def cross_attention(sd: SD, p: str, x: Tensor, heads: int, context: Optional[Tensor],
@@ -686,8 +700,8 @@ def ddim_step(tab: DiffusionTables, sch: DDIMSchedule, index: int, x: Tensor, v_
     pred_x0 = sa * x - s1 * v                              # ddpm3d.py:239-245
     if dynamic_rescale:
         pred_x0 = pred_x0 * (sch.scale_arr_prev[index] / sch.scale_arr[index])
-    a_prev = torch.tensor(sch.alphas_prev[index], dtype=torch.float32)
-    sigma = torch.tensor(sch.sigmas[index], dtype=torch.float32)
+    a_prev = torch.tensor(sch.alphas_prev[index], dtype=torch.float32, device=x.device)
+    sigma = torch.tensor(sch.sigmas[index], dtype=torch.float32, device=x.device)
     dir_xt = (1.0 - a_prev - sigma ** 2).sqrt() * e_t
     x_prev = a_prev.sqrt() * pred_x0 + dir_xt + sigma * noise
     return x_prev, pred_x0
@@ -698,10 +712,16 @@ def ddim_sample(unet_sd: SD, ucfg: UNetCfg, tab: DiffusionTables, *, S: int, sha
                 context: Tensor, uc_context: Optional[Tensor], class_label: Tensor, fs: Tensor,
                 cfg_scale: float = 1.0, guidance_rescale: float = 0.0, eta: float = 1.0,
                 spacing: str = "uniform_trailing", generator: Optional[torch.Generator] = None,
-                noises: Optional[List[Tensor]] = None, device="cpu") -> Tensor:
+                noises: Optional[List[Tensor]] = None, device="cpu", unet_fn=None) -> Tensor:
     """DDIMSampler.sample/ddim_sampling (ddim.py:60-203) with the hybrid DiffusionWrapper
     (ddpm3d.py:1320-1324).  RNG order: x_T first, then one draw per step (App. D #10);
-    `noises` (len S+1) overrides the generator so CUDA/CPU runs can share draws."""
+    `noises` (len S+1) overrides the generator so CUDA/CPU runs can share draws.
+    `unet_fn(xc, ts, class_label, context, fs)` replaces the oracle's own UNet forward (used to put the reference's
+    autocast-fp16 UNetModel into the same loop when calibrating tolerances)."""
+    if unet_fn is not None:
+        unet_forward = lambda _sd, _cfg, xc, ts, lab, ctx, fs_: unet_fn(xc, ts, lab, ctx, fs_).float()   # noqa: E731
+    else:
+        unet_forward = globals()["unet_forward"]
     sch = make_ddim_schedule(tab, S, spacing, eta)
     draw = (lambda i: noises[i]) if noises is not None else (lambda i: torch.randn(shape, generator=generator, device=device))
     x = draw(0)

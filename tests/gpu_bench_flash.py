@@ -7,6 +7,16 @@ from mudg_b200._lib import test_lib, check, ptr, cur_stream   # noqa: E402
 
 def main():
     L = test_lib()
+    sweep = [(0, 3)] if len(sys.argv) < 2 else [(p_, s_) for p_ in (0, 1, 2, 3) for s_ in (0, 3, 4)]
+    for poly, stagger in sweep:
+        check(L.mudg_test_set_knob(b"flash_poly", poly))
+        check(L.mudg_test_set_knob(b"flash_stagger", stagger))
+        print(f"-- flash_poly={poly} flash_stagger={stagger}", flush=True)
+        bench(L)
+    check(L.mudg_test_set_knob(b"reset", 0))
+
+
+def bench(L):
     for name, F, Nq, heads in (("L0 9216x5", 32, 9216, 5), ("L1 2304x10", 32, 2304, 10), ("L2 576x20", 32, 576, 20)):
         C = heads * 64
         qkv = torch.randn(F, Nq, 3 * C, device="cuda").half()

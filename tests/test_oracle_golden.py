@@ -47,6 +47,14 @@ def test_unet_forward_matches_reference(golden_dir):
     y2 = O.unet_forward(sd, cfg, t("x"), t("ts"), t("lab"), t("ctx2"), t("fs"))
     assert float((y2 - t("y2")).abs().max()) < 5e-5
     assert float(t("y").abs().max()) > 0.5          # non-vacuous (zero-inits were re-randomised)
+    # the memory-bounded (frame-sliced) attention used for the full-size GPU parity runs is the same arithmetic
+    old = O.ATTN_SCORE_BYTES_MAX
+    try:
+        O.ATTN_SCORE_BYTES_MAX = 1 << 16          # forces slices of one / a few frames at every level
+        y3 = O.unet_forward(sd, cfg, t("x"), t("ts"), t("lab"), t("ctx"), t("fs"))
+    finally:
+        O.ATTN_SCORE_BYTES_MAX = old
+    assert float((y3 - t("y")).abs().max()) < 5e-5
 
 
 def test_vae_decode_matches_reference(golden_dir):

@@ -41,6 +41,13 @@ def _worker(rank, ws, port, q):
         ids = torch.tensor([it["id"] for it in mine], dtype=torch.long)
         allf, alli = shard.gather_frames(frames, ids)
         tmax = shard.max_over_ranks(1.0 + rank)
+        # gather to the writing rank only (bench.py's e2e leg): equal clip counts per call
+        one = shard.frames_to_uint8(fake_clip({"id": 100 + rank}))[None]
+        gf, gi = shard.gather_frames_to(one, torch.tensor([100 + rank]), dst=0)
+        if rank == 0:
+            assert gi.tolist() == [100, 101] and torch.equal(gf[1], shard.frames_to_uint8(fake_clip({"id": 101})))
+        else:
+            assert gf is None and gi is None
         q.put((rank, sorted(trajs), [(it["traj"], it["window"]) for it in mine], allf.clone(), alli.clone(), tmax))
     finally:
         dist.destroy_process_group()
