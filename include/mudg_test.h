@@ -17,7 +17,10 @@ extern "C" {
  * gn_fuse; "reset" restores the shipped defaults */
 MUDG_EXPORT int mudg_test_set_knob(const char* name, int value);
 /* kernel the last tap-GEMM launch took: 2 = tapgemm_tc2<1>, 3 = tapgemm_tc2<2>, 4 = tapgemm_tc3; | (EPI + 1) << 8 */
-MUDG_EXPORT int mudg_test_last_gemm_path(void);
+MUDG_EXPORT int mudg_test_last_gemm_path(void);   /* bit 16: GroupNorm statistics were accumulated by the epilogue */
+/* request GroupNorm statistics of the output from the NEXT mudg_test_tapgemm(backend 0) call: sums [S][32][2] fp64,
+ * pre-zeroed; sample = (b*T + t) / gn_div */
+MUDG_EXPORT int mudg_test_next_gemm_gn(void* sums_f64, int gn_div);
 
 /* backend 0 = product dispatch (tcgen05), 1 = CUDA-core checker.  mode 0 linear, 1 conv 3x3, 2 temporal conv (3,1,1).
  * ln_stats ([rows] float2 mean,rstd) / ln_c1 ([N]): folded-LayerNorm epilogue (bias then carries W beta + bias), or NULL */
@@ -29,12 +32,18 @@ MUDG_EXPORT int mudg_test_flash(const void* Q, int q_pitch, void* O, int o_pitch
                                 const void* K0, const void* V0, int pitch0, int len0, int nbatch0, int div0,
                                 const void* K1, const void* V1, int pitch1, int len1, int nbatch1, int div1, float scale,
                                 int backend, void* stream);
+/* cross-attention to a per-frame context through the merged 96-key kernel (xattn.cu): Q / O [F][Nq][heads*64],
+ * text_kv [F/T][77][2*heads*64], img_kv [F][16][2*heads*64] (K in the first half of a row, V in the second) */
+MUDG_EXPORT int mudg_test_xattn(const void* Q, void* O, int F, int T, int Nq, int heads, const void* text_kv, const void* img_kv,
+                                float scale, void* stream);
 /* debug: device buffer [3][96][8] int64 receiving the clock64 time line of CTA 0 of the next flash launches (NULL = off) */
 MUDG_EXPORT int mudg_test_flash_trace(void* buf);
 /* debug: device buffer [4][64][8] int64 receiving the clock64 time line of CTA 0 of the next pair-GEMM launches */
 MUDG_EXPORT int mudg_test_gemm_trace(void* buf);
 /* debug: tcgen05.mma issue-rate probe; out = device int64 [ctas][2] (clocks until issued, until complete) */
 MUDG_EXPORT int mudg_test_mma_probe(int variant, int reps, int ctas, int mode, void* out, void* stream);
+/* debug: special-function-unit throughput (mode 0 ex2.f32, 1 ex2.f16x2, 2 rcp, 3 FFMA reference); 8 ops per thread and iteration */
+MUDG_EXPORT int mudg_test_mufu_probe(int mode, int iters, int ctas, int threads, void* out, void* clocks, void* stream);
 MUDG_EXPORT int mudg_test_temporal_attn(const void* qkv, void* out, int B, int T, int HW, int heads, float scale,
                                         void* stream);
 MUDG_EXPORT int mudg_test_groupnorm(const void* x, void* y, int S, int64_t rows_per_sample, int C, const float* gamma,

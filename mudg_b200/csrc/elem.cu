@@ -100,44 +100,52 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, double* __restrict
   }
 }
 
-// scale/shift per (sample, channel): y = x * scale + shift  ==  (x - mean) * rstd * gamma + beta
-__global__ void gn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift,
-                                   int S, int C, int cpg, double count, float eps) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= S * C) return;
-  const int s = i / C, c = i % C, g = c / cpg;
-  const double mean = sums[(s * 32 + g) * 2] / count;
-  double var = sums[(s * 32 + g) * 2 + 1] / count - mean * mean;
-  if (var < 0) var = 0;
-  const float rstd = rsqrtf((float)var + eps);
-  const float sc = gamma[c] * rstd;
-  scale[i] = sc;
-  shift[i] = beta[c] - (float)mean * sc;
-}
-
-__global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ scale,
-                                const float* __restrict__ shift, int64_t total_vecs, int C, int64_t rows_per_sample,
-                                int act) {
+// Normalise + affine (+ SiLU) in ONE pass straight from the (sum, sum of squares) pairs: block = (C/8) x rows_per_iter
+// threads working on rows [row_begin, row_end) of sample blockIdx.y.  A thread owns one 8-channel vector column, so its
+// 8 scales / shifts  y = x * scale + shift == (x - mean) * rstd * gamma + beta  are computed once and stay in registers;
+// the row loop keeps 4 independent 128-bit loads in flight per thread.
+__global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y, const double* __restrict__ sums,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int64_t R, int C, int cpg,
+                                double count, float eps, int rows_per_block, int act) {
   const int vecs = C >> 3;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vecs; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / vecs;
-    const int v = i - row * vecs;
-    const int s = row / rows_per_sample;
-    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(x) + i);
+  const int v = threadIdx.x % vecs, r0 = threadIdx.x / vecs, rstep = blockDim.x / vecs;
+  const int s = blockIdx.y;
+  if (r0 >= rstep) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int c = v * 8 + i, g = c / cpg;
+    const double mean = sums[((int64_t)s * 32 + g) * 2] / count;
+    double var = sums[((int64_t)s * 32 + g) * 2 + 1] / count - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = rsqrtf((float)var + eps);
+    sc[i] = __ldg(gamma + c) * rstd;
+    sh[i] = __ldg(beta + c) - (float)mean * sc[i];
+  }
+  const int64_t row_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t row_end = min(R, row_begin + rows_per_block);
+  const __half* xb = x + ((int64_t)s * R) * C + v * 8;
+  __half* yb = y + ((int64_t)s * R) * C + v * 8;
+  auto one = [&](const uint4& raw) {
     float f[8];
     unpack8(raw, f);
-    const float4* sc = reinterpret_cast<const float4*>(scale + (int64_t)s * C + v * 8);
-    const float4* sh = reinterpret_cast<const float4*>(shift + (int64_t)s * C + v * 8);
-    const float4 s0 = __ldg(sc), s1 = __ldg(sc + 1), h0 = __ldg(sh), h1 = __ldg(sh + 1);
-    f[0] = f[0] * s0.x + h0.x; f[1] = f[1] * s0.y + h0.y; f[2] = f[2] * s0.z + h0.z; f[3] = f[3] * s0.w + h0.w;
-    f[4] = f[4] * s1.x + h1.x; f[5] = f[5] * s1.y + h1.y; f[6] = f[6] * s1.z + h1.z; f[7] = f[7] * s1.w + h1.w;
+#pragma unroll
+    for (int i = 0; i < 8; i++) f[i] = fmaf(f[i], sc[i], sh[i]);
     if (act) {
 #pragma unroll
-      for (int k = 0; k < 8; k++) f[k] = silu(f[k]);
+      for (int i = 0; i < 8; i++) f[i] = silu(f[i]);
     }
-    reinterpret_cast<uint4*>(y)[i] = pack8(f);
+    return pack8(f);
+  };
+  int64_t r = row_begin + r0;
+  for (; r + 3 * (int64_t)rstep < row_end; r += 4 * (int64_t)rstep) {
+    uint4 raw[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) raw[u] = __ldg(reinterpret_cast<const uint4*>(xb + (r + u * (int64_t)rstep) * C));
+#pragma unroll
+    for (int u = 0; u < 4; u++) *reinterpret_cast<uint4*>(yb + (r + u * (int64_t)rstep) * C) = one(raw[u]);
   }
+  for (; r < row_end; r += rstep) *reinterpret_cast<uint4*>(yb + r * C) = one(__ldg(reinterpret_cast<const uint4*>(xb + r * C)));
 }
 
 // ---------------------------------------------------------------- LayerNorm (warp per row, row kept in registers)
@@ -206,6 +214,61 @@ __global__ void concat_kernel(const uint4* __restrict__ a, const uint4* __restri
     const int v = i - r * vo;
     const int64_t rb = r < rows_b ? r : r % rows_b;
     o[i] = v < va ? __ldg(a + r * va + v) : __ldg(b + rb * vb + (v - va));
+  }
+}
+
+// Channel concat of one sample's rows [row_begin, row_end) that also accumulates the GroupNorm statistics of its output
+// (the ResBlock that consumes a skip concat starts with a GroupNorm): same thread layout and accumulation discipline as
+// gn_stats_kernel -- a thread owns one 8-channel vector column of the OUTPUT, fp32 partials, fp64 atomics.
+__global__ void concat_stats_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ o,
+                                    double* __restrict__ sums, int64_t R, int64_t rows_b, int va, int vb, int cpg,
+                                    int rows_per_block) {
+  __shared__ double acc[32][2];
+  const int vecs = va + vb;
+  const int v = threadIdx.x % vecs, r0 = threadIdx.x / vecs, rstep = blockDim.x / vecs;
+  if (threadIdx.x < 64) (&acc[0][0])[threadIdx.x] = 0.0;
+  __syncthreads();
+  const int s = blockIdx.y;
+  const int64_t row_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t row_end = min(R, row_begin + rows_per_block);
+  float sm[8], sq[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) sm[i] = sq[i] = 0.f;
+  if (r0 < rstep) {
+    for (int64_t r = row_begin + r0; r < row_end; r += rstep) {
+      const int64_t gr = (int64_t)s * R + r;                 // global row
+      const int64_t rb = gr < rows_b ? gr : gr % rows_b;
+      const uint4 raw = v < va ? __ldg(a + gr * va + v) : __ldg(b + rb * vb + (v - va));
+      o[gr * vecs + v] = raw;
+      float f[8];
+      unpack8(raw, f);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        sm[i] += f[i];
+        sq[i] += f[i] * f[i];
+      }
+    }
+    int g_cur = (v * 8) / cpg;
+    float x = 0.f, y = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int g = (v * 8 + i) / cpg;
+      if (g != g_cur) {
+        atomicAdd(&acc[g_cur][0], (double)x);
+        atomicAdd(&acc[g_cur][1], (double)y);
+        x = y = 0.f;
+        g_cur = g;
+      }
+      x += sm[i];
+      y += sq[i];
+    }
+    atomicAdd(&acc[g_cur][0], (double)x);
+    atomicAdd(&acc[g_cur][1], (double)y);
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int g = threadIdx.x >> 1, k = threadIdx.x & 1;
+    atomicAdd(&sums[((int64_t)s * 32 + g) * 2 + k], acc[g][k]);
   }
 }
 
@@ -376,43 +439,72 @@ __global__ void from_channels_last_kernel(const __half* __restrict__ y, __half* 
   }
 }
 
-// LayerNorm statistics only (the normalisation itself is folded into the consuming GEMM): warp per row -> (mean, rstd)
-template <int MAXV>
-__global__ void ln_stats_kernel(const __half* __restrict__ x, float2* __restrict__ out, int64_t rows, int C, float eps) {
+// LayerNorm statistics only (the normalisation itself is folded into the consuming GEMM): (mean, rstd) per row.
+// A warp handles ROWS consecutive rows at once: all their 128-bit loads are issued before the first shuffle, so a warp
+// keeps ROWS x MAXV x 16 B in flight per lane instead of one row's worth (the one-row version ran at 39 % of the HBM
+// roofline inside the clip: too few bytes in flight per SM while the warps sat in their dependent shuffle chains), and
+// the ROWS butterfly reductions interleave.
+template <int MAXV, int ROWS>
+__global__ void __launch_bounds__(256) ln_stats_kernel(const __half* __restrict__ x, float2* __restrict__ out, int64_t rows, int C, float eps) {
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS;
+  if (row0 >= rows) return;
   const int vecs = C >> 3;
-  float f[MAXV][8];
-  float sum = 0.f;
-  const uint4* xr = reinterpret_cast<const uint4*>(x + row * C);
+  uint4 raw[ROWS][MAXV];
 #pragma unroll
-  for (int k = 0; k < MAXV; k++) {
-    const int v = lane + 32 * k;
-    if (v < vecs) {
-      unpack8(__ldg(xr + v), f[k]);
+  for (int r = 0; r < ROWS; r++) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (row0 + r) * C);
 #pragma unroll
-      for (int i = 0; i < 8; i++) sum += f[k][i];
+    for (int k = 0; k < MAXV; k++) {
+      const int v = lane + 32 * k;
+      raw[r][k] = (v < vecs && row0 + r < rows) ? __ldg(xr + v) : make_uint4(0, 0, 0, 0);
+    }
+  }
+  float sum[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; r++) {
+    sum[r] = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; k++) {
+      float f[8];
+      unpack8(raw[r][k], f);
+#pragma unroll
+      for (int i = 0; i < 8; i++) sum[r] += f[i];
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum / C;
-  float var = 0.f;
+  for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-  for (int k = 0; k < MAXV; k++) {
-    const int v = lane + 32 * k;
-    if (v < vecs) {
+    for (int r = 0; r < ROWS; r++) sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], o);
+  float var[ROWS], mean[ROWS];
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const float d = f[k][i] - mean;
-        var += d * d;
+  for (int r = 0; r < ROWS; r++) {
+    mean[r] = sum[r] / C;
+    var[r] = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; k++) {
+      if (lane + 32 * k < vecs) {          // padding vectors must not contribute (0 - mean)^2
+        float f[8];
+        unpack8(raw[r][k], f);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const float d = f[i] - mean[r];
+          var[r] += d * d;
+        }
       }
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
-  if (lane == 0) out[row] = make_float2(mean, rsqrtf(var / C + eps));
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) var[r] += __shfl_xor_sync(0xffffffffu, var[r], o);
+  if (lane < ROWS && row0 + lane < rows) {
+    float m = mean[0], v = var[0];
+#pragma unroll
+    for (int r = 1; r < ROWS; r++)
+      if (lane == r) { m = mean[r]; v = var[r]; }
+    out[row0 + lane] = make_float2(m, rsqrtf(v / C + eps));
+  }
 }
 
 // Fold a LayerNorm's affine part into the Linear that consumes it: W[n][k] *= gamma[k] (re-rounded to fp16, in place),
@@ -448,30 +540,33 @@ inline int grid_for(int64_t work, int threads) {
 }  // namespace
 
 // ================================================================ launchers
-void gn_scale_shift(const __half* x, int S, int64_t rows_per_sample, int C, const float* gamma, const float* beta,
-                    float eps, double* sums_ws, float* scale, float* shift, cudaStream_t st) {
-  MUDG_REQUIRE(C % 32 == 0 && C % 8 == 0, "GroupNorm needs C %% 32 == 0 (C=%d)", C);
-  const int cpg = C / 32, vecs = C / 8;
-  MUDG_REQUIRE(vecs <= 1024, "C too large for gn_stats");
-  MUDG_CUDA(cudaMemsetAsync(sums_ws, 0, sizeof(double) * S * 64, st));
+static void gn_geometry(int S, int64_t rows_per_sample, int C, int& threads, int& rpb, int& chunks) {
+  const int vecs = C / 8;
   const int rpi = std::max(1, 256 / vecs);
-  const int threads = vecs * rpi;
+  threads = vecs * rpi;
   // enough blocks to fill the machine, at least 32 rows per block
-  int64_t want_blocks = std::max<int64_t>(1, (int64_t)sm_count() * 8 / std::max(1, S));
-  int64_t rpb = std::max<int64_t>(32, (rows_per_sample + want_blocks - 1) / want_blocks);
-  rpb = (rpb + rpi - 1) / rpi * rpi;
-  const int chunks = (int)((rows_per_sample + rpb - 1) / rpb);
-  gn_stats_kernel<<<dim3(chunks, S), threads, 0, st>>>(x, sums_ws, rows_per_sample, C, cpg, (int)rpb);
-  MUDG_CUDA(cudaGetLastError());
-  gn_finalize_kernel<<<(S * C + 255) / 256, 256, 0, st>>>(sums_ws, gamma, beta, scale, shift, S, C, cpg,
-                                                         (double)rows_per_sample * cpg, eps);
+  const int64_t want_blocks = std::max<int64_t>(1, (int64_t)sm_count() * 8 / std::max(1, S));
+  int64_t r = std::max<int64_t>(32, (rows_per_sample + want_blocks - 1) / want_blocks);
+  r = (r + rpi - 1) / rpi * rpi;
+  rpb = (int)r;
+  chunks = (int)((rows_per_sample + r - 1) / r);
+}
+
+void gn_stats(const __half* x, int S, int64_t rows_per_sample, int C, double* sums /*[S*64], zeroed*/, cudaStream_t st) {
+  MUDG_REQUIRE(C % 32 == 0 && C / 8 <= 1024, "GroupNorm needs C %% 32 == 0 and C <= 8192 (C=%d)", C);
+  int threads, rpb, chunks;
+  gn_geometry(S, rows_per_sample, C, threads, rpb, chunks);
+  gn_stats_kernel<<<dim3(chunks, S), threads, 0, st>>>(x, sums, rows_per_sample, C, C / 32, rpb);
   MUDG_CUDA(cudaGetLastError());
 }
 
-void gn_apply(const __half* x, __half* y, const float* scale, const float* shift, int64_t rows, int C,
-              int64_t rows_per_sample, bool silu_act, cudaStream_t st) {
-  const int64_t total = rows * (C / 8);
-  gn_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, y, scale, shift, total, C, rows_per_sample, silu_act ? 1 : 0);
+void gn_apply(const __half* x, __half* y, const double* sums, int S, int64_t rows_per_sample, int C, const float* gamma,
+              const float* beta, float eps, bool silu_act, cudaStream_t st) {
+  MUDG_REQUIRE(C % 32 == 0 && C / 8 <= 1024, "GroupNorm needs C %% 32 == 0 and C <= 8192 (C=%d)", C);
+  int threads, rpb, chunks;
+  gn_geometry(S, rows_per_sample, C, threads, rpb, chunks);
+  gn_apply_kernel<<<dim3(chunks, S), threads, 0, st>>>(x, y, sums, gamma, beta, rows_per_sample, C, C / 32,
+                                                     (double)rows_per_sample * (C / 32), eps, rpb, silu_act ? 1 : 0);
   MUDG_CUDA(cudaGetLastError());
 }
 
@@ -493,6 +588,18 @@ void concat_channels(const __half* a, int Ca, const __half* b, int Cb, __half* o
   const int64_t total = rows * ((Ca + Cb) / 8);
   concat_kernel<<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b),
                                                       reinterpret_cast<uint4*>(out), rows, rows_b, Ca / 8, Cb / 8);
+  MUDG_CUDA(cudaGetLastError());
+}
+
+void concat_channels_stats(const __half* a, int Ca, const __half* b, int Cb, __half* out, int S, int64_t rows_per_sample,
+                           int64_t rows_b, double* sums, cudaStream_t st) {
+  const int C = Ca + Cb;
+  MUDG_REQUIRE(Ca % 8 == 0 && Cb % 8 == 0 && C % 32 == 0 && C / 8 <= 1024, "concat + GroupNorm statistics: channels %d + %d", Ca, Cb);
+  int threads, rpb, chunks;
+  gn_geometry(S, rows_per_sample, C, threads, rpb, chunks);
+  concat_stats_kernel<<<dim3(chunks, S), threads, 0, st>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b),
+                                                        reinterpret_cast<uint4*>(out), sums, rows_per_sample, rows_b, Ca / 8,
+                                                        Cb / 8, C / 32, rpb);
   MUDG_CUDA(cudaGetLastError());
 }
 
@@ -609,11 +716,11 @@ void from_channels_last(const __half* y, __half* out, int B, int C, int64_t R, i
 void ln_stats(const __half* x, float2* out, int64_t rows, int C, float eps, cudaStream_t st) {
   MUDG_REQUIRE(C % 8 == 0 && C <= 2560, "LayerNorm width %d unsupported", C);
   const int wpb = 8;
-  const int64_t blocks = (rows + wpb - 1) / wpb;
   const int vecs = C / 8;
-  if (vecs <= 64) ln_stats_kernel<2><<<(unsigned)blocks, wpb * 32, 0, st>>>(x, out, rows, C, eps);
-  else if (vecs <= 160) ln_stats_kernel<5><<<(unsigned)blocks, wpb * 32, 0, st>>>(x, out, rows, C, eps);
-  else ln_stats_kernel<10><<<(unsigned)blocks, wpb * 32, 0, st>>>(x, out, rows, C, eps);
+  auto blocks = [&](int rpw) { return (unsigned)((rows + (int64_t)wpb * rpw - 1) / ((int64_t)wpb * rpw)); };
+  if (vecs <= 64) ln_stats_kernel<2, 4><<<blocks(4), wpb * 32, 0, st>>>(x, out, rows, C, eps);
+  else if (vecs <= 160) ln_stats_kernel<5, 2><<<blocks(2), wpb * 32, 0, st>>>(x, out, rows, C, eps);
+  else ln_stats_kernel<10, 1><<<blocks(1), wpb * 32, 0, st>>>(x, out, rows, C, eps);
   MUDG_CUDA(cudaGetLastError());
 }
 

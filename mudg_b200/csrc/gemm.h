@@ -31,6 +31,12 @@ struct TapGemm {
   //   D = rstd[m] * (acc - mean[m] * ln_c1[n]) + bias[n]      with bias = W beta (+ the layer's own bias)
   const float2* ln_stats = nullptr;   // [rows] (mean, rstd)
   const float* ln_c1 = nullptr;       // [N] row sums of the gamma-scaled fp16 weight
+  // GroupNorm statistics of the OUTPUT for the norm that consumes it (32 groups over the n_out channels): REQUEST to
+  // accumulate (sum, sum of squares) per (sample, group) into gn_sums [S][32][2] fp64 (pre-zeroed) from the epilogue;
+  // sample = (b*T + t) / gn_div.  tapgemm() returns whether it did (only the CTA-pair kernel does, and only when a
+  // 128-pixel tile cannot straddle samples); otherwise the caller runs gn_stats on the output.
+  double* gn_sums = nullptr;
+  int gn_div = 1;
 };
 
 // generic-stride variant for the irregular layers (tiny Cin / tiny N, fp32 NCTHW in/out)
@@ -52,10 +58,11 @@ struct TapGemmGeneric {
 };
 
 bool tapgemm_tc_eligible(const TapGemm& g);
-void tapgemm_tc2(const TapGemm& g, cudaStream_t st);       // persistent single-CTA kernel, or the CTA-pair kernel for large problems
+bool tapgemm_tc2(const TapGemm& g, cudaStream_t st);       // persistent single-CTA kernel, or the CTA-pair kernel for large problems
 void tapgemm_generic(const TapGemmGeneric& g, cudaStream_t st);
-// The product entry: tcgen05 path (+ optional per-launch timing); throws when the layer is not eligible (no fallback).
-void tapgemm(const TapGemm& g, cudaStream_t st);
+// The product entry: tcgen05 path (+ optional per-launch timing).  Returns true when the GroupNorm statistics requested
+// through g.gn_sums were accumulated by the epilogue.
+bool tapgemm(const TapGemm& g, cudaStream_t st);
 
 void gemm_set_trace(long long* buf);   // debug: clock64 time line of the pair GEMM's CTA 0 ([4][64][8] int64), null = off
 

@@ -181,6 +181,8 @@ Model::~Model() {
     cudaFree(kv.second.img);
     cudaFree(kv.second.text_vt);
     cudaFree(kv.second.img_vt);
+    cudaFree(kv.second.kx);
+    cudaFree(kv.second.vtx);
   }
   cudaFree(ctx_text_stage_);
   cudaFree(ctx_img_stage_);
@@ -415,23 +417,44 @@ void* Model::alloc_bytes(size_t n) { return arena_.alloc(n); }
 void Model::release_bytes(void* p) { arena_.free(p); }
 
 // ================================================================ ops
-Act Model::group_norm(const Act& x, const std::string& p, float eps, bool silu, bool over_time) {
+// Statistics buffer of a GroupNorm whose input is about to be produced: [S][32][2] fp64, zeroed on the stream.
+void Model::gn_request(GnReq& r, int S) {
+  r.sums = static_cast<double*>(alloc_bytes(sizeof(double) * S * 64));
+  r.fused = false;
+  if (live()) {
+    MUDG_CUDA(cudaMemsetAsync(r.sums, 0, sizeof(double) * S * 64, st_));
+    launches++;
+  }
+}
+
+// GroupNorm (+ SiLU).  `pre`: statistics requested from the op that produced x (GnReq filled by conv3x3 / conv_t3); when
+// the producer's epilogue accumulated them (pre->fused) the norm is ONE pass over x, otherwise a statistics pass runs first.
+Act Model::group_norm(const Act& x, const std::string& p, float eps, bool silu, bool over_time, GnReq* pre) {
   const int S = over_time ? x.B : x.B * x.T;
   const int64_t rps = over_time ? (int64_t)x.T * x.H * x.W : (int64_t)x.H * x.W;
   Act y = alloc(x.B, x.T, x.H, x.W, x.C);
-  double* sums = static_cast<double*>(alloc_bytes(sizeof(double) * S * 64));
-  float* scale = static_cast<float*>(alloc_bytes(sizeof(float) * S * x.C * 2));
+  GnReq own;
+  if (pre == nullptr || pre->sums == nullptr) {
+    gn_request(own, S);
+    pre = &own;
+  } else {
+    MUDG_REQUIRE(pre->over_time == over_time, "GroupNorm %s: statistics were requested for the other sample partition", p.c_str());
+  }
   if (live()) {
     const Vec& g = ws_->V(p + ".weight");
     const Vec& b = ws_->V(p + ".bias");
     MUDG_REQUIRE(g.n == x.C, "GroupNorm %s: %d channels vs activation %d", p.c_str(), g.n, x.C);
-    ProfScope ps(PF_GN, 0.0, 4.0 * (double)x.numel(), st_, fmt("%lldx%d", (long long)x.rows(), x.C).c_str());   // ideal: 1 read + 1 write
-    gn_scale_shift(x.p, S, rps, x.C, g.p, b.p, eps, sums, scale, scale + (size_t)S * x.C, st_);
-    gn_apply(x.p, y.p, scale, scale + (size_t)S * x.C, x.rows(), x.C, rps, silu, st_);
-    launches += 4;
+    // ideal traffic: 1 read + 1 write of the activation
+    ProfScope ps(PF_GN, 0.0, 4.0 * (double)x.numel(), st_, fmt("%lldx%d%s", (long long)x.rows(), x.C, pre->fused ? ":fused" : "").c_str());
+    if (!pre->fused) {
+      gn_stats(x.p, S, rps, x.C, pre->sums, st_);
+      launches++;
+    }
+    gn_apply(x.p, y.p, pre->sums, S, rps, x.C, g.p, b.p, eps, silu, st_);
+    launches++;
   }
-  release_bytes(sums);
-  release_bytes(scale);
+  release_bytes(pre->sums);
+  pre->sums = nullptr;
   return y;
 }
 
@@ -485,9 +508,10 @@ Act Model::linear(const Act& x, const std::string& wkey, const std::string& bkey
   return y;
 }
 
-Act Model::conv3x3(const Act& x, const std::string& p, const Act* residual, const float* bias2) {
+Act Model::conv3x3(const Act& x, const std::string& p, const Act* residual, const float* bias2, GnReq* gn) {
   const Weight& w = ws_->W(p + ".weight");
   Act y = alloc(x.B, x.T, x.H, x.W, w.O);
+  if (gn) gn_request(*gn, gn->over_time ? x.B : x.B * x.T);
   if (live()) {
     MUDG_REQUIRE(w.taps == 9 && w.Ipad == x.C, "conv3x3 %s: weight [%d][%d][%d] vs activation C=%d", p.c_str(), w.O, w.taps,
                  w.Ipad, x.C);
@@ -498,15 +522,18 @@ Act Model::conv3x3(const Act& x, const std::string& p, const Act* residual, cons
     g.R = residual ? residual->p : nullptr;
     g.bias = ws_->V(p + ".bias").p;
     if (bias2) { g.bias2 = bias2; g.bias2_div = T_real_; g.nb2 = N_; }
-    tapgemm(g, st_);
+    if (gn) { g.gn_sums = gn->sums; g.gn_div = gn->over_time ? x.T : 1; }      // frames are flattened into the T dimension
+    const bool fused = tapgemm(g, st_);
+    if (gn) gn->fused = fused;
     launches++;
   }
   return y;
 }
 
-Act Model::conv_t3(const Act& x, const std::string& p, const Act* residual) {
+Act Model::conv_t3(const Act& x, const std::string& p, const Act* residual, GnReq* gn) {
   const Weight& w = ws_->W(p + ".weight");
   Act y = alloc(x.B, x.T, x.H, x.W, w.O);
+  if (gn) gn_request(*gn, gn->over_time ? x.B : x.B * x.T);
   if (live()) {
     MUDG_REQUIRE(w.taps == 3 && w.Ipad == x.C, "temporal conv %s: weight shape", p.c_str());
     TapGemm g;
@@ -515,19 +542,28 @@ Act Model::conv_t3(const Act& x, const std::string& p, const Act* residual) {
     g.Wt = w.w; g.N = w.O; g.D = y.p;
     g.R = residual ? residual->p : nullptr;
     g.bias = ws_->V(p + ".bias").p;
-    tapgemm(g, st_);
+    if (gn) { g.gn_sums = gn->sums; g.gn_div = gn->over_time ? x.T : 1; }
+    const bool fused = tapgemm(g, st_);
+    if (gn) gn->fused = fused;
     launches++;
   }
   return y;
 }
 
-Act Model::concat(const Act& a, const Act& b) {
-  // b may hold fewer samples than a (a skip tensor from the shared CFG prefix): its rows then repeat with period b.rows()
+Act Model::concat(const Act& a, const Act& b, GnReq* gn) {
+  // b may hold fewer samples than a (a skip tensor from the shared CFG prefix): its rows then repeat with period b.rows().
+  // gn: per-frame GroupNorm statistics of the result, accumulated in the same pass (the consumer is a ResBlock).
   Act y = alloc(a.B, a.T, a.H, a.W, a.C + b.C);
+  if (gn) gn_request(*gn, a.B * a.T);
   if (live()) {
     MUDG_REQUIRE(a.rows() % b.rows() == 0, "concat: %lld rows vs %lld", (long long)a.rows(), (long long)b.rows());
     ProfScope ps(PF_CONCAT, 0.0, 4.0 * (double)y.numel(), st_, fmt("%lldx%d", (long long)y.rows(), y.C).c_str());
-    concat_channels(a.p, a.C, b.p, b.C, y.p, a.rows(), b.rows(), st_);
+    if (gn && !gn->over_time && y.C % 32 == 0 && knobs().gn_fuse != 0) {
+      concat_channels_stats(a.p, a.C, b.p, b.C, y.p, a.B * a.T, (int64_t)a.H * a.W, b.rows(), gn->sums, st_);
+      gn->fused = true;
+    } else {
+      concat_channels(a.p, a.C, b.p, b.C, y.p, a.rows(), b.rows(), st_);
+    }
     launches++;
   }
   return y;
@@ -572,26 +608,34 @@ Act Model::downsample(const Act& x, const std::string& p, int pad) {
 }
 
 // ================================================================ UNet blocks
-Act Model::res_block(const Act& x, const Layer& l) {   // ResBlock._forward (openaimodel3d.py:210-236)
+// ResBlock._forward (openaimodel3d.py:210-236).  Every GroupNorm whose input comes out of a conv takes its statistics from
+// that conv's epilogue (GnReq): out_layers.0 <- in_layers.2, temporal conv1..4 <- out_layers.3 / conv1..3, and -- when
+// `out_gn` is given -- the norm of the SpatialTransformer that follows <- conv4.
+Act Model::res_block(const Act& x, const Layer& l, GnReq* out_gn, GnReq* in_gn) {
   const std::string& p = l.prefix;
-  Act a = group_norm(x, p + ".in_layers.0", 1e-5f, true, false);
-  Act h = conv3x3(a, p + ".in_layers.2", nullptr, emb_out_[l.res_index]);
+  Act a = group_norm(x, p + ".in_layers.0", 1e-5f, true, false, in_gn);
+  GnReq r1;
+  Act h = conv3x3(a, p + ".in_layers.2", nullptr, emb_out_[l.res_index], &r1);
   release(a);
-  Act a2 = group_norm(h, p + ".out_layers.0", 1e-5f, true, false);
+  Act a2 = group_norm(h, p + ".out_layers.0", 1e-5f, true, false, &r1);
   release(h);
   Act skip;
   const bool has_skip = l.cin != l.cout;
   if (has_skip) skip = linear(x, p + ".skip_connection.weight", p + ".skip_connection.bias", nullptr);
-  Act h2 = conv3x3(a2, p + ".out_layers.3", has_skip ? &skip : &x, nullptr);
+  GnReq rt;
+  rt.over_time = true;
+  Act h2 = conv3x3(a2, p + ".out_layers.3", has_skip ? &skip : &x, nullptr, &rt);
   release(a2);
   if (has_skip) release(skip);
   // TemporalConvBlock (openaimodel3d.py:272-279): GroupNorm statistics span (C/32, T, H, W)
   Act y = h2;
   for (int j = 1; j <= 4; j++) {
     const std::string q = p + ".temopral_conv.conv" + std::to_string(j);
-    Act n = group_norm(y, q + ".0", 1e-5f, true, true);
+    Act n = group_norm(y, q + ".0", 1e-5f, true, true, &rt);
     if (j > 1) release(y);
-    y = conv_t3(n, q + (j == 1 ? ".2" : ".3"), j == 4 ? &h2 : nullptr);
+    rt = GnReq{};
+    rt.over_time = true;
+    y = conv_t3(n, q + (j == 1 ? ".2" : ".3"), j == 4 ? &h2 : nullptr, j < 4 ? &rt : out_gn);
     release(n);
   }
   release(h2);
@@ -609,11 +653,11 @@ Act Model::transformer_block_tail(Act x, const std::string& tb) {
   return y;
 }
 
-Act Model::spatial_transformer(const Act& xin, const Layer& l) {   // attention.py:451-467, use_linear=True
+Act Model::spatial_transformer(const Act& xin, const Layer& l, GnReq* in_gn) {   // attention.py:451-467, use_linear=True
   const std::string& p = l.prefix;
   const std::string tb = p + ".transformer_blocks.0";
   const int C = l.ch, HW = xin.H * xin.W;
-  Act g = group_norm(xin, p + ".norm", 1e-6f, false, false);
+  Act g = group_norm(xin, p + ".norm", 1e-6f, false, false, in_gn);
   Act x = linear(g, p + ".proj_in.weight", p + ".proj_in.bias", nullptr);
   release(g);
   // attn1: self-attention over the H*W tokens of each frame
@@ -671,6 +715,13 @@ Act Model::spatial_transformer(const Act& xin, const Layer& l) {   // attention.
     const int lkv = ucfg_.text_context_len + (ctx_per_frame_ ? 16 : ctx_Limg_);
     ProfScope ps(PF_FLASH_CROSS, 4.0 * (double)HW * lkv * 64.0 * l.heads * F, 4.0 * (double)F * HW * C, st_,
                  fmt("%dx%dx%dx%d", F, HW, lkv, l.heads).c_str());
+    if (ctx_per_frame_) {
+      XattnArgs xa;
+      xa.Q = q.p; xa.q_pitch = C; xa.O = a2.p; xa.o_pitch = C; xa.F = F; xa.Nq = HW; xa.heads = l.heads;
+      xa.K = kc.kx; xa.VT = kc.vtx; xa.scale = 0.125f;
+      xattn_per_frame(xa, st_);
+      launches++;
+    } else {
     FlashArgs fa;
     fa.Q = q.p; fa.q_pitch = C; fa.O = a2.p; fa.o_pitch = C; fa.F = F; fa.Nq = HW; fa.heads = l.heads;
     fa.nseg = 2;
@@ -684,6 +735,7 @@ Act Model::spatial_transformer(const Act& xin, const Layer& l) {   // attention.
     fa.scale = 0.125f;
     flash_attention(fa, st_);
     launches++;
+    }
   }
   release(q);
   Act x2 = linear(a2, tb + ".attn2.to_out.0.weight", tb + ".attn2.to_out.0.bias", &x1);
@@ -729,12 +781,18 @@ Act Model::temporal_transformer(const Act& xin, const Layer& l) {   // attention
 
 // TimestepEmbedSequential dispatch (openaimodel3d.py:36-48).  Frees the intermediate tensors; the block input
 // is freed only when `owns_input` (skip tensors stay alive until the output path consumes them).
-Act Model::run_block(Act h, const Block& b, bool owns_input) {
+Act Model::run_block(Act h, const Block& b, bool owns_input, GnReq* in_gn) {
   bool owned = owns_input;
-  for (const Layer& l : b.layers) {
+  GnReq pend;                      // per-frame statistics of a ResBlock output for the SpatialTransformer norm that follows
+  for (size_t li = 0; li < b.layers.size(); li++) {
+    const Layer& l = b.layers[li];
+    const bool next_spatial = li + 1 < b.layers.size() && b.layers[li + 1].kind == "spatial";
     Act y;
-    if (l.kind == "res") y = res_block(h, l);
-    else if (l.kind == "spatial") y = spatial_transformer(h, l);
+    if (l.kind == "res") {
+      pend = GnReq{};
+      y = res_block(h, l, next_spatial ? &pend : nullptr, (li == 0 && in_gn && in_gn->sums) ? in_gn : nullptr);
+    }
+    else if (l.kind == "spatial") y = spatial_transformer(h, l, pend.sums ? &pend : nullptr);
     else if (l.kind == "temporal") y = temporal_transformer(h, l);
     else if (l.kind == "down") y = downsample(h, l.prefix + ".op", 1);
     else if (l.kind == "up") { Act u = upsample(h); y = conv3x3(u, l.prefix + ".conv", nullptr, nullptr); release(u); }
@@ -821,10 +879,12 @@ void Model::unet_body(const void* x, const int64_t* t, const int64_t* label, con
   cur = run_block(cur, mid_, false);              // hs.back() is still needed by output block 0
   for (const Block& b : out_blocks_) {
     Act skip = hs.back(); hs.pop_back();
-    Act cat = concat(cur, skip);
+    GnReq cat_gn;                                   // statistics for the first GroupNorm of the block, from the concat pass
+    const bool res_first = !b.layers.empty() && b.layers[0].kind == "res";
+    Act cat = concat(cur, skip, res_first ? &cat_gn : nullptr);
     release(cur);
     release(skip);
-    cur = run_block(cat, b, true);
+    cur = run_block(cat, b, true, &cat_gn);
   }
   // out: GroupNorm32 + SiLU + Conv3x3(model_channels -> out_channels), written as [N, Cout, T, h, w] fp16
   Act o = group_norm(cur, "out.0", 1e-5f, true, false);
@@ -908,9 +968,19 @@ void Model::set_context(const void* ctx, int dtype, int N, int L, int T, cudaStr
     const size_t tvb = sizeof(__half) * (size_t)N * C * tl_pad, ivb = sizeof(__half) * (size_t)nbi * C * li_pad;
     if (kc.text_vt_bytes < tvb) { cudaFree(kc.text_vt); MUDG_CUDA(cudaMalloc(&kc.text_vt, tvb)); kc.text_vt_bytes = tvb; realloc = true; }
     if (kc.img_vt_bytes < ivb) { cudaFree(kc.img_vt); MUDG_CUDA(cudaMalloc(&kc.img_vt, ivb)); kc.img_vt_bytes = ivb; realloc = true; }
-    transpose_v(kc.text + C, 2 * C, tl, N, heads, kc.text_vt, tl_pad, st);
-    transpose_v(kc.img + C, 2 * C, li, nbi, heads, kc.img_vt, li_pad, st);
-    launches += 2;
+    if (per_frame) {
+      // one merged 96-key block per frame (xattn.cu); the two-segment flash kernel is not used for this context layout
+      const size_t kb = sizeof(__half) * (size_t)N * T * 96 * C, vb = sizeof(__half) * (size_t)N * T * C * 128;
+      if (kc.kx_bytes < kb) { cudaFree(kc.kx); MUDG_CUDA(cudaMalloc(&kc.kx, kb)); kc.kx_bytes = kb; realloc = true; }
+      if (kc.vtx_bytes < vb) { cudaFree(kc.vtx); MUDG_CUDA(cudaMalloc(&kc.vtx, vb)); kc.vtx_bytes = vb; realloc = true; }
+      MUDG_REQUIRE(tl == 77, "xattn: the merged block is laid out for 77 text tokens (got %d)", tl);
+      xattn_pack(kc.text, kc.img, kc.kx, kc.vtx, N * T, T, C, st);
+      launches++;
+    } else {
+      transpose_v(kc.text + C, 2 * C, tl, N, heads, kc.text_vt, tl_pad, st);
+      transpose_v(kc.img + C, 2 * C, li, nbi, heads, kc.img_vt, li_pad, st);
+      launches += 2;
+    }
   };
   for (auto& b : in_blocks_) for (auto& l : b.layers) visit(l);
   for (auto& l : mid_.layers) visit(l);

@@ -67,6 +67,10 @@ struct KvCache {          // per SpatialTransformer: [N][77][2C] and [Nimg_batch
   __half* text_vt = nullptr;   // V halves transposed for the tcgen05 kernel: [N][C][80], [Nimg_batches][C][Limg padded to 8]
   __half* img_vt = nullptr;
   size_t text_vt_bytes = 0, img_vt_bytes = 0;
+  // per-frame context (L == 77 + 16 T): text + image keys merged into one 96-key block per frame for xattn_per_frame
+  __half* kx = nullptr;        // [F][96][C]
+  __half* vtx = nullptr;       // [F][C][128]
+  size_t kx_bytes = 0, vtx_bytes = 0;
 };
 
 class Model {
@@ -151,24 +155,31 @@ class Model {
   bool live() const { return !planning_; }
 
   // ---- ops (all no-ops apart from allocation when planning)
-  Act group_norm(const Act& x, const std::string& p, float eps, bool silu, bool over_time);
+  // GroupNorm statistics handed from a producing conv to the norm that consumes its output
+  struct GnReq {
+    bool over_time = false;   // statistics per sample over (C/32, T, H, W) instead of per frame
+    double* sums = nullptr;   // [S][32][2] fp64 in the arena (allocated + zeroed by gn_request, released by group_norm)
+    bool fused = false;       // the producer's epilogue accumulated them
+  };
+  void gn_request(GnReq& r, int S);
+  Act group_norm(const Act& x, const std::string& p, float eps, bool silu, bool over_time, GnReq* pre = nullptr);
   Act layer_norm(const Act& x, const std::string& p);
   Act linear(const Act& x, const std::string& wkey, const std::string& bkey, const Act* residual, bool geglu = false,
              float alpha = 1.f, const float2* ln = nullptr);
   float2* layer_norm_stats(const Act& x);
-  Act conv3x3(const Act& x, const std::string& p, const Act* residual, const float* bias2);
-  Act conv_t3(const Act& x, const std::string& p, const Act* residual);
+  Act conv3x3(const Act& x, const std::string& p, const Act* residual, const float* bias2, GnReq* gn = nullptr);
+  Act conv_t3(const Act& x, const std::string& p, const Act* residual, GnReq* gn = nullptr);
   Act gemm_raw(const __half* A, int M, int K, const __half* Wt, int N, const float* bias, const Act* residual, float alpha);
-  Act concat(const Act& a, const Act& b);
+  Act concat(const Act& a, const Act& b, GnReq* gn = nullptr);
   Act tile_batch(const Act& x, int n);
   Act upsample(const Act& x);
   Act downsample(const Act& x, const std::string& p, int pad);
 
-  Act res_block(const Act& x, const Layer& l);
+  Act res_block(const Act& x, const Layer& l, GnReq* out_gn = nullptr, GnReq* in_gn = nullptr);
   Act transformer_block_tail(Act x, const std::string& p);   // LN3 + GEGLU FF + residual (consumes x)
-  Act spatial_transformer(const Act& x, const Layer& l);
+  Act spatial_transformer(const Act& x, const Layer& l, GnReq* in_gn = nullptr);
   Act temporal_transformer(const Act& x, const Layer& l);
-  Act run_block(Act h, const Block& b, bool owns_input);
+  Act run_block(Act h, const Block& b, bool owns_input, GnReq* in_gn = nullptr);
   void compute_embeddings(const int64_t* t, const int64_t* label, const int64_t* fs, int N);
   void unet_body(const void* x, const int64_t* t, const int64_t* label, const int64_t* fs, int N, int dup, int T, int h, int w,
                  void* out);

@@ -4,11 +4,12 @@
 
 namespace mudg {
 
-// GroupNorm over [S samples][rows_per_sample][C] (32 groups): per-(sample,channel) scale/shift, then apply (+SiLU)
-void gn_scale_shift(const __half* x, int S, int64_t rows_per_sample, int C, const float* gamma, const float* beta,
-                    float eps, double* sums_ws /*[S*64]*/, float* scale /*[S*C]*/, float* shift, cudaStream_t st);
-void gn_apply(const __half* x, __half* y, const float* scale, const float* shift, int64_t rows, int C,
-              int64_t rows_per_sample, bool silu_act, cudaStream_t st);
+// GroupNorm over [S samples][rows_per_sample][C] (32 groups, fp64 (sum, sum of squares) pairs [S][32][2]):
+// gn_stats accumulates into pre-zeroed sums (or the producing GEMM's epilogue does: TapGemm::gn_sums); gn_apply
+// normalises straight from the sums in one pass (+ SiLU).
+void gn_stats(const __half* x, int S, int64_t rows_per_sample, int C, double* sums, cudaStream_t st);
+void gn_apply(const __half* x, __half* y, const double* sums, int S, int64_t rows_per_sample, int C, const float* gamma,
+              const float* beta, float eps, bool silu_act, cudaStream_t st);
 void layernorm(const __half* x, __half* y, const float* gamma, const float* beta, int64_t rows, int C, float eps,
                cudaStream_t st);
 void ln_stats(const __half* x, float2* out, int64_t rows, int C, float eps, cudaStream_t st);
@@ -17,6 +18,10 @@ void ln_fold(__half* W, const float* gamma, const float* beta, const float* bias
 // out[r] = [a[r] | b[r % rows_b]] (rows_b divides rows: a skip tensor shared by the copies of a CFG batch)
 void concat_channels(const __half* a, int Ca, const __half* b, int Cb, __half* out, int64_t rows, int64_t rows_b,
                      cudaStream_t st);
+// the same concat, also accumulating the GroupNorm statistics of its output into pre-zeroed sums [S][32][2] (S samples of
+// rows_per_sample rows each)
+void concat_channels_stats(const __half* a, int Ca, const __half* b, int Cb, __half* out, int S, int64_t rows_per_sample,
+                           int64_t rows_b, double* sums, cudaStream_t st);
 void upsample2x(const __half* x, __half* y, int F, int H, int W, int C, cudaStream_t st);
 void im2col_s2(const __half* x, __half* y, int F, int H, int W, int C, int pad, cudaStream_t st);   // Ho = (H + pad - 2) / 2 + 1
 void softmax_rows(__half* x, int64_t rows, int n, cudaStream_t st);
@@ -60,6 +65,23 @@ struct FlashArgs {
 void flash_attention(const FlashArgs& a, cudaStream_t st);
 void transpose_v(const __half* V, int pitch, int len, int nbatch, int heads, __half* VT, int len_pad, cudaStream_t st);
 void flash_set_trace(long long* buf);   // debug: clock64 time line of CTA 0 ([3][96][8] int64), null = off
+
+// ---- cross-attention to the per-frame context (xattn.cu): 77 text + 16 image keys merged into one 96-key block.
+// xattn_pack builds the merged operands from the projected K|V rows (text_kv [N][77][2C], img_kv [F][16][2C], K in the first
+// C columns, V in the last): K [F][96][C] and V^T [F][C][128]; xattn_per_frame is the attention itself (separate text /
+// image softmaxes, outputs summed), Q / O rows [F][Nq] with head h at columns [h*64, h*64+64).
+struct XattnArgs {
+  const __half* Q = nullptr;
+  int q_pitch = 0;
+  __half* O = nullptr;
+  int o_pitch = 0;
+  int F = 0, Nq = 0, heads = 0;
+  const __half* K = nullptr;     // [F][96][heads*64]
+  const __half* VT = nullptr;    // [F][heads*64][128]
+  float scale = 0.125f;
+};
+void xattn_pack(const __half* text_kv, const __half* img_kv, __half* K, __half* VT, int F, int T, int C, cudaStream_t st);
+void xattn_per_frame(const XattnArgs& a, cudaStream_t st);
 
 // Temporal self-attention over T for every (b, h, w, head): qkv rows [B*T*HW][3*inner] (q | k | v), out [rows][inner]
 void temporal_attention(const __half* qkv, __half* out, int B, int T, int HW, int heads, float scale, cudaStream_t st);

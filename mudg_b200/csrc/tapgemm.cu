@@ -480,7 +480,9 @@ struct G3Params {
   int dimW, dimH, dimB;
   const __half* R;
   int alpha_is_one;
-  int dbg;                      // debug experiments (MUDG_GEMM_DBG): 1 = do not issue the output TMA stores
+  double* gn_sums;              // GroupNorm statistics of the output ([S][32][2] fp64, pre-zeroed), or null
+  FastDiv fd_cpg, fd_gn;        // channels per group; frames per GroupNorm sample (sample = (b*T + t) / d)
+  int dbg;                      // debug experiments (knob gemm_dbg): 1 = do not issue the output TMA stores
   long long* trace;             // debug (tests/gpu_trace_gemm.py): clock64 time line of cluster 0 / rank 0, [4 roles][64 tiles][8]
 };
 
@@ -505,6 +507,41 @@ __device__ __forceinline__ G2Tile g3_decode(const G3Params& p, int tile, int ran
   fd_divmod(p.b.fd_tt, m, tb, tt);
   t.w0 = tw * p.b.bw; t.h0 = th * p.b.bh; t.t0 = tt * p.b.bt; t.b0 = tb * p.b.bb;
   return t;
+}
+
+// GroupNorm statistics of one staged 64-column output chunk (fp16, SWIZZLE_128B, 128 rows x 128 B), fused into the
+// producing GEMM so the consumer norm needs no statistics pass over HBM.  Warp q of an epilogue group sums the 32 rows it
+// staged itself: lane l owns columns (2l, 2l+1) -- a row is one conflict-free 128 B shared-memory wavefront --, fp32 partials
+// over <= 32 rows, a fixed-order segmented shuffle reduction over the lanes of a group (channels per group is even, so a
+// column pair never straddles groups), then one fp64 RED per (group, moment): the same accumulation discipline as
+// gn_stats_kernel (fp64 sums of fixed-order fp32 partials), hence the same run-to-run repeatability.
+__device__ __forceinline__ void gn_chunk_stats(const uint8_t* stg, int q, int lane, uint32_t valid, int col_base,
+                                               const FastDiv& fd_cpg, double* sums_sample) {
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  const uint32_t coff = (uint32_t)(lane & 3) * 4u, chunk = (uint32_t)lane >> 2;
+  const uint8_t* base = stg + q * 32 * 128;
+#pragma unroll
+  for (int i = 0; i < 32; i++) {
+    if (valid & (1u << i)) {                 // warp-uniform: rows past the tensor edge hold bias-only garbage
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(base + i * 128 + ((chunk ^ (uint32_t)(i & 7)) << 4) + coff);
+      const float2 f = unpack_half2(w);
+      s0 += f.x; q0 = fmaf(f.x, f.x, q0);
+      s1 += f.y; q1 = fmaf(f.y, f.y, q1);
+    }
+  }
+  float sm = s0 + s1, sq = q0 + q1;
+  const int g = fd_div(fd_cpg, col_base + 2 * lane);
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const float so = __shfl_down_sync(0xffffffffu, sm, d), qo = __shfl_down_sync(0xffffffffu, sq, d);
+    const int go = __shfl_down_sync(0xffffffffu, g, d);
+    if (lane + d < 32 && go == g) { sm += so; sq += qo; }
+  }
+  const int gprev = __shfl_up_sync(0xffffffffu, g, 1);
+  if (lane == 0 || gprev != g) {
+    atomicAdd(sums_sample + 2 * g, (double)sm);
+    atomicAdd(sums_sample + 2 * g + 1, (double)sq);
+  }
 }
 
 // EPI: epilogue specialisation.  -1 = everything decided at run time (and the only variant with the GEGLU path);
@@ -857,6 +894,13 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
           }
           __syncwarp();
+          if (p.gn_sums != nullptr) {          // GroupNorm statistics of this chunk for the consumer norm (see gn_chunk_stats)
+            const uint32_t valid = __ballot_sync(0xffffffffu, row_ok);
+            if (valid != 0u) {
+              const int smp = __shfl_sync(0xffffffffu, fd_div(p.fd_gn, pb * p.b.dimT + pt), __ffs((int)valid) - 1);
+              gn_chunk_stats(stg, q, lane, valid, tl.n0 + ch * 64, p.fd_cpg, p.gn_sums + (size_t)smp * 64);
+            }
+          }
           chunk_no++;
           if (q == 2 && lane == 0) G3_TRACE(2 + grp, lt, 2 + (sl >> 1));   // chunk stored
         }
@@ -982,7 +1026,7 @@ bool tapgemm_pair_wanted(const TapGemm& g, int64_t m_tiles, int nt128) {
   return m_tiles * nt128 >= 8 * (int64_t)sm_count() && ktot_steps >= 4;
 }
 
-void tapgemm_tc3(const TapGemm& g, cudaStream_t st) {
+bool tapgemm_tc3(const TapGemm& g, cudaStream_t st) {
   G3Params p{};
   p.b = make_params(g);
   int budget = BM;
@@ -1014,6 +1058,17 @@ void tapgemm_tc3(const TapGemm& g, cudaStream_t st) {
   p.dimW = g.W; p.dimH = g.H; p.dimB = g.B;
   p.R = g.R;
   p.alpha_is_one = g.alpha == 1.f ? 1 : 0;
+  // fused GroupNorm statistics: a 128-pixel box must lie inside one sample, and a column pair inside one group
+  const int gn_div = g.gn_div > 0 ? g.gn_div : 1;
+  // (only where the MMA main loop leaves the epilogue slack: measured at level 0, the 3-tap temporal conv -- K = 960, already
+  // epilogue-bound -- got 95 us slower with the statistics, twice what the separate statistics pass costs; the 9-tap convs
+  // absorb them for free)
+  const int gn_min_taps = knobs().gn_fuse == 2 ? 1 : 9;
+  const bool gn_fuse = g.gn_sums != nullptr && knobs().gn_fuse != 0 && g.ntaps >= gn_min_taps && !g.geglu && p.b.bb == 1 &&
+                       gn_div % p.b.bt == 0 && p.b.n_out % 64 == 0 && (p.b.n_out / 32) % 2 == 0;
+  p.gn_sums = gn_fuse ? g.gn_sums : nullptr;
+  p.fd_cpg = make_fastdiv(std::max(1, p.b.n_out / 32));
+  p.fd_gn = make_fastdiv(gn_div);
   p.trace = g_gemm_trace;
   p.dbg = knobs().gemm_dbg;
 
@@ -1058,11 +1113,12 @@ void tapgemm_tc3(const TapGemm& g, cudaStream_t st) {
     case 9: tapgemm_tc3_kernel<9><<<grid, G3_THREADS, G3_SMEM, st>>>(*ma, *mb0, *mb1, *md, p); break;
     default: epi = -1; tapgemm_tc3_kernel<-1><<<grid, G3_THREADS, G3_SMEM, st>>>(*ma, *mb0, *mb1, *md, p); break;
   }
-  knobs().last_gemm_path = 4 | ((epi + 1) << 8);
+  knobs().last_gemm_path = 4 | ((epi + 1) << 8) | (gn_fuse ? 1 << 16 : 0);
   MUDG_CUDA(cudaGetLastError());
+  return gn_fuse;
 }
 
-void tapgemm_tc2(const TapGemm& g, cudaStream_t st) {
+bool tapgemm_tc2(const TapGemm& g, cudaStream_t st) {
   MUDG_REQUIRE(tapgemm_tc_eligible(g), "layer not eligible for the tcgen05 path (Cin=%d N=%d)", g.Cin, g.N);
   {
     int budget = BM;
@@ -1131,6 +1187,7 @@ void tapgemm_tc2(const TapGemm& g, cudaStream_t st) {
   }
   knobs().last_gemm_path = sub == 1 ? 2 : 3;
   MUDG_CUDA(cudaGetLastError());
+  return false;
 }
 
 void tapgemm_generic(const TapGemmGeneric& g, cudaStream_t st) {
@@ -1146,7 +1203,7 @@ void tapgemm_generic(const TapGemmGeneric& g, cudaStream_t st) {
 // The product entry.  With the profiler on (bench.py's roofline leg) the launch is bracketed by a CUDA-event pair and
 // booked with its algorithmic work: 2 * rows * N * taps * Cin FLOPs (padding and tile overhang not counted) and the HBM
 // bytes an ideal kernel moves (A once, W once, D once, residual once, LayerNorm statistics).
-void tapgemm(const TapGemm& g, cudaStream_t st) {
+bool tapgemm(const TapGemm& g, cudaStream_t st) {
   if (!tapgemm_tc_eligible(g)) {
     // Irregular plain GEMMs (N not a multiple of 64: the VAE mid-block attention at latent sizes whose token count is
     // not, e.g. 8 x 12) run on the arbitrary-stride CUDA-core kernel like the other irregular layers; anything with a
@@ -1162,7 +1219,8 @@ void tapgemm(const TapGemm& g, cudaStream_t st) {
     q.D = g.D; q.d_sn = 1; q.d_sw = g.N; q.d_sh = (int64_t)g.W * g.N; q.d_st = q.d_sh * g.H; q.d_sb = q.d_st * g.T;
     q.bias = g.bias; q.alpha = g.alpha;
     ProfScope ps(PF_GENERIC_CONV, 0.0, 0.0, st, "irregular gemm");
-    return tapgemm_generic(q, st);
+    tapgemm_generic(q, st);
+    return false;
   }
   if (!prof_active()) return tapgemm_tc2(g, st);
   const double rows = (double)g.B * g.T * g.H * g.W;
@@ -1174,7 +1232,7 @@ void tapgemm(const TapGemm& g, cudaStream_t st) {
   snprintf(buf, sizeof buf, "%.0fx%dx%dx%d:g%dr%dl%db%d", rows, g.N, g.ntaps, g.Cin, g.geglu ? 1 : 0, g.R ? 1 : 0,
            g.ln_stats ? 1 : 0, g.bias2 ? 1 : 0);
   ProfScope ps(PF_GEMM, flops, bytes, st, buf);
-  tapgemm_tc2(g, st);
+  return tapgemm_tc2(g, st);
 }
 
 }  // namespace mudg

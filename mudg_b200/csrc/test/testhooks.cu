@@ -232,6 +232,39 @@ void mma_probe(int variant, int reps, int ctas, int mode, long long* out, cudaSt
 }
 
 
+// ---------------------------------------------------------------- MUFU throughput probe
+// mode 0: ex2.approx.ftz.f32 (1 exponential per lane-op), mode 1: ex2.approx.f16x2 (2 per lane-op as written; SASS shows
+// two MUFU.EX2.F16), mode 2: rcp.approx, mode 3: FFMA only (loop overhead reference).  8 independent chains per thread.
+__global__ void mufu_probe_kernel(int mode, int iters, float seed, float* out, long long* clocks) {
+  float v[8];
+  uint32_t h[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { v[i] = seed + 0.001f * (threadIdx.x + i); h[i] = 0x30003000u + threadIdx.x + i; }
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; it++) {
+    if (mode == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(v[i]));
+    } else if (mode == 1) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(h[i]));
+    } else if (mode == 2) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(v[i]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; i++) asm volatile("fma.rn.f32 %0, %0, %0, %0;" : "+f"(v[i]));
+    }
+  }
+  const long long t1 = clock64();
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; i++) acc += v[i] + __uint_as_float(h[i]);
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+  if (threadIdx.x == 0) clocks[blockIdx.x] = t1 - t0;
+}
+
 }  // namespace
 }  // namespace mudg
 
@@ -273,6 +306,15 @@ MUDG_EXPORT int mudg_test_set_knob(const char* name, int value) {
 
 MUDG_EXPORT int mudg_test_last_gemm_path(void) { return knobs().last_gemm_path; }
 
+// GroupNorm statistics request for the NEXT mudg_test_tapgemm call (TapGemm::gn_sums / gn_div); cleared by that call
+static double* g_next_gn_sums = nullptr;
+static int g_next_gn_div = 1;
+MUDG_EXPORT int mudg_test_next_gemm_gn(void* sums_f64, int gn_div) {
+  g_next_gn_sums = static_cast<double*>(sums_f64);
+  g_next_gn_div = gn_div;
+  return 0;
+}
+
 MUDG_EXPORT int mudg_test_tapgemm(const void* A, int B, int T, int H, int W, int Cin, int mode, const void* Wt, int N,
                                   void* D, const void* R, const float* bias, const float* bias2, int bias2_div, int nb2,
                                   float alpha, int geglu, const void* ln_stats, const float* ln_c1, int backend,
@@ -293,8 +335,14 @@ MUDG_EXPORT int mudg_test_tapgemm(const void* A, int B, int T, int H, int W, int
   g.ln_stats = static_cast<const float2*>(ln_stats);
   g.ln_c1 = ln_c1;
   knobs().last_gemm_path = 0;
-  if (backend == 0) tapgemm(g, S(stream));          // the product dispatch (tcgen05)
-  else tapgemm_simt(g, S(stream));
+  if (backend == 0) {                                // the product dispatch (tcgen05)
+    g.gn_sums = g_next_gn_sums;
+    g.gn_div = g_next_gn_div;
+    g_next_gn_sums = nullptr;
+    tapgemm(g, S(stream));
+  } else {
+    tapgemm_simt(g, S(stream));
+  }
   MUDG_API_END
 }
 
@@ -337,6 +385,25 @@ MUDG_EXPORT int mudg_test_flash(const void* Q, int q_pitch, void* O, int o_pitch
   MUDG_API_END
 }
 
+// cross-attention to a per-frame context through the merged-block kernel: text_kv [N][77][2C], img_kv [F][16][2C] (K | V)
+MUDG_EXPORT int mudg_test_xattn(const void* Q, void* O, int F, int T, int Nq, int heads, const void* text_kv, const void* img_kv,
+                                float scale, void* stream) {
+  MUDG_API_BEGIN
+  const int C = heads * 64;
+  static __half* kx = nullptr;
+  static __half* vtx = nullptr;
+  static size_t kb = 0, vb = 0;
+  const size_t nk = sizeof(__half) * (size_t)F * 96 * C, nv = sizeof(__half) * (size_t)F * C * 128;
+  if (kb < nk) { MUDG_CUDA(cudaDeviceSynchronize()); cudaFree(kx); MUDG_CUDA(cudaMalloc(&kx, nk)); kb = nk; }
+  if (vb < nv) { MUDG_CUDA(cudaDeviceSynchronize()); cudaFree(vtx); MUDG_CUDA(cudaMalloc(&vtx, nv)); vb = nv; }
+  xattn_pack(static_cast<const __half*>(text_kv), static_cast<const __half*>(img_kv), kx, vtx, F, T, C, S(stream));
+  XattnArgs a;
+  a.Q = static_cast<const __half*>(Q); a.q_pitch = C; a.O = static_cast<__half*>(O); a.o_pitch = C;
+  a.F = F; a.Nq = Nq; a.heads = heads; a.K = kx; a.VT = vtx; a.scale = scale;
+  xattn_per_frame(a, S(stream));
+  MUDG_API_END
+}
+
 MUDG_EXPORT int mudg_test_gemm_trace(void* buf) {
   MUDG_API_BEGIN
   gemm_set_trace(static_cast<long long*>(buf));
@@ -346,6 +413,14 @@ MUDG_EXPORT int mudg_test_gemm_trace(void* buf) {
 MUDG_EXPORT int mudg_test_mma_probe(int variant, int reps, int ctas, int mode, void* out, void* stream) {
   MUDG_API_BEGIN
   mma_probe(variant, reps, ctas, mode, static_cast<long long*>(out), S(stream));
+  MUDG_API_END
+}
+
+// out: float [ctas * threads], clocks: int64 [ctas] (clocks of the timed loop in CTA's thread 0)
+MUDG_EXPORT int mudg_test_mufu_probe(int mode, int iters, int ctas, int threads, void* out, void* clocks, void* stream) {
+  MUDG_API_BEGIN
+  mufu_probe_kernel<<<ctas, threads, 0, S(stream)>>>(mode, iters, 0.5f, static_cast<float*>(out), static_cast<long long*>(clocks));
+  MUDG_CUDA(cudaGetLastError());
   MUDG_API_END
 }
 
@@ -366,16 +441,13 @@ MUDG_EXPORT int mudg_test_groupnorm(const void* x, void* y, int Sn, int64_t rows
                                     const float* beta, float eps, int silu, void* stream) {
   MUDG_API_BEGIN
   double* sums = nullptr;
-  float* ss = nullptr;
   MUDG_CUDA(cudaMalloc(&sums, sizeof(double) * Sn * 64));
-  MUDG_CUDA(cudaMalloc(&ss, sizeof(float) * Sn * C * 2));
-  gn_scale_shift(static_cast<const __half*>(x), Sn, rows_per_sample, C, gamma, beta, eps, sums, ss, ss + (size_t)Sn * C,
-                 S(stream));
-  gn_apply(static_cast<const __half*>(x), static_cast<__half*>(y), ss, ss + (size_t)Sn * C, (int64_t)Sn * rows_per_sample, C,
-           rows_per_sample, silu != 0, S(stream));
+  MUDG_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * Sn * 64, S(stream)));
+  gn_stats(static_cast<const __half*>(x), Sn, rows_per_sample, C, sums, S(stream));
+  gn_apply(static_cast<const __half*>(x), static_cast<__half*>(y), sums, Sn, rows_per_sample, C, gamma, beta, eps, silu != 0,
+           S(stream));
   MUDG_CUDA(cudaStreamSynchronize(S(stream)));
   cudaFree(sums);
-  cudaFree(ss);
   MUDG_API_END
 }
 

@@ -1,0 +1,398 @@
+// Cross-attention of the SpatialTransformers to the per-frame context (77 text tokens shared by the frames of a sample +
+// 16 image tokens of the frame: attention.py:89-94,129-142 with the context split of openaimodel3d.py:580-585).
+//
+// Both K/V segments fit ONE 96-key block, so there is no K/V loop and no running softmax state: the op is a stream over
+// Q (read once) and O (written once) and is bound by HBM, not by the tensor cores.  The general two-segment flash kernel
+// (attn.cu) spends a whole CTA -- TMEM allocation, barrier set-up, pipeline fill and drain -- on 256 queries and two mostly
+// padded 128-key blocks (measured 0.10 of the HBM roofline inside the clip); this kernel is persistent instead:
+//
+//   merged operands, built once per clip by mudg_set_context (xattn_pack): K [F][96][C] with rows 0..76 = text K of the
+//   frame's sample, 77..79 = 0, 80..95 = the frame's image K; V^T [F][C][128] with the same key order (96..127 = 0).
+//   work unit = (frame, head, run of query tiles); a CTA loads the unit's K (12 KB) and V^T (16 KB) once, then streams
+//   128-query tiles through a 4-stage TMA ring:
+//     warp 0      producer: K / V^T per unit (double buffered), Q tiles
+//     warp 1      tcgen05 issuer (event loop, one elected lane): S = Q K^T (M128 N96 K64), O = P V (M128 N64 K96, P in TMEM)
+//     warps 2-5 / 6-9  two softmax + epilogue groups on alternate tiles (thread == query row == TMEM lane): the 96 scores of
+//                 a row in one TMEM round trip, separate max / sum over the text and the image columns, P = e / l per
+//                 segment (so ONE P V product adds the two attention outputs), packed fp16 back to TMEM; then O -> fp16 ->
+//                 swizzled staging tile -> TMA store (clips partial tiles).
+#include "ops.h"
+#include "ptx.cuh"
+
+#include <algorithm>
+
+namespace mudg {
+
+namespace {
+
+constexpr int XA_THREADS = 320;
+constexpr int XA_QSTAGES = 4;
+constexpr int XA_TILE = 128 * 64 * 2;                  // 16 KB: 128 rows x 64 fp16, SWIZZLE_128B
+constexpr int XA_K_BYTES = 96 * 128;                   // 12 KB
+constexpr int XA_KV_BYTES = XA_K_BYTES + XA_TILE;      // K + two 64-key V^T atoms (8 KB each)
+constexpr int XA_SMEM = XA_QSTAGES * XA_TILE + 2 * XA_KV_BYTES + 2 * XA_TILE + 1024 + 256;
+constexpr int XA_TEXT = 77, XA_IMG0 = 80, XA_KEYS = 96;
+
+struct XaParams {
+  int heads, qtiles, tpu, chunks, units;   // query tiles per (frame, head); tiles per unit; units per (frame, head); total units
+  float scale_log2;
+};
+
+struct XaCursor {                          // walks this CTA's tiles in the one order every role agrees on
+  int u, ord, t, c;                        // global unit, unit ordinal of this CTA, tile inside the unit, global tile counter
+  int nt;                                  // tiles in the current unit
+};
+__device__ __forceinline__ int xa_unit_tiles(const XaParams& p, int u) {
+  const int chunk = u % p.chunks;
+  return min(p.tpu, p.qtiles - chunk * p.tpu);
+}
+__device__ __forceinline__ XaCursor xa_begin(const XaParams& p) {
+  XaCursor k;
+  k.u = blockIdx.x; k.ord = 0; k.t = 0; k.c = 0;
+  k.nt = k.u < p.units ? xa_unit_tiles(p, k.u) : 0;
+  return k;
+}
+__device__ __forceinline__ bool xa_valid(const XaParams& p, const XaCursor& k) { return k.u < p.units; }
+__device__ __forceinline__ void xa_next(const XaParams& p, XaCursor& k) {
+  k.c++;
+  if (++k.t == k.nt) {
+    k.t = 0; k.ord++;
+    k.u += gridDim.x;
+    k.nt = k.u < p.units ? xa_unit_tiles(p, k.u) : 0;
+  }
+}
+// unit -> (frame, head, first query tile)
+__device__ __forceinline__ void xa_decode(const XaParams& p, int u, int& f, int& head, int& qt0) {
+  const int chunk = u % p.chunks;
+  const int fh = u / p.chunks;
+  head = fh % p.heads;
+  f = fh / p.heads;
+  qt0 = chunk * p.tpu;
+}
+
+__global__ void __launch_bounds__(XA_THREADS, 1)
+xattn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmO,
+             const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const XaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                       // XA_QSTAGES tiles
+  uint8_t* sKV = sQ + XA_QSTAGES * XA_TILE;                 // buffer b: K at + b*XA_KV_BYTES, V^T at + XA_K_BYTES
+  uint8_t* sOut = sKV + 2 * XA_KV_BYTES;                    // one staging tile per group
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + 2 * XA_TILE);
+  uint64_t* q_full = bars;                                  // [XA_QSTAGES]
+  uint64_t* q_empty = q_full + XA_QSTAGES;                  // [XA_QSTAGES]
+  uint64_t* kv_full = q_empty + XA_QSTAGES;                 // [2]
+  uint64_t* kv_empty = kv_full + 2;                         // [2]
+  uint64_t* s_full = kv_empty + 2;                          // [2] per group
+  uint64_t* p_ready = s_full + 2;                           // [2]
+  uint64_t* o_full = p_ready + 2;                           // [2]
+  uint64_t* o_free = o_full + 2;                            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < XA_QSTAGES; i++) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: S0 [0,128) S1 [128,256) (96 used) | O0 [256,320) O1 [320,384) | P0 [384,448) P1 [448,512) (48 used)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (XaCursor k = xa_begin(p); xa_valid(p, k); xa_next(p, k)) {
+        int f, head, qt0;
+        xa_decode(p, k.u, f, head, qt0);
+        if (k.t == 0) {                                     // the unit's K and V^T
+          const int b = k.ord & 1;
+          mbar_wait(&kv_empty[b], ((k.ord >> 1) & 1) ^ 1);
+          mbar_expect_tx(&kv_full[b], XA_KV_BYTES);
+          uint8_t* kb = sKV + b * XA_KV_BYTES;
+          tma_load_5d(kb, &tmK, &kv_full[b], head * 64, 0, f, 0, 0);
+          tma_load_5d(kb + XA_K_BYTES, &tmV, &kv_full[b], 0, head * 64, f, 0, 0);
+          tma_load_5d(kb + XA_K_BYTES + XA_TILE / 2, &tmV, &kv_full[b], 64, head * 64, f, 0, 0);
+        }
+        const int s = k.c % XA_QSTAGES;
+        mbar_wait(&q_empty[s], ((k.c / XA_QSTAGES) & 1) ^ 1);
+        mbar_expect_tx(&q_full[s], XA_TILE);
+        tma_load_5d(sQ + s * XA_TILE, &tmQ, &q_full[s], head * 64, (qt0 + k.t) * 128, f, 0, 0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // Event loop (whole warp, uniform control flow, one elected lane issues): each group is served on its own -- S of its
+    // next tile as soon as the Q tile (and the unit's K) has landed and the group has consumed its previous S (p_ready),
+    // P V as soon as the group has stored P and read out its previous O (o_free).
+    constexpr uint32_t idesc_s = umma_idesc_f16(128, XA_KEYS, 0, 0);
+    constexpr uint32_t idesc_o = umma_idesc_f16(128, 64, 0, 0);
+    const uint64_t dq0 = umma_desc_sw128(smem_u32(sQ), 16, 1024);
+    const uint64_t dk0 = umma_desc_sw128(smem_u32(sKV), 16, 1024);
+    XaCursor cs[2], cp[2];                                   // per group: next tile whose S / P V is to be issued
+    for (int g = 0; g < 2; g++) {
+      cs[g] = xa_begin(p);
+      if (g == 1 && xa_valid(p, cs[g])) xa_next(p, cs[g]);
+      cp[g] = cs[g];
+    }
+    int issued_pv[2] = {0, 0};                               // P V products issued per K/V buffer (to release it)
+    uint32_t idle = 0;
+    while (xa_valid(p, cp[0]) || xa_valid(p, cp[1])) {
+      bool progress = false;
+#pragma unroll
+      for (int g = 0; g < 2; g++) {
+        if (xa_valid(p, cs[g])) {
+          const XaCursor& k = cs[g];
+          const int s = k.c % XA_QSTAGES, b = k.ord & 1;
+          const int m = k.c >> 1;                            // per-group sequence number of this tile
+          bool ok = mbar_test(&q_full[s], (uint32_t)(k.c / XA_QSTAGES) & 1u) && mbar_test(&kv_full[b], (uint32_t)(k.ord >> 1) & 1u);
+          if (m > 0) ok = ok && mbar_test(&p_ready[g], (uint32_t)(m - 1) & 1u);   // S of the previous tile is in registers
+          if (__all_sync(0xffffffffu, ok)) {
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t dq = dq0 + (uint64_t)(s * (XA_TILE >> 4));
+              const uint64_t dk = dk0 + (uint64_t)(b * (XA_KV_BYTES >> 4));
+#pragma unroll
+              for (int kk = 0; kk < 4; kk++) umma_f16(tmem_base + g * 128, dq + 2 * kk, dk + 2 * kk, idesc_s, kk != 0 ? 1u : 0u);
+              umma_commit(&s_full[g]);
+              umma_commit(&q_empty[s]);                      // the Q tile is dead once S is complete
+            }
+            __syncwarp();
+            xa_next(p, cs[g]);
+            if (xa_valid(p, cs[g])) xa_next(p, cs[g]);
+            progress = true;
+          }
+        }
+        if (xa_valid(p, cp[g])) {
+          const XaCursor& k = cp[g];
+          const int b = k.ord & 1;
+          const int m = k.c >> 1;
+          bool ok = mbar_test(&p_ready[g], (uint32_t)m & 1u);
+          if (m > 0) ok = ok && mbar_test(&o_free[g], (uint32_t)(m - 1) & 1u);
+          if (__all_sync(0xffffffffu, ok)) {
+            tc_fence_after();
+            const bool last_of_unit = (++issued_pv[b] == k.nt);
+            if (last_of_unit) issued_pv[b] = 0;
+            if (elect_one()) {
+              const uint64_t dv = dk0 + (uint64_t)(b * (XA_KV_BYTES >> 4) + (XA_K_BYTES >> 4));
+#pragma unroll
+              for (int kk = 0; kk < XA_KEYS / 16; kk++) {     // K = 16 keys = 8 TMEM columns of P = 32 B inside a V^T atom
+                const uint64_t dvk = dv + (uint64_t)((kk >> 2) * ((XA_TILE / 2) >> 4) + (kk & 3) * 2);
+                umma_f16_ts(tmem_base + 256 + g * 64, tmem_base + 384 + g * 64 + kk * 8, dvk, idesc_o, kk != 0 ? 1u : 0u);
+              }
+              umma_commit(&o_full[g]);
+              if (last_of_unit) umma_commit(&kv_empty[b]);   // covers every S / P V of the unit issued before
+            }
+            __syncwarp();
+            xa_next(p, cp[g]);
+            if (xa_valid(p, cp[g])) xa_next(p, cp[g]);
+            progress = true;
+          }
+        }
+      }
+      if (progress) idle = 0;
+      else {
+        if (++idle > (1u << 24)) __trap();       // a protocol bug traps (error to the host) instead of hanging the GPU
+        __nanosleep(32);
+      }
+    }
+  } else {
+    const int grp = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t tS = tmem_base + grp * 128 + lane_off;
+    const uint32_t tO = tmem_base + 256 + grp * 64 + lane_off;
+    const uint32_t tP = tmem_base + 384 + grp * 64 + lane_off;
+    uint8_t* myOut = sOut + grp * XA_TILE;
+    XaCursor k = xa_begin(p);
+    if (grp == 1 && xa_valid(p, k)) xa_next(p, k);
+    for (; xa_valid(p, k);) {
+      const uint32_t m = (uint32_t)(k.c >> 1);
+      int f, head, qt0;
+      xa_decode(p, k.u, f, head, qt0);
+      mbar_wait(&s_full[grp], m & 1u);
+      __syncwarp();
+      tc_fence_after();
+      uint32_t sr[3][32];
+#pragma unroll
+      for (int c = 0; c < 3; c++) tmem_ld32(tS + c * 32, sr[c]);
+      tmem_ld_wait();
+      // ---- two softmaxes: text = columns [0, 77), image = columns [80, 96)
+      float mt[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int j = 0; j < XA_TEXT; j++) mt[j & 3] = fmaxf(mt[j & 3], __uint_as_float(sr[j >> 5][j & 31]));
+      float mi[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int j = XA_IMG0; j < XA_KEYS; j++) mi[j & 1] = fmaxf(mi[j & 1], __uint_as_float(sr[2][j & 31]));
+      const float mxt = fmaxf(fmaxf(mt[0], mt[1]), fmaxf(mt[2], mt[3])) * p.scale_log2;
+      const float mxi = fmaxf(mi[0], mi[1]) * p.scale_log2;
+      float lt[4] = {0.f, 0.f, 0.f, 0.f}, li[2] = {0.f, 0.f};
+      // exponentials in place over the score registers (96 live registers, not 192)
+#pragma unroll
+      for (int j = 0; j < XA_KEYS; j++) {
+        const float sv = __uint_as_float(sr[j >> 5][j & 31]);
+        float ev = 0.f;
+        if (j < XA_TEXT) { ev = ex2_approx(fmaf(sv, p.scale_log2, -mxt)); lt[j & 3] += ev; }
+        else if (j >= XA_IMG0) { ev = ex2_approx(fmaf(sv, p.scale_log2, -mxi)); li[j & 1] += ev; }
+        sr[j >> 5][j & 31] = __float_as_uint(ev);
+      }
+      const float rt = __fdividef(1.f, (lt[0] + lt[1]) + (lt[2] + lt[3]));
+      const float ri = __fdividef(1.f, li[0] + li[1]);
+      // P = e / l per segment, packed fp16, again in place: keys 0..63 -> sr[0][0..31], keys 64..95 -> sr[1][0..15]
+#pragma unroll
+      for (int j = 0; j < XA_KEYS; j += 2) {
+        const float r0 = j < XA_TEXT ? rt : ri, r1 = (j + 1) < XA_TEXT ? rt : ri;                   // 76|77 straddles: key 77 is padding (e = 0)
+        const uint32_t w = pack_half2(__uint_as_float(sr[j >> 5][j & 31]) * r0, __uint_as_float(sr[(j + 1) >> 5][(j + 1) & 31]) * r1);
+        sr[j >> 6][(j >> 1) & 31] = w;             // word j/2 of the packed row; never overtakes the unread scores
+      }
+#pragma unroll
+      for (int j = (XA_KEYS - 64) / 2; j < 32; j++) sr[1][j] = 0u;
+      // P may be overwritten: the P V product of this group's previous tile has retired (its O was read out below)
+      tmem_st32(tP, sr[0]);
+      tmem_st32(tP + 32, sr[1]);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_ready[grp]);
+      // ---- O = P V  ->  fp16  ->  staging tile  ->  TMA store
+      mbar_wait(&o_full[grp], m & 1u);
+      __syncwarp();
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      tmem_ld32(tO, o0);
+      tmem_ld32(tO + 32, o1);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&o_free[grp]);
+      if (q == 2 && lane == 0) tma_store_wait_read0();       // the previous store of this group has read the staging tile
+      __syncwarp();
+      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+      uint8_t* stg = myOut + row * 128;
+#pragma unroll
+      for (int jj = 0; jj < 4; jj++) {
+        *reinterpret_cast<uint4*>(stg + ((jj ^ (row & 7)) << 4)) =
+            make_uint4(pack_half2(__uint_as_float(o0[8 * jj]), __uint_as_float(o0[8 * jj + 1])),
+                       pack_half2(__uint_as_float(o0[8 * jj + 2]), __uint_as_float(o0[8 * jj + 3])),
+                       pack_half2(__uint_as_float(o0[8 * jj + 4]), __uint_as_float(o0[8 * jj + 5])),
+                       pack_half2(__uint_as_float(o0[8 * jj + 6]), __uint_as_float(o0[8 * jj + 7])));
+        *reinterpret_cast<uint4*>(stg + (((jj + 4) ^ (row & 7)) << 4)) =
+            make_uint4(pack_half2(__uint_as_float(o1[8 * jj]), __uint_as_float(o1[8 * jj + 1])),
+                       pack_half2(__uint_as_float(o1[8 * jj + 2]), __uint_as_float(o1[8 * jj + 3])),
+                       pack_half2(__uint_as_float(o1[8 * jj + 4]), __uint_as_float(o1[8 * jj + 5])),
+                       pack_half2(__uint_as_float(o1[8 * jj + 6]), __uint_as_float(o1[8 * jj + 7])));
+      }
+      fence_proxy_async_smem();
+      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (q == 2 && lane == 0) {
+        tma_store_5d(&tmO, myOut, head * 64, (qt0 + k.t) * 128, f, 0, 0);
+        tma_store_commit();
+      }
+      __syncwarp();
+      xa_next(p, k);
+      if (xa_valid(p, k)) xa_next(p, k);
+    }
+    if (q == 2 && lane == 0) tma_store_wait_read0();
+    __syncwarp();
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// merged cross-attention operands of one SpatialTransformer (see the header comment)
+__global__ void xattn_pack_kernel(const __half* __restrict__ text /*[N][77][2C]*/, const __half* __restrict__ img /*[F][16][2C]*/,
+                                  __half* __restrict__ K /*[F][96][C]*/, __half* __restrict__ VT /*[F][C][128]*/, int F, int T,
+                                  int C) {
+  const int f = blockIdx.y;
+  const int n = f / T;
+  const int64_t nk = (int64_t)XA_KEYS * C, nv = (int64_t)C * 128;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nk + nv; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < nk) {
+      const int r = i / C, c = i % C;
+      __half v = __float2half_rn(0.f);
+      if (r < XA_TEXT) v = text[((int64_t)n * XA_TEXT + r) * 2 * C + c];
+      else if (r >= XA_IMG0) v = img[((int64_t)f * 16 + (r - XA_IMG0)) * 2 * C + c];
+      K[(int64_t)f * nk + i] = v;
+    } else {
+      const int64_t j2 = i - nk;
+      const int c = j2 / 128, j = j2 % 128;
+      __half v = __float2half_rn(0.f);
+      if (j < XA_TEXT) v = text[((int64_t)n * XA_TEXT + j) * 2 * C + C + c];
+      else if (j >= XA_IMG0 && j < XA_KEYS) v = img[((int64_t)f * 16 + (j - XA_IMG0)) * 2 * C + C + c];
+      VT[(int64_t)f * nv + j2] = v;
+    }
+  }
+}
+
+}  // namespace
+
+void xattn_pack(const __half* text_kv, const __half* img_kv, __half* K, __half* VT, int F, int T, int C, cudaStream_t st) {
+  dim3 grid(32, F);
+  xattn_pack_kernel<<<grid, 256, 0, st>>>(text_kv, img_kv, K, VT, F, T, C);
+  MUDG_CUDA(cudaGetLastError());
+}
+
+void xattn_per_frame(const XattnArgs& a, cudaStream_t st) {
+  MUDG_REQUIRE(a.q_pitch % 8 == 0 && a.o_pitch % 8 == 0 && a.heads >= 1 && a.Nq >= 1 && a.F >= 1, "xattn: arguments");
+  const int C = a.heads * 64;
+  auto rows_map = [&](const __half* base, int pitch) {
+    const uint64_t dims[5] = {(uint64_t)C, (uint64_t)a.Nq, (uint64_t)a.F, 1, 1};
+    const uint64_t pb = (uint64_t)pitch * 2;
+    const uint64_t str[4] = {pb, pb * a.Nq, pb * a.Nq * a.F, pb * a.Nq * a.F};
+    const uint32_t box[5] = {64, 128, 1, 1, 1};
+    return get_tmap(base, dims, str, box);
+  };
+  const CUtensorMap* mq = rows_map(a.Q, a.q_pitch);
+  const CUtensorMap* mo = rows_map(a.O, a.o_pitch);
+  const CUtensorMap* mk;
+  const CUtensorMap* mv;
+  {
+    const uint64_t dims[5] = {(uint64_t)C, XA_KEYS, (uint64_t)a.F, 1, 1};
+    const uint64_t pb = (uint64_t)C * 2;
+    const uint64_t str[4] = {pb, pb * XA_KEYS, pb * XA_KEYS * a.F, pb * XA_KEYS * a.F};
+    const uint32_t box[5] = {64, XA_KEYS, 1, 1, 1};
+    mk = get_tmap(a.K, dims, str, box);
+  }
+  {
+    const uint64_t dims[5] = {128, (uint64_t)C, (uint64_t)a.F, 1, 1};
+    const uint64_t str[4] = {256, 256ull * C, 256ull * C * a.F, 256ull * C * a.F};
+    const uint32_t box[5] = {64, 64, 1, 1, 1};
+    mv = get_tmap(a.VT, dims, str, box);
+  }
+  XaParams p{};
+  p.heads = a.heads;
+  p.qtiles = (a.Nq + 127) / 128;
+  // enough units to balance the SMs (>= 8 per SM when the problem allows), each long enough to amortise its K / V^T load
+  const int64_t fh = (int64_t)a.F * a.heads;
+  int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(p.qtiles, ((int64_t)sm_count() * 8 + fh - 1) / fh));
+  p.tpu = (p.qtiles + chunks - 1) / chunks;
+  p.chunks = (p.qtiles + p.tpu - 1) / p.tpu;
+  const int64_t units = fh * p.chunks;
+  MUDG_REQUIRE(units < (int64_t(1) << 30), "xattn: too many units");
+  p.units = (int)units;
+  p.scale_log2 = a.scale * 1.4426950408889634f;
+  static bool attr = false;
+  if (!attr) {
+    MUDG_CUDA(cudaFuncSetAttribute(xattn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XA_SMEM));
+    attr = true;
+  }
+  const int grid = (int)std::min<int64_t>(units, sm_count());
+  xattn_kernel<<<grid, XA_THREADS, XA_SMEM, st>>>(*mq, *mo, *mk, *mv, p);
+  MUDG_CUDA(cudaGetLastError());
+}
+
+}  // namespace mudg

@@ -60,6 +60,10 @@ CASES = {
     "geglu_ln_small": (1, 1, 1, 2048, 64, 512, 0, 0, 1, 0, 1, 1, 1.0, 2),
 }
 PAIR_CASES = [k for k in CASES if k.startswith("pair_")]
+# cases that also request the fused GroupNorm statistics of their output: name -> frames per GroupNorm sample
+# (1 = per-frame norm, T = TemporalConvBlock norm over (C/32, T, H, W)); the conv modes flatten (B, T) like the model does
+GN_CASES = {"pair_conv_l0_emb": 1, "pair_conv_l0_res": 16, "pair_conv_l0_cat": 1, "pair_tconv_l0_res": 1, "pair_tconv_l0": 16,
+            "pair_conv_l1_cat": 1, "conv3x3_l0": 1}
 
 
 def run_case(name, backends=((1, "simt"), (0, "tc"))):
@@ -131,8 +135,15 @@ def run_case(name, backends=((1, "simt"), (0, "tc"))):
     if R is not None:
         y = y + R.float()
     out = {}
+    gn_div = GN_CASES.get(name)
+    n_samples = (B * T) // gn_div if gn_div else 0
     for backend, label in backends:
         D = torch.full((B, T, H, W, n_out), float("nan"), device=dev).half()
+        gn_sums = None
+        if gn_div and backend == 0:
+            gn_sums = torch.zeros(n_samples, 32, 2, device=dev, dtype=torch.float64)
+            check(L.mudg_test_set_knob(b"gn_fuse", 2))      # also the 3-tap convs (the product only fuses 9-tap ones: slack)
+            check(L.mudg_test_next_gemm_gn(ptr(gn_sums), gn_div))
         torch.cuda.synchronize()
         t0 = time.time()
         rc = L.mudg_test_tapgemm(ptr(A), B, T, H, W, Cin, mode, ptr(Wt), N, ptr(D), ptr(R),
@@ -140,13 +151,21 @@ def run_case(name, backends=((1, "simt"), (0, "tc"))):
                                  ctypes.c_float(alpha), int(geglu), ptr(ln_stats), ptr(ln_c1), backend, cur_stream())
         check(rc)
         torch.cuda.synchronize()
+        check(L.mudg_test_set_knob(b"reset", 0))
         path = int(L.mudg_test_last_gemm_path()) if backend == 0 else 0
         err = (D.float() - y).abs()
         nan = int(torch.isnan(D.float()).sum())
         emax = float(err[~torch.isnan(err)].max()) if nan < err.numel() else float("nan")
         out[label] = (emax, nan)
         if backend == 0:
-            out["_path"] = (path, want_path)
+            out["_path"] = (path & 0xffff, want_path)
+            if gn_sums is not None:
+                # fused GroupNorm statistics against fp64 sums of the fp16 output the kernel stored
+                d64 = D.double().reshape(n_samples, -1, 32, n_out // 32)
+                want = torch.stack([d64.sum(dim=(1, 3)), (d64 * d64).sum(dim=(1, 3))], dim=-1)
+                rel = float(((gn_sums - want).abs() / (want.abs() + 1e-3 * want.abs().max())).max())
+                out["_gn"] = (bool(path >> 16), rel)
+                print(f"{name:18s} fused GroupNorm statistics: taken={bool(path >> 16)} max rel err {rel:.2e}", flush=True)
         print(f"{name:18s} {label:5s} max|d|={emax:.5f} mean|d|={float(err.nan_to_num().mean()):.6f} nans={nan} "
               f"ref_absmax={float(y.abs().max()):.3f} path={path & 255} epi={(path >> 8) - 1} ({(time.time() - t0) * 1e3:.1f} ms)", flush=True)
         if label.startswith("tc") and (emax > 0.05 or nan):

@@ -83,6 +83,23 @@ def run_case(name):
                                     f32(0.125), backend, cur_stream()))
             torch.cuda.synchronize()
             report(name, label, O, ref)
+    elif name.startswith("xattn"):
+        # merged 96-key cross-attention kernel (per-frame context): ragged / small, BASELINE level 0 and level 3 sizes
+        N, T, HW, heads = {"xattn_small": (2, 4, 320, 5), "xattn_ragged": (1, 3, 200, 2), "xattn_l0": (2, 16, 9216, 5),
+                           "xattn_l3": (2, 16, 144, 20), "xattn_one_tile": (1, 2, 64, 1)}[name]
+        C = heads * 64
+        F = N * T
+        q = (2.0 * torch.randn(F, HW, C, device=dev)).half()
+        kv_t = torch.randn(N, 77, 2 * C, device=dev).half()
+        kv_i = torch.randn(F, 16, 2 * C, device=dev).half()
+        kt = kv_t[..., :C].repeat_interleave(T, 0); vt = kv_t[..., C:].repeat_interleave(T, 0)
+        ref = torch.cat([ref_attn(q[f:f + 1], kt[f:f + 1], vt[f:f + 1], heads, 0.125) +
+                         ref_attn(q[f:f + 1], kv_i[f:f + 1, :, :C], kv_i[f:f + 1, :, C:], heads, 0.125) for f in range(F)])
+        for rep in range(2):                      # twice: the merged operands are rebuilt into the same scratch buffers
+            O = torch.full((F, HW, C), float("nan"), device=dev).half()
+            check(L.mudg_test_xattn(ptr(q), ptr(O), F, T, HW, heads, ptr(kv_t), ptr(kv_i), f32(0.125), cur_stream()))
+            torch.cuda.synchronize()
+            report(name, f"tc{rep}", O, ref)
     elif name.startswith("tattn"):
         T = int(name[5:])
         B, HW, heads = 2, 37, 5

@@ -47,6 +47,12 @@ def test_tapgemm(case):
     import gpu_probe_gemm as P
     out = P.run_case(case)
     path, want = out.pop("_path")
+    gn = out.pop("_gn", None)
+    if gn is not None:          # GroupNorm statistics of the output, accumulated by the pair kernel's epilogue
+        taken, rel = gn
+        assert taken == case.startswith("pair_"), (case, taken)
+        if taken:
+            assert rel < 1e-5, (case, "fused GroupNorm statistics", rel)
     if want is not None:
         assert (path & 255) == (want & 255), (case, "kernel", path & 255, "expected", want & 255)
         if want >> 8:
@@ -56,6 +62,7 @@ def test_tapgemm(case):
 
 
 @pytest.mark.parametrize("case", ["flash_self_small", "flash_self_l1", "flash_self_ragged", "flash_cross", "flash_cross_else",
+                                  "xattn_small", "xattn_ragged", "xattn_l0", "xattn_l3", "xattn_one_tile",
                                   "tattn16", "tattn4", "tattn64", "gn_frame", "gn_time", "ln320", "ln1280", "ln512"])
 def test_ops(case):
     import gpu_probe_ops as P
