@@ -35,10 +35,38 @@ SHAPES = [
 ]
 
 
+# MDM512 (config 2, N = 1, T = 16, 40x64 latent): mid-size problems around the single-CTA / CTA-pair switch-over
+SHAPES_512 = [
+    ("512 conv3 L0 320->320", 1, 16, 40, 64, 320, 320, 1, 1, 0),
+    ("512 tconv L0 320", 1, 16, 40, 64, 320, 320, 2, 0, 0),
+    ("512 lin L0 320->320 +res", 1, 1, 1, 40960, 320, 320, 0, 1, 0),
+    ("512 lin L0 320->960 qkv", 1, 1, 1, 40960, 320, 960, 0, 0, 0),
+    ("512 lin L0 320->2560 geglu", 1, 1, 1, 40960, 320, 2560, 0, 0, 1),
+    ("512 lin L0 1280->320 +res", 1, 1, 1, 40960, 1280, 320, 0, 1, 0),
+    ("512 conv3 L1 640->640", 1, 16, 20, 32, 640, 640, 1, 1, 0),
+    ("512 lin L1 640->1920 qkv", 1, 1, 1, 10240, 640, 1920, 0, 0, 0),
+    ("512 lin L1 640->5120 geglu", 1, 1, 1, 10240, 640, 5120, 0, 0, 1),
+    ("512 lin L1 640->640 +res", 1, 1, 1, 10240, 640, 640, 0, 1, 0),
+    ("512 conv3 L2 1280->1280", 1, 16, 10, 16, 1280, 1280, 1, 1, 0),
+    ("512 lin L2 1280->10240 geglu", 1, 1, 1, 2560, 1280, 10240, 0, 0, 1),
+    ("512 lin L2 1280->1280 +res", 1, 1, 1, 2560, 1280, 1280, 0, 1, 0),
+    ("512 conv3 L3 1280->1280", 1, 16, 5, 8, 1280, 1280, 1, 1, 0),
+]
+
+
 def main():
     dev = "cuda"
     L = test_lib()
+    global SHAPES
+    knob = b"gemm_epi"
     backends = [(0, "tc")]
+    vals = {"tc": 1}
+    if len(sys.argv) > 1 and sys.argv[1] == "mdm512":
+        # columns: single-CTA kernel forced, CTA-pair kernel forced (knob gemm_pair), the product heuristic
+        SHAPES, knob = SHAPES_512, b"gemm_pair"
+        backends = [(0, "single"), (0, "pair"), (0, "auto")]
+        vals = {"single": 0, "pair": 1, "auto": -1}
+        sys.argv = sys.argv[:1]
     print(f"{'shape':28s} " + " ".join(f"{n:>8s}us {n:>6s}TF" for _, n in backends))
     only = sys.argv[1] if len(sys.argv) > 1 else None
     for name, B, T, H, W, Cin, N, mode, res, geglu in SHAPES:
@@ -54,6 +82,8 @@ def main():
         flops = 2.0 * B * T * H * W * N * ntaps * Cin
         row = f"{name:28s} "
         for backend, bn in backends:
+            check(L.mudg_test_set_knob(knob, vals[bn]))
+
             def run():
                 check(L.mudg_test_tapgemm(ptr(A), B, T, H, W, Cin, mode, ptr(Wt), N, ptr(D), ptr(R), ptr(bias), None,
                                           ctypes.c_int(1), ctypes.c_int(0), ctypes.c_float(1.0), int(geglu), None, None, backend, cur_stream()))

@@ -151,8 +151,8 @@ def run_case(name, backends=((1, "simt"), (0, "tc"))):
                                  ctypes.c_float(alpha), int(geglu), ptr(ln_stats), ptr(ln_c1), backend, cur_stream())
         check(rc)
         torch.cuda.synchronize()
-        check(L.mudg_test_set_knob(b"reset", 0))
         path = int(L.mudg_test_last_gemm_path()) if backend == 0 else 0
+        check(L.mudg_test_set_knob(b"reset", 0))
         err = (D.float() - y).abs()
         nan = int(torch.isnan(D.float()).sum())
         emax = float(err[~torch.isnan(err)].max()) if nan < err.numel() else float("nan")
