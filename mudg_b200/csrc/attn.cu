@@ -38,10 +38,11 @@ struct FaParams {
 //   P = 2^(s - m) is written back to TMEM as packed fp16, O stays in TMEM across kv blocks; the running max is only
 //   raised when it grows by > 2^8 (lazy rescale: P <= 256 fits fp16), in which case the warp rescales its O rows
 //   in place (tcgen05.ld/st); the row sum l is a register.
-constexpr int F2_THREADS = 320;
+constexpr int F2_THREADS = 320;                     // SPLIT 1; SPLIT 2 runs 64 + 2 x 256 = 576 threads
 constexpr int F2_KV_STAGES = 5;
 // Q0,Q1 (reused as the two output staging tiles once every S MMA of the tile has retired) + the K / V^T ring
-constexpr int F2_SMEM = 2 * TILE + F2_KV_STAGES * 2 * TILE + 1024 + 256;
+constexpr int F2_XCH = 2 * 2 * 2 * 128 * 4;         // SPLIT 2: row max / row sum exchange [parity][group][half][row] fp32
+constexpr int F2_SMEM = 2 * TILE + F2_KV_STAGES * 2 * TILE + 1024 + 256 + F2_XCH;
 constexpr float F2_LAZY = 8.0f;
 
 #define F2_TRACE(role, blk, ev)                                                                        \
@@ -50,8 +51,15 @@ constexpr float F2_LAZY = 8.0f;
       p.trace[((role) * 96 + (blk)) * 8 + (ev)] = clock64();                                            \
   } while (0)
 
-template <int NSEG, int F2_POLY>
-__global__ void __launch_bounds__(F2_THREADS, 1)
+// SPLIT = softmax warps per TMEM lane quarter and group.  SPLIT 2 (long self-attention): a row's 128 scores of a block are
+// halved between two warps (they may both touch the quarter's 32 TMEM lanes), 8 warps per group, 576 threads, so FOUR
+// softmax warps sit on every SM sub-partition instead of two.  Why: the MUFU unit needs 2-4 resident issuing warps per
+// sub-partition to reach its 16 ex2/clk/SM (tests/gpu_probe_mufu.py: 1 warp 10.5, 2 warps 14.4, 4 warps 16.0) and the
+// exponent phase of SPLIT 1 runs ONE warp per sub-partition at 10.8 clk per MUFU op.  The halves agree on the row max
+// through shared memory (one group barrier per block), keep partial row sums (added once per segment), and each rescales /
+// reads out its 32 of the 64 O columns.
+template <int NSEG, int F2_POLY, int SPLIT>
+__global__ void __launch_bounds__(64 + SPLIT * 256, 1)
 flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmO,
               const __grid_constant__ CUtensorMap tmK0, const __grid_constant__ CUtensorMap tmV0,
               const __grid_constant__ CUtensorMap tmK1, const __grid_constant__ CUtensorMap tmV1, const FaParams p) {
@@ -70,6 +78,7 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   uint64_t* s_free = o_done + 2;                       // [2]  S tile copied to registers -> TMEM tile reusable
   uint64_t* exp_done = s_free + 2;                     // [2]  group i has finished the exponentials of a block (MUFU turn)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(exp_done + 2);
+  float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2 parity][2 groups][2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 256, head = blockIdx.y, f = blockIdx.z;
@@ -78,9 +87,9 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     mbar_init(q_full, 1);
     for (int i = 0; i < F2_KV_STAGES; i++) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int i = 0; i < 2; i++) {
-      mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); mbar_init(&o_done[i], 1); mbar_init(&s_free[i], 128);
+      mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128 * SPLIT); mbar_init(&o_done[i], 1); mbar_init(&s_free[i], 128 * SPLIT);
     }
-    mbar_init(&exp_done[0], 128); mbar_init(&exp_done[1], 128);
+    mbar_init(&exp_done[0], 128 * SPLIT); mbar_init(&exp_done[1], 128 * SPLIT);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -196,6 +205,148 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       }
       if (!progress) __nanosleep(64);
     }
+  } else if (SPLIT == 2) {
+    // ---------------- SPLIT 2: 8 warps per group; warp (q, half) owns columns [64 half, 64 half + 64) of rows 32 q .. 32 q + 31
+    const int grp = (warp - 2) >> 3;
+    const int half = ((warp - 2) >> 2) & 1;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t tS = tmem_base + grp * 128 + half * 64 + lane_off;
+    const uint32_t tO = tmem_base + 256 + grp * 64 + half * 32 + lane_off;
+    const uint32_t tP = tmem_base + 384 + grp * 64 + half * 32 + lane_off;
+    uint8_t* myOut = sOut + grp * TILE;
+    auto group_sync = [&]() {                        // the 256 threads of this group
+      if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+      else asm volatile("bar.sync 2, 256;" ::: "memory");
+    };
+    auto xslot = [&](int parity, int h) { return xch + ((parity * 2 + grp) * 2 + h) * 128 + row; };
+    float m_used = -INFINITY, l_run = 0.f;
+    const int nb1 = nblk[0];
+#pragma unroll 1
+    for (int it = 0; it < nb1; it++) {
+      const int valid = p.len[0] - it * 128 - half * 64;      // my columns >= valid are padding (TMA zero fill)
+      mbar_wait(&s_full[grp], it & 1);
+      __syncwarp();
+      tc_fence_after();
+      uint32_t sr[2][32];
+      tmem_ld32(tS, sr[0]);
+      tmem_ld32(tS + 32, sr[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_free[grp]);
+      float mx = -INFINITY;
+      if (valid >= 64) {
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+#pragma unroll
+          for (int i = 0; i < 32; i += 2)
+            m4[(i >> 1) & 3] = fmaxf(m4[(i >> 1) & 3], fmaxf(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])));
+        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+#pragma unroll
+          for (int i = 0; i < 32; i++)
+            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(sr[c][i]));
+      }
+      // the two halves of a row agree on the block's row max (slots double-buffered by block parity)
+      *xslot(it & 1, half) = mx;
+      group_sync();
+      mx = fmaxf(mx, *xslot(it & 1, half ^ 1));
+      if (do_stagger) {
+        if (grp == 1) mbar_wait(&exp_done[0], (uint32_t)it & 1u);
+        else if (it > 0) mbar_wait(&exp_done[1], (uint32_t)(it - 1) & 1u);
+        __syncwarp();
+      }
+      mx *= p.scale_log2;
+      const bool grow = (it > 0) && (mx > m_used + F2_LAZY);
+      const float m_old = m_used;
+      if (it == 0 || grow) m_used = mx;
+      float lsum = 0.f;
+      if (valid >= 64) {
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float a0 = fmaf(__uint_as_float(sr[c][i]), p.scale_log2, -m_used);
+            const float a1 = fmaf(__uint_as_float(sr[c][i + 1]), p.scale_log2, -m_used);
+            const float p0 = (F2_POLY == 3 && (i & 2)) ? ex2_poly(a0) : ex2_approx(a0);
+            const float p1 = ((F2_POLY == 1 && (i & 2)) || F2_POLY >= 2) ? ex2_poly(a1) : ex2_approx(a1);
+            l4[(i >> 1) & 3] += p0 + p1;
+            sr[c][i >> 1] = pack_half2(p0, p1);
+            if (i == 30 && c == 0 && do_stagger && p.stagger >= 2 && p.stagger <= 4) mbar_arrive_after(&exp_done[grp], sr[c][15]);
+          }
+        lsum = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = (c * 32 + i < valid) ? ex2_approx(fmaf(__uint_as_float(sr[c][i]), p.scale_log2, -m_used)) : 0.f;
+            const float p1 = (c * 32 + i + 1 < valid) ? ex2_approx(fmaf(__uint_as_float(sr[c][i + 1]), p.scale_log2, -m_used)) : 0.f;
+            lsum += p0 + p1;
+            sr[c][i >> 1] = pack_half2(p0, p1);
+          }
+      }
+      if (do_stagger && (p.stagger == 1 || p.stagger > 4 || valid < 64)) mbar_arrive(&exp_done[grp]);
+      if (it > 0) {                                  // the previous P V of this tile has retired: P and O may be touched
+        mbar_wait(&o_done[grp], (it - 1) & 1);
+        __syncwarp();
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, grow)) {         // both halves see the same row maxima, hence the same decision
+          const float factor = ex2_approx(m_old - m_used);
+          l_run *= factor;
+          uint32_t v[32];
+          tmem_ld32(tO, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++) v[i] = __float_as_uint(__uint_as_float(v[i]) * factor);
+          tmem_st32(tO, v);
+        }
+      }
+      l_run += lsum;
+      {
+        uint32_t w[32];                              // my 64 keys = 32 packed words = P columns [32 half, 32 half + 32)
+#pragma unroll
+        for (int i = 0; i < 16; i++) { w[i] = sr[0][i]; w[16 + i] = sr[1][i]; }
+        tmem_st32(tP, w);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_ready[grp]);
+    }
+    // ---- O / l: the halves add their partial row sums, each reads out its 32 of the 64 O columns
+    mbar_wait(&o_done[grp], (nb1 - 1) & 1);
+    __syncwarp();
+    tc_fence_after();
+    *xslot(nb1 & 1, half) = l_run;
+    group_sync();
+    const float inv = 1.f / (l_run + *xslot(nb1 & 1, half ^ 1));
+    uint32_t v[32];
+    tmem_ld32(tO, v);
+    tmem_ld_wait();
+    tc_fence_before();
+    uint8_t* stg = myOut + row * 128;
+#pragma unroll
+    for (int jj = 0; jj < 4; jj++) {
+      const uint4 val = make_uint4(pack_half2(__uint_as_float(v[8 * jj]) * inv, __uint_as_float(v[8 * jj + 1]) * inv),
+                                   pack_half2(__uint_as_float(v[8 * jj + 2]) * inv, __uint_as_float(v[8 * jj + 3]) * inv),
+                                   pack_half2(__uint_as_float(v[8 * jj + 4]) * inv, __uint_as_float(v[8 * jj + 5]) * inv),
+                                   pack_half2(__uint_as_float(v[8 * jj + 6]) * inv, __uint_as_float(v[8 * jj + 7]) * inv));
+      *reinterpret_cast<uint4*>(stg + (((half * 4 + jj) ^ (row & 7)) << 4)) = val;
+    }
+    fence_proxy_async_smem();
+    group_sync();
+    if (((warp - 2) & 7) == 0 && lane == 0) {        // first warp of each group
+      tma_store_5d(&tmO, myOut, head * 64, q0 + grp * 128, f, 0, 0);
+      tma_store_commit();
+      tma_store_wait_read0();
+    }
+    __syncwarp();
+    tc_fence_before();
   } else {
     const int grp = (warp - 2) >> 2;                 // query tile handled by this softmax group
     const int q = warp & 3;
@@ -697,7 +848,7 @@ void flash_attention(const FlashArgs& a, cudaStream_t st) {
   FaParams p{};
   p.nseg = a.nseg;
   p.scale_log2 = a.scale * 1.4426950408889634f;
-  p.stagger = knobs().flash_stagger;
+  p.stagger = knobs().flash_stagger;      // (-1: 3 for SPLIT 1, 1 for SPLIT 2 -- set below once the split is known)
   p.trace = g_flash_trace;
   for (int i = 0; i < 2; i++) {
     const FlashSeg& s = a.seg[i < a.nseg ? i : 0];
@@ -710,22 +861,31 @@ void flash_attention(const FlashArgs& a, cudaStream_t st) {
   }
   static bool attr = false;
   if (!attr) {
-    MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
-    MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
-    MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
-    MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
-    MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
+    MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
+    MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
+    MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<1, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
+    MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<1, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
+    MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<1, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
+    MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<2, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
     attr = true;
   }
   // Polynomial exp2 offload (FA4 trick).  Measured on B200 (tests/gpu_bench_flash.py): 5.49 ms vs 4.99 ms without it at
   // 9216 tokens -- the exponent phase is latency-bound at this occupancy, so it stays off (knob flash_poly).
   const int poly = a.nseg == 1 ? knobs().flash_poly : 0;
   dim3 grid((a.Nq + 255) / 256, a.heads, a.F);
-  if (a.nseg == 2) flash2_kernel<2, 0><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
-  else if (poly == 1) flash2_kernel<1, 1><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
-  else if (poly == 2) flash2_kernel<1, 2><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
-  else if (poly == 3) flash2_kernel<1, 3><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
-  else flash2_kernel<1, 0><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
+  // two softmax warps per TMEM lane quarter (SPLIT 2) for the long self-attentions; knob flash_split = 1 | 2 forces
+  const int nb_total = (p.len[0] + 127) / 128;
+  int split = (a.nseg == 1 && nb_total >= 4) ? 2 : 1;
+  if (knobs().flash_split == 1 || (knobs().flash_split == 2 && a.nseg == 1)) split = knobs().flash_split;
+  // MUFU hand-over point: measured best (level 0, 9216 keys) is "after half of the exponentials" with one softmax warp
+  // per sub-partition (4.93 ms) and "after all of them" with two (4.77 ms; 5.50 ms with the early hand-over)
+  if (p.stagger < 0) p.stagger = split == 2 ? 1 : 3;
+  if (a.nseg == 2) flash2_kernel<2, 0, 1><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
+  else if (split == 2 && poly == 1) flash2_kernel<1, 1, 2><<<grid, 576, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
+  else if (split == 2 && poly == 2) flash2_kernel<1, 2, 2><<<grid, 576, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
+  else if (split == 2) flash2_kernel<1, 0, 2><<<grid, 576, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
+  else if (poly == 1) flash2_kernel<1, 1, 1><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
+  else flash2_kernel<1, 0, 1><<<grid, F2_THREADS, F2_SMEM, st>>>(*mq, *mo, *mk[0], *mv[0], *mk[1], *mv[1], p);
   MUDG_CUDA(cudaGetLastError());
 }
 

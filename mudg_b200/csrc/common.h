@@ -86,12 +86,14 @@ struct Knobs {
   int gemm_pair = -1;       // -1 heuristic, 0 never, 1 always use the CTA-pair kernel (tapgemm_tc3)
   int gemm_sub = 0;         // 0 heuristic, 1 | 2: force the M sub-tile count of the single-CTA kernel (tapgemm_tc2)
   int gemm_epi = 1;         // compile-time epilogue variants of tapgemm_tc3 (0 = run-time variant only)
+  int gemm_groups = 0;      // epilogue groups of tapgemm_tc3: 0 per-shape rule, 2 | 3 forced
   int gemm_dbg = 0;         // bit 0: skip the output TMA stores, bit 1: release (not relaxed) accumulator hand-back
-  int flash_stagger = 3;    // MUFU hand-over point of the two softmax groups (0 off, 1 end, 2 / 3 / 4 after 3/4, 1/2, 1/4)
-  int flash_poly = 0;       // polynomial exp2 on every 4th element
+  int flash_stagger = -1;   // MUFU hand-over point of the two softmax groups (-1 per-split default, 0 off, 1 end, 2 / 3 / 4 after 3/4, 1/2, 1/4)
+  int flash_poly = 0;       // polynomial exp2 on 1/4 (1) or 1/2 (2) of the exponentials
+  int flash_split = 0;      // softmax warps per TMEM lane quarter: 0 heuristic (2 for self-attention over >= 512 keys), 1 | 2 forced
   int tattn_generic = 0;    // force the generic-T temporal attention kernel for T == 16
   int gn_fuse = 1;          // GroupNorm statistics from the producing GEMM's epilogue
-  int last_gemm_path = 0;   // written by tapgemm(): 2 = tc2<1>, 3 = tc2<2>, 4 = tc3; | (epi + 1) << 8
+  int last_gemm_path = 0;   // written by tapgemm(): 2 = tc2<1>, 3 = tc2<2>, 4 = tc3; | (epi + 1) << 8 | gn fused << 16 | groups << 20
 };
 Knobs& knobs();
 

@@ -460,14 +460,26 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 //   warp 0 producer (both CTAs; bytes are signalled on the LEADER's full barrier), warp 1 MMA issuer (leader only),
 //   warps 2-5 / 6-9: epilogue groups draining columns [0,128) / [128,256) of the CTA's rows (same fused epilogue as v2).
 // N is split into balanced tiles of whole 64-column units (128 for GEGLU): 320 -> 192+128, 640 -> 256+192+192.
-constexpr int G3_STAGES = 5;
+constexpr int G3_STAGES = 5;                              // NG 2 (see below); NG 3 runs 4 stages
 constexpr int G3_A_BYTES = BM * BK * 2;                   // 16 KB: this CTA's 128 pixels x 64 channels
 constexpr int G3_B_BYTES = 128 * BK * 2;                  // 16 KB: up to 128 weight rows (half of the N tile)
 constexpr int G3_STAGE_BYTES = G3_A_BYTES + G3_B_BYTES;
-constexpr int G3_STG_BYTES = 2 * 2 * 16384;              // per epilogue group: two 16 KB staging tiles (ping-pong)
-constexpr int G3_SMEM = G3_STAGES * G3_STAGE_BYTES + G3_STG_BYTES + 256;
-constexpr int G3_THREADS = 64 + 2 * 128;
-static_assert(G3_SMEM <= 232448, "pair GEMM must fit one SM");
+// NG = epilogue groups of 4 warps, each with two 16 KB staging tiles (ping-pong).
+//   NG 2: 320 threads, 5-stage operand ring: the long-K layers, whose epilogue hides behind the MMA main loop.
+//   NG 3: 512 threads -- warps 0-3 = {producer, issuer, 2 idle} shrink to 40 registers (setmaxnreg), the 12 epilogue warps grow
+//         to 152 --, 4-stage ring: the short-K Linear layers (K = 320 / 640), whose latency-bound epilogue (IPC 0.25) is the
+//         bottleneck at 4 700 clk per 256 x 256 tile against 1 300-2 600 clk of MMA.  Measured INSIDE the power-capped clip
+//         (SM clock 1.58 GHz): QKV 320->960 260 -> 210 us, GEGLU 320->2560 783 -> 686 us, 320->320+res 169 -> 156 us; in
+//         isolation at boost clocks the third group is a LOSS (profiles/r2_gemm_groups_ab.log), and so it is for the 3-tap
+//         temporal convs and the no-residual K = 640 layers in the clip -- hence the narrow selection rule in tapgemm_tc3().
+template <int NG> struct G3Cfg {
+  static constexpr int STAGES = NG == 2 ? G3_STAGES : 4;
+  static constexpr int STG_BYTES = NG * 2 * 16384;
+  static constexpr int SMEM = STAGES * G3_STAGE_BYTES + STG_BYTES + 256;
+  static constexpr int THREADS = NG == 2 ? 64 + 2 * 128 : 128 + 3 * 128;
+  static constexpr int EW0 = NG == 2 ? 2 : 4;          // first epilogue warp
+};
+static_assert(G3Cfg<2>::SMEM <= 232448 && G3Cfg<3>::SMEM <= 232448, "pair GEMM must fit one SM");
 
 struct G3Params {
   TcParams b;
@@ -548,28 +560,29 @@ __device__ __forceinline__ void gn_chunk_stats(const uint8_t* stg, int q, int la
 // >= 0: bit 0 bias, bit 1 per-sample bias, bit 2 residual, bit 3 folded LayerNorm, alpha == 1, no GEGLU.  Tested from the
 // kernel-parameter bank, every `if (p.b.bias ...)` in the 32-column slice loop is a dependent LDCU -> UISETP -> BRA.U chain of
 // 60-80 clocks that a lone, latency-bound epilogue warp cannot overlap with anything (clock64 trace: ~500 clk per slice).
-template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G3_THREADS, 1)
+template <int EPI, int NG>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G3Cfg<NG>::THREADS, 1)
 tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
                    const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmD,
                    const G3Params p) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   uint8_t* smem = smem_dyn;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  uint8_t* stg_all = smem + G3_STAGES * G3_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_all + G3_STG_BYTES);
+  constexpr int NST = G3Cfg<NG>::STAGES, EW0 = G3Cfg<NG>::EW0;
+  uint8_t* stg_all = smem + NST * G3_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_all + G3Cfg<NG>::STG_BYTES);
   uint64_t* full = bars;                        // [STAGES]  used in the leader CTA only
-  uint64_t* empty = bars + G3_STAGES;           // [STAGES]  one per CTA, signalled by the multicast commit
-  uint64_t* tmem_full = bars + 2 * G3_STAGES;   // [2]       one per CTA, multicast commit
-  uint64_t* tmem_empty = bars + 2 * G3_STAGES + 2;   // [2]  leader only: 2 CTAs x 2 epilogue groups arrive
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G3_STAGES + 4);
+  uint64_t* empty = bars + NST;                 // [STAGES]  one per CTA, signalled by the multicast commit
+  uint64_t* tmem_full = bars + 2 * NST;         // [2]       one per CTA, multicast commit
+  uint64_t* tmem_empty = bars + 2 * NST + 2;    // [2]  leader only: 2 CTAs x NG epilogue groups arrive
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < G3_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    for (int i = 0; i < NST; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * NG); }
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -584,7 +597,10 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int ktotal = p.b.ntaps * p.b.kchunks;
-
+  // NG 3: register re-partition between the warpgroups.  Each warpgroup executes its setmaxnreg at the top of a region
+  // that does not merge with the other's before the end of the kernel, so ptxas budgets the two regions separately.
+  if (warp < EW0) {
+  if (NG == 3) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0) {
     // The whole warp runs the loop so that addresses and coordinates stay in uniform registers; one elected lane
     // issues.  The body runs once per k-step (every 256-512 tensor clocks): no divisions, no modulo.
@@ -610,7 +626,7 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             tma_load_5d_pair(a_s + G3_A_BYTES, mb, full0 + 8u * s, kb, brow, 0, 0, 0);
           }
           __syncwarp();
-          if (++s == G3_STAGES) { s = 0; ph ^= 1u; }
+          if (++s == NST) { s = 0; ph ^= 1u; }
         }
       }
       if (lane == 0) G3_TRACE(0, plt, 1);                 // all loads of the tile issued
@@ -642,26 +658,29 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (k == ktotal - 1) umma_commit_pair(&tmem_full[acc], 3);
           }
           __syncwarp();
-          if (++s == G3_STAGES) { s = 0; ph ^= 1u; }
+          if (++s == NST) { s = 0; ph ^= 1u; }
         }
         if (lane == 0) G3_TRACE(1, lt, 3);                     // last MMA of the tile issued
       }
     }
+  }
   } else {
-    // Two epilogue groups of 4 warps (a warp may only touch TMEM lanes 32*(warp%4)..+32, so each group spans all 128
+    if (NG == 3) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    // NG epilogue groups of 4 warps (a warp may only touch TMEM lanes 32*(warp%4)..+32, so each group spans all 128
     // rows).  The tile's 64-column output chunks are dealt round-robin to the groups across tiles (a running chunk
-    // counter), so odd chunk counts (bn = 192) do not leave one group with twice the work.
-    const int grp = (warp - 2) >> 2;
+    // counter), so chunk counts that are no multiple of NG (bn = 192) do not leave one group with more work.
+    const int grp = (warp - EW0) >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const bool issuer = (((warp - 2) & 3) == 0 && lane == 0);
+    const bool issuer = (((warp - EW0) & 3) == 0 && lane == 0);
     uint8_t* stg_grp = stg_all + grp * 32768;   // two staging tiles: this group's n-th chunk uses tile n & 1
     uint32_t chunk_no = 0;                      // chunks this group has stored
-    uint32_t cc = 0;                            // chunks of all tiles so far (both groups)
+    uint32_t cc = 0;                            // chunks of all tiles so far (all groups), modulo NG
     auto group_sync = [&]() {
       if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-      else asm volatile("bar.sync 2, 128;" ::: "memory");
+      else if (grp == 1) asm volatile("bar.sync 2, 128;" ::: "memory");
+      else asm volatile("bar.sync 3, 128;" ::: "memory");
     };
     int r = row;
     const int iw = r % p.b.bw; r /= p.b.bw;
@@ -686,9 +705,9 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const uint32_t acc = lt & 1;
       const uint32_t empty_bar = mapa_u32(&tmem_empty[acc], 0);
       const int nchunks = tl.bn >> csh;
-      const int first = (int)((grp - cc) & 1u);                // my chunks: first, first + 2, ...
-      const int mine = first < nchunks ? (nchunks - first + 1) >> 1 : 0;
-      cc += (uint32_t)nchunks;
+      const int first = (grp + NG - (int)cc) % NG;             // my chunks: first, first + NG, ...
+      const int mine = first < nchunks ? (nchunks - first + NG - 1) / NG : 0;
+      cc = (cc + (uint32_t)nchunks) % NG;
       if (mine == 0) {
         mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
         if (issuer) arrive_empty(empty_bar);
@@ -707,7 +726,7 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         tc_fence_after();
 #pragma unroll 1
         for (int ci = 0; ci < mine; ci++) {
-          const int ch = first + 2 * ci;                       // chunk: accumulator columns [128 ch, 128 ch + 128)
+          const int ch = first + NG * ci;                      // chunk: accumulator columns [128 ch, 128 ch + 128)
           const int nbase = tl.n0 + ch * 128;
           uint8_t* stg = stg_grp + (chunk_no & 1) * 16384;
           uint8_t* srow = stg + row * 128;
@@ -786,7 +805,7 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (nw < p.dimW && nh_ < p.dimH && nt_ < p.b.dimT && nb_ < p.dimB) {
           const int64_t npix = (((int64_t)nb_ * p.b.dimT + nt_) * p.dimH + nh_) * p.dimW + nw;
           const __half* np_ = p.R + npix * p.b.n_out + nx.n0;
-          for (int c = grp; c < (nx.bn >> 6); c += 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(np_ + c * 64));
+          for (int c = grp; c < (nx.bn >> 6); c += NG) asm volatile("prefetch.global.L2 [%0];" ::"l"(np_ + c * 64));
         }
       }
       uint4 res_nxt[4];
@@ -794,29 +813,29 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
         for (int j = 0; j < 4; j++) res_nxt[j] = __ldg(rp + first * 8 + j);
       }
-      if (q == 2 && lane == 0) G3_TRACE(2 + grp, lt, 0);       // epilogue group ready for the tile
+      if (grp < 2 && q == 2 && lane == 0) G3_TRACE(2 + grp, lt, 0);       // epilogue group ready for the tile
       mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
       __syncwarp();
       tc_fence_after();
-      if (q == 2 && lane == 0) G3_TRACE(2 + grp, lt, 1);       // accumulator complete
+      if (grp < 2 && q == 2 && lane == 0) G3_TRACE(2 + grp, lt, 1);       // accumulator complete
       const int nslices = mine * 2;          // my 32-column slices, two per chunk
       // Two register sets for the accumulator slices: the tcgen05.ld of slice s+1 is in flight while slice s is converted
       // and staged (tcgen05.wait::ld covers every outstanding load, so the next one is issued right after the wait).
       // Only where it fits the 168-register cap without spilling (measured: with the residual registers, or in the
       // run-time variant that also carries the GEGLU path, the spills cost more than the overlap gains).
-      constexpr bool kPrefetchLd = EPI >= 0 && (EPI & 4) == 0;
+      constexpr bool kPrefetchLd = NG == 2 && EPI >= 0 && (EPI & 4) == 0;      // (NG 3 runs at 152 registers: no room)
       uint32_t va[32], vb[32];
       if (kPrefetchLd) tmem_ld32(t_row + first * 64, va);
       auto do_slice = [&](int sl, uint32_t (&v)[32], uint32_t (&vn)[32]) {
         const int hf = sl & 1;
-        const int ch = first + (sl >> 1) * 2;                  // chunk: accumulator / output columns [64 ch, 64 ch + 64)
+        const int ch = first + (sl >> 1) * NG;                 // chunk: accumulator / output columns [64 ch, 64 ch + 64)
         const int coff = ch * 64 + hf * 32;
         uint4 res[4];
         if (rp != nullptr) {
 #pragma unroll
           for (int j = 0; j < 4; j++) res[j] = res_nxt[j];
           if (sl + 1 < nslices) {
-            const int nch = first + ((sl + 1) >> 1) * 2;
+            const int nch = first + ((sl + 1) >> 1) * NG;
             const uint4* np4 = rp + nch * 8 + ((sl + 1) & 1) * 4;
 #pragma unroll
             for (int j = 0; j < 4; j++) res_nxt[j] = __ldg(np4 + j);
@@ -826,7 +845,7 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         uint8_t* srow = stg + row * 128;
         if (kPrefetchLd) {
           tmem_ld_wait_regs(v);
-          if (sl + 1 < nslices) tmem_ld32(t_row + (first + ((sl + 1) >> 1) * 2) * 64 + ((sl + 1) & 1) * 32, vn);
+          if (sl + 1 < nslices) tmem_ld32(t_row + (first + ((sl + 1) >> 1) * NG) * 64 + ((sl + 1) & 1) * 32, vn);
           else tc_fence_before();            // last TMEM read of this accumulator (released at the next group_sync)
         } else {
           tmem_ld32(t_row + coff, v);
@@ -902,7 +921,7 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
           }
           chunk_no++;
-          if (q == 2 && lane == 0) G3_TRACE(2 + grp, lt, 2 + (sl >> 1));   // chunk stored
+          if (grp < 2 && q == 2 && lane == 0) G3_TRACE(2 + grp, lt, 2 + (sl >> 1));   // chunk stored
         }
       };
 #pragma unroll 1
@@ -1023,7 +1042,9 @@ bool tapgemm_pair_wanted(const TapGemm& g, int64_t m_tiles, int nt128) {
   if (mode == 0) return false;
   if (mode == 1) return true;
   const int ktot_steps = g.ntaps * ((g.Cin + BK - 1) / BK);
-  return m_tiles * nt128 >= 8 * (int64_t)sm_count() && ktot_steps >= 4;
+  // switch-over measured on the MDM512 shapes (tests/gpu_bench_gemm.py mdm512): the pair kernel wins from about one
+  // 128 x 128 tile per SM upward (conv 3x3 1280 at 2 560 rows: 64.6 vs 77.9 us), the single-CTA kernel below (640 rows)
+  return m_tiles * nt128 >= (int64_t)sm_count() && ktot_steps >= 4;
 }
 
 bool tapgemm_tc3(const TapGemm& g, cudaStream_t st) {
@@ -1086,16 +1107,6 @@ bool tapgemm_tc3(const TapGemm& g, cudaStream_t st) {
   const CUtensorMap* mb0 = get_tmap(g.Wt, bdims, bstr, bbox0);
   const CUtensorMap* mb1 = get_tmap(g.Wt, bdims, bstr, bbox1);
   const CUtensorMap* md = get_tmap(g.D, ddims, dstr, abox);
-  static bool attr_set = false;
-  if (!attr_set) {
-    MUDG_CUDA(cudaFuncSetAttribute(tapgemm_tc3_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM));
-    MUDG_CUDA(cudaFuncSetAttribute(tapgemm_tc3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM));
-    MUDG_CUDA(cudaFuncSetAttribute(tapgemm_tc3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM));
-    MUDG_CUDA(cudaFuncSetAttribute(tapgemm_tc3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM));
-    MUDG_CUDA(cudaFuncSetAttribute(tapgemm_tc3_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM));
-    MUDG_CUDA(cudaFuncSetAttribute(tapgemm_tc3_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM));
-    attr_set = true;
-  }
   const int clusters = (int)std::min<int64_t>(total, sm_count() / 2);
   p.rot_div = FastDiv{0u, 0u, 0};
   if (p.nt > 1 && clusters % p.nt == 0) p.rot_div = make_fastdiv(clusters);
@@ -1104,16 +1115,38 @@ bool tapgemm_tc3(const TapGemm& g, cudaStream_t st) {
   int epi = -1;
   if (epi_on && !g.geglu && g.alpha == 1.f)
     epi = (g.bias ? 1 : 0) | (g.bias2 ? 2 : 0) | (g.R ? 4 : 0) | (g.ln_stats ? 8 : 0);
+  if (epi != 0 && epi != 1 && epi != 3 && epi != 5 && epi != 9) epi = -1;
+  // three epilogue groups (see G3Cfg) for the short-K Linear layers: K = 320 always, K = 640 when the epilogue carries a
+  // residual or GEGLU (measured per shape inside the clip); knob gemm_groups = 2 | 3 forces
+  const int ktot_steps = g.ntaps * p.b.kchunks;
+  int ng = (g.ntaps == 1 && (ktot_steps <= 5 || (ktot_steps <= 10 && (g.geglu || g.R != nullptr)))) ? 3 : 2;
+  if (knobs().gemm_groups == 2 || knobs().gemm_groups == 3) ng = knobs().gemm_groups;
   const dim3 grid(2 * clusters);
+#define MUDG_TC3_LAUNCH(E, G)                                                                                         \
+  do {                                                                                                                 \
+    static bool attr_done = false;                                                                                     \
+    if (!attr_done) {                                                                                                  \
+      MUDG_CUDA(cudaFuncSetAttribute(tapgemm_tc3_kernel<E, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, G3Cfg<G>::SMEM)); \
+      attr_done = true;                                                                                                \
+    }                                                                                                                  \
+    tapgemm_tc3_kernel<E, G><<<grid, G3Cfg<G>::THREADS, G3Cfg<G>::SMEM, st>>>(*ma, *mb0, *mb1, *md, p);                 \
+  } while (0)
+#define MUDG_TC3_EPI(E)                 \
+  do {                                  \
+    if (ng == 3) MUDG_TC3_LAUNCH(E, 3); \
+    else MUDG_TC3_LAUNCH(E, 2);         \
+  } while (0)
   switch (epi) {
-    case 0: tapgemm_tc3_kernel<0><<<grid, G3_THREADS, G3_SMEM, st>>>(*ma, *mb0, *mb1, *md, p); break;
-    case 1: tapgemm_tc3_kernel<1><<<grid, G3_THREADS, G3_SMEM, st>>>(*ma, *mb0, *mb1, *md, p); break;
-    case 3: tapgemm_tc3_kernel<3><<<grid, G3_THREADS, G3_SMEM, st>>>(*ma, *mb0, *mb1, *md, p); break;
-    case 5: tapgemm_tc3_kernel<5><<<grid, G3_THREADS, G3_SMEM, st>>>(*ma, *mb0, *mb1, *md, p); break;
-    case 9: tapgemm_tc3_kernel<9><<<grid, G3_THREADS, G3_SMEM, st>>>(*ma, *mb0, *mb1, *md, p); break;
-    default: epi = -1; tapgemm_tc3_kernel<-1><<<grid, G3_THREADS, G3_SMEM, st>>>(*ma, *mb0, *mb1, *md, p); break;
+    case 0: MUDG_TC3_EPI(0); break;
+    case 1: MUDG_TC3_EPI(1); break;
+    case 3: MUDG_TC3_EPI(3); break;
+    case 5: MUDG_TC3_EPI(5); break;
+    case 9: MUDG_TC3_EPI(9); break;
+    default: MUDG_TC3_EPI(-1); break;
   }
-  knobs().last_gemm_path = 4 | ((epi + 1) << 8) | (gn_fuse ? 1 << 16 : 0);
+#undef MUDG_TC3_EPI
+#undef MUDG_TC3_LAUNCH
+  knobs().last_gemm_path = 4 | ((epi + 1) << 8) | (gn_fuse ? 1 << 16 : 0) | (ng << 20);
   MUDG_CUDA(cudaGetLastError());
   return gn_fuse;
 }

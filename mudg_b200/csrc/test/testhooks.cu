@@ -295,8 +295,10 @@ MUDG_EXPORT int mudg_test_set_knob(const char* name, int value) {
   else if (n == "gemm_sub") k.gemm_sub = value;
   else if (n == "gemm_epi") k.gemm_epi = value;
   else if (n == "gemm_dbg") k.gemm_dbg = value;
+  else if (n == "gemm_groups") k.gemm_groups = value;
   else if (n == "flash_stagger") k.flash_stagger = value;
   else if (n == "flash_poly") k.flash_poly = value;
+  else if (n == "flash_split") k.flash_split = value;
   else if (n == "tattn_generic") k.tattn_generic = value;
   else if (n == "gn_fuse") k.gn_fuse = value;
   else if (n == "reset") k = Knobs{};

@@ -7,11 +7,12 @@ from mudg_b200._lib import test_lib, check, ptr, cur_stream   # noqa: E402
 
 def main():
     L = test_lib()
-    sweep = [(0, 3)] if len(sys.argv) < 2 else [(p_, s_) for p_ in (0, 1, 2, 3) for s_ in (0, 3, 4)]
-    for poly, stagger in sweep:
+    sweep = [(0, 3, 0)] if len(sys.argv) < 2 else [(p_, s_, sp) for sp in (1, 2) for p_ in (0, 1, 2) for s_ in (0, 1, 3)]
+    for poly, stagger, split in sweep:
         check(L.mudg_test_set_knob(b"flash_poly", poly))
         check(L.mudg_test_set_knob(b"flash_stagger", stagger))
-        print(f"-- flash_poly={poly} flash_stagger={stagger}", flush=True)
+        check(L.mudg_test_set_knob(b"flash_split", split))
+        print(f"-- flash_split={split} flash_poly={poly} flash_stagger={stagger}", flush=True)
         bench(L)
     check(L.mudg_test_set_knob(b"reset", 0))
 

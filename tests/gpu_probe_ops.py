@@ -47,7 +47,12 @@ def run_case(name):
     L = test_lib()
     f32 = ctypes.c_float
     if name.startswith("flash_self"):
-        F, Nq, heads = {"flash_self_small": (2, 256, 1), "flash_self_l1": (3, 2304, 10), "flash_self_ragged": (2, 200, 2)}[name]
+        # *_s1 / *_s2: softmax split forced (knob flash_split); long sequences take split 2 (8 warps per group) by default
+        F, Nq, heads = {"flash_self_small": (2, 256, 1), "flash_self_l1": (3, 2304, 10), "flash_self_ragged": (2, 200, 2),
+                        "flash_self_split_ragged": (2, 1000, 2), "flash_self_split_tail": (1, 650, 1),
+                        "flash_self_small_s2": (2, 256, 1), "flash_self_ragged_s2": (2, 200, 2), "flash_self_l1_s1": (3, 2304, 10),
+                        "flash_self_l0": (2, 9216, 5)}[name]
+        check(L.mudg_test_set_knob(b"flash_split", 2 if name.endswith("_s2") else 1 if name.endswith("_s1") else 0))
         C = heads * 64
         qkv = torch.randn(F, Nq, 3 * C, device=dev).half()
         ref = ref_attn(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], heads, 0.125)
@@ -59,6 +64,7 @@ def run_case(name):
                                     None, None, 0, 0, 0, 1, f32(0.125), backend, cur_stream()))
             torch.cuda.synchronize()
             report(name, label, O, ref)
+        check(L.mudg_test_set_knob(b"reset", 0))
     elif name.startswith("flash_cross"):
         N, T, HW, heads = 2, 4, 320, 5
         C = heads * 64

@@ -62,6 +62,8 @@ def test_tapgemm(case):
 
 
 @pytest.mark.parametrize("case", ["flash_self_small", "flash_self_l1", "flash_self_ragged", "flash_cross", "flash_cross_else",
+                                  "flash_self_split_ragged", "flash_self_split_tail", "flash_self_small_s2", "flash_self_ragged_s2",
+                                  "flash_self_l1_s1", "flash_self_l0",
                                   "xattn_small", "xattn_ragged", "xattn_l0", "xattn_l3", "xattn_one_tile",
                                   "tattn16", "tattn4", "tattn64", "gn_frame", "gn_time", "ln320", "ln1280", "ln512"])
 def test_ops(case):
