@@ -21,6 +21,9 @@ MUDG_EXPORT int mudg_test_last_gemm_path(void);   /* bit 16: GroupNorm statistic
 /* request GroupNorm statistics of the output from the NEXT mudg_test_tapgemm(backend 0) call: sums [S][32][2] fp64,
  * pre-zeroed; sample = (b*T + t) / gn_div */
 MUDG_EXPORT int mudg_test_next_gemm_gn(void* sums_f64, int gn_div);
+/* per-sample weight matrices for the NEXT mudg_test_tapgemm(backend 0) call: Wt is [samples][N][K], rows of sample
+ * (b*T + t) / div use matrix number that (TapGemm::wt_samples; the GroupNorm-into-proj_in fold) */
+MUDG_EXPORT int mudg_test_next_gemm_per_sample(int samples, int div);
 
 /* backend 0 = product dispatch (tcgen05), 1 = CUDA-core checker.  mode 0 linear, 1 conv 3x3, 2 temporal conv (3,1,1).
  * ln_stats ([rows] float2 mean,rstd) / ln_c1 ([N]): folded-LayerNorm epilogue (bias then carries W beta + bias), or NULL */

@@ -37,6 +37,12 @@ struct TapGemm {
   // 128-pixel tile cannot straddle samples); otherwise the caller runs gn_stats on the output.
   double* gn_sums = nullptr;
   int gn_div = 1;
+  // Per-sample weights: Wt is [wt_samples][N][ntaps*Cin] and the rows of sample (b*T + t) / wt_div use matrix number that.
+  // This is how a GroupNorm WITHOUT activation is folded into the Linear that consumes it (SpatialTransformer /
+  // TemporalTransformer norm -> proj_in): y = (x * scale_s + shift_s) W^T + b = x (W diag(scale_s))^T + (W shift_s + b), the
+  // second term arriving as bias2.  CTA-pair kernel only, and only when a 128-pixel tile cannot straddle samples:
+  // ask tapgemm_per_sample_ok() first.
+  int wt_samples = 0, wt_div = 1;
 };
 
 // generic-stride variant for the irregular layers (tiny Cin / tiny N, fp32 NCTHW in/out)
@@ -58,6 +64,7 @@ struct TapGemmGeneric {
 };
 
 bool tapgemm_tc_eligible(const TapGemm& g);
+bool tapgemm_per_sample_ok(const TapGemm& g);   // would tapgemm() run g (with wt_samples / wt_div set) on the pair kernel, tiles inside one sample?
 bool tapgemm_tc2(const TapGemm& g, cudaStream_t st);       // persistent single-CTA kernel, or the CTA-pair kernel for large problems
 void tapgemm_generic(const TapGemmGeneric& g, cudaStream_t st);
 // The product entry: tcgen05 path (+ optional per-launch timing).  Returns true when the GroupNorm statistics requested

@@ -458,6 +458,63 @@ Act Model::group_norm(const Act& x, const std::string& p, float eps, bool silu, 
   return y;
 }
 
+// proj_in(GroupNorm(x)) of the Spatial / Temporal transformers (attention.py:454-456, 532-540).  The norm has no activation,
+// so it is affine per (sample, channel) and folds into per-sample weights: the Linear reads the RAW activation and the
+// normalised tensor is never written (saves one read + one write of the activation per transformer).  Used when the GEMM runs
+// on the pair kernel with tiles inside one sample and the per-sample weights are small next to the activation; otherwise
+// the norm runs as its own pass.
+Act Model::linear_gn(const Act& x, const std::string& norm, float eps, bool over_time, const std::string& wkey,
+                     const std::string& bkey, GnReq* pre) {
+  const Weight& w = ws_->W(wkey);
+  const int S = over_time ? x.B : x.B * x.T;
+  const int64_t rps = over_time ? (int64_t)x.T * x.H * x.W : (int64_t)x.H * x.W;
+  TapGemm g;
+  g.A = x.p; g.B = x.B; g.T = x.T; g.H = x.H; g.W = x.W; g.Cin = x.C;
+  g.ntaps = 1;
+  g.Wt = w.w; g.N = w.O;                      // (pointers are placeholders until the buffers below exist: geometry check only)
+  g.D = x.p;
+  g.wt_samples = S; g.wt_div = over_time ? x.T : 1;
+  const bool small_weights = (int64_t)S * w.O * 2 <= x.rows();      // per-sample weights <= 1/2 of the activation bytes
+  const bool fold = knobs().gn_fold != 0 && w.taps == 1 && w.K() == x.C && x.C % 32 == 0 && small_weights &&
+                    (planning_ ? fold_plan_ok(g) : tapgemm_per_sample_ok(g));
+  if (!fold) {
+    Act n = group_norm(x, norm, eps, false, over_time, pre);
+    Act y = linear(n, wkey, bkey, nullptr);
+    release(n);
+    return y;
+  }
+  GnReq own;
+  if (pre == nullptr || pre->sums == nullptr) {
+    gn_request(own, S);
+    pre = &own;
+  }
+  Act y = alloc(x.B, x.T, x.H, x.W, w.O);
+  __half* Ws = static_cast<__half*>(alloc_bytes(sizeof(__half) * (size_t)S * w.O * w.K()));
+  float* cs = static_cast<float*>(alloc_bytes(sizeof(float) * (size_t)S * w.O));
+  if (live()) {
+    if (!pre->fused) {
+      ProfScope ps(PF_GN, 0.0, 2.0 * (double)x.numel(), st_, fmt("%lldx%d:stats", (long long)x.rows(), x.C).c_str());
+      gn_stats(x.p, S, rps, x.C, pre->sums, st_);
+      launches++;
+    }
+    {
+      ProfScope ps(PF_GN, 0.0, 0.0, st_, "fold_weights");
+      gn_fold_weights(w.w, pre->sums, S, rps, ws_->V(norm + ".weight").p, ws_->V(norm + ".bias").p, eps, Ws, cs, w.O, w.K(), st_);
+      launches++;
+    }
+    g.Wt = Ws; g.D = y.p;
+    g.bias = bkey.empty() ? nullptr : ws_->V(bkey).p;
+    g.bias2 = cs; g.bias2_div = g.wt_div; g.nb2 = S;
+    tapgemm(g, st_);
+    launches++;
+  }
+  release_bytes(Ws);
+  release_bytes(cs);
+  release_bytes(pre->sums);
+  pre->sums = nullptr;
+  return y;
+}
+
 Act Model::layer_norm(const Act& x, const std::string& p) {
   Act y = alloc(x.B, x.T, x.H, x.W, x.C);
   if (live()) {
@@ -657,9 +714,7 @@ Act Model::spatial_transformer(const Act& xin, const Layer& l, GnReq* in_gn) {  
   const std::string& p = l.prefix;
   const std::string tb = p + ".transformer_blocks.0";
   const int C = l.ch, HW = xin.H * xin.W;
-  Act g = group_norm(xin, p + ".norm", 1e-6f, false, false, in_gn);
-  Act x = linear(g, p + ".proj_in.weight", p + ".proj_in.bias", nullptr);
-  release(g);
+  Act x = linear_gn(xin, p + ".norm", 1e-6f, false, p + ".proj_in.weight", p + ".proj_in.bias", in_gn);
   // attn1: self-attention over the H*W tokens of each frame
   float2* s1 = layer_norm_stats(x);
   Act qkv = linear(x, tb + ".attn1.qkv.weight", "", nullptr, false, 1.f, s1);
@@ -752,9 +807,7 @@ Act Model::temporal_transformer(const Act& xin, const Layer& l) {   // attention
   const std::string& p = l.prefix;
   const std::string tb = p + ".transformer_blocks.0";
   const int HW = xin.H * xin.W;
-  Act g = group_norm(xin, p + ".norm", 1e-6f, false, true);
-  Act x = linear(g, p + ".proj_in.weight", p + ".proj_in.bias", nullptr);
-  release(g);
+  Act x = linear_gn(xin, p + ".norm", 1e-6f, true, p + ".proj_in.weight", p + ".proj_in.bias", nullptr);
   for (int k = 1; k <= 2; k++) {   // attn1 and attn2 are both self-attention over T (only_self_att)
     const std::string an = tb + ".attn" + std::to_string(k);
     float2* sk = layer_norm_stats(x);

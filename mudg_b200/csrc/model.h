@@ -163,6 +163,10 @@ class Model {
   };
   void gn_request(GnReq& r, int S);
   Act group_norm(const Act& x, const std::string& p, float eps, bool silu, bool over_time, GnReq* pre = nullptr);
+  Act linear_gn(const Act& x, const std::string& norm, float eps, bool over_time, const std::string& wkey,
+                const std::string& bkey, GnReq* pre);
+  // planning walks use fake pointers: the fold decision must not depend on pointer alignment
+  bool fold_plan_ok(TapGemm g) { g.A = g.D = nullptr; g.Wt = nullptr; return tapgemm_per_sample_ok(g); }
   Act layer_norm(const Act& x, const std::string& p);
   Act linear(const Act& x, const std::string& wkey, const std::string& bkey, const Act* residual, bool geglu = false,
              float alpha = 1.f, const float2* ln = nullptr);

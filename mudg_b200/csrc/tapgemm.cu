@@ -494,6 +494,7 @@ struct G3Params {
   int alpha_is_one;
   double* gn_sums;              // GroupNorm statistics of the output ([S][32][2] fp64, pre-zeroed), or null
   FastDiv fd_cpg, fd_gn;        // channels per group; frames per GroupNorm sample (sample = (b*T + t) / d)
+  FastDiv fd_ws;                // per-sample weights: weight matrix of a tile = (b0*T + t0) / d; d = 0: one matrix
   int dbg;                      // debug experiments (knob gemm_dbg): 1 = do not issue the output TMA stores
   long long* trace;             // debug (tests/gpu_trace_gemm.py): clock64 time line of cluster 0 / rank 0, [4 roles][64 tiles][8]
 };
@@ -613,6 +614,7 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if (lane == 0) G3_TRACE(0, plt, 0);                 // producer starts the tile
       const CUtensorMap* mb = (tl.bn == p.bn_first) ? &tmB0 : &tmB1;
       const int brow = tl.n0 + (int)rank * (tl.bn >> 1);
+      const int wsmp = p.fd_ws.d > 0 ? fd_div(p.fd_ws, tl.b0 * p.b.dimT + tl.t0) : 0;   // per-sample weight matrix
       const uint32_t stage_tx = 2u * (uint32_t)(G3_A_BYTES + (tl.bn >> 1) * (BK * 2));
       for (int tap = 0; tap < ntaps; tap++) {
         const int cw = tl.w0 + p.b.taps[tap][0], ch = tl.h0 + p.b.taps[tap][1], ct = tl.t0 + p.b.taps[tap][2];
@@ -623,7 +625,7 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (rank == 0) mbar_expect_tx(&full[s], stage_tx);     // bytes of BOTH CTAs' boxes
             uint8_t* a_s = smem + s * G3_STAGE_BYTES;
             tma_load_5d_pair(a_s, &tmA, full0 + 8u * s, kc * BK, cw, ch, ct, tl.b0);
-            tma_load_5d_pair(a_s + G3_A_BYTES, mb, full0 + 8u * s, kb, brow, 0, 0, 0);
+            tma_load_5d_pair(a_s + G3_A_BYTES, mb, full0 + 8u * s, kb, brow, wsmp, 0, 0);
           }
           __syncwarp();
           if (++s == NST) { s = 0; ph ^= 1u; }
@@ -1047,6 +1049,23 @@ bool tapgemm_pair_wanted(const TapGemm& g, int64_t m_tiles, int nt128) {
   return m_tiles * nt128 >= (int64_t)sm_count() && ktot_steps >= 4;
 }
 
+static int64_t tapgemm_boxes(const TapGemm& g, int& bw, int& bh, int& bt, int& bb) {
+  int budget = BM;
+  bw = pick_box(g.W, budget); budget /= bw;
+  bh = pick_box(g.H, budget); budget /= bh;
+  bt = pick_box(g.T, budget); budget /= bt;
+  bb = budget;
+  return (int64_t)((g.W + bw - 1) / bw) * ((g.H + bh - 1) / bh) * ((g.T + bt - 1) / bt) * ((g.B + bb - 1) / bb);
+}
+
+bool tapgemm_per_sample_ok(const TapGemm& g) {
+  if (!tapgemm_tc_eligible(g) || g.wt_samples <= 0) return false;
+  int bw, bh, bt, bb;
+  const int64_t m_tiles = tapgemm_boxes(g, bw, bh, bt, bb);
+  const int div = g.wt_div > 0 ? g.wt_div : 1;
+  return tapgemm_pair_wanted(g, m_tiles, (g.N + G2_BN_MAX - 1) / G2_BN_MAX) && bb == 1 && div % bt == 0;
+}
+
 bool tapgemm_tc3(const TapGemm& g, cudaStream_t st) {
   G3Params p{};
   p.b = make_params(g);
@@ -1099,8 +1118,15 @@ bool tapgemm_tc3(const TapGemm& g, cudaStream_t st) {
   const uint32_t abox[5] = {BK, (uint32_t)p.b.bw, (uint32_t)p.b.bh, (uint32_t)p.b.bt, (uint32_t)p.b.bb};
   const uint64_t ddims[5] = {No, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.T, (uint64_t)g.B};
   const uint64_t dstr[4] = {No * 2, No * 2 * g.W, No * 2 * g.W * g.H, No * 2 * g.W * g.H * g.T};
-  const uint64_t bdims[5] = {Ktot, (uint64_t)g.N, 1, 1, 1};
-  const uint64_t bstr[4] = {Ktot * 2, Ktot * 2 * g.N, Ktot * 2 * g.N, Ktot * 2 * g.N};
+  // weights [samples][N][K]: one matrix, or one per GroupNorm sample (see TapGemm::wt_samples)
+  const uint64_t nws = g.wt_samples > 0 ? (uint64_t)g.wt_samples : 1;
+  p.fd_ws = FastDiv{0u, 0u, 0};
+  if (g.wt_samples > 0) {
+    MUDG_REQUIRE(p.b.bb == 1 && (g.wt_div > 0 ? g.wt_div : 1) % p.b.bt == 0, "per-sample weights: a tile would straddle samples");
+    p.fd_ws = make_fastdiv(g.wt_div > 0 ? g.wt_div : 1);
+  }
+  const uint64_t bdims[5] = {Ktot, (uint64_t)g.N, nws, 1, 1};
+  const uint64_t bstr[4] = {Ktot * 2, Ktot * 2 * g.N, Ktot * 2 * g.N * nws, Ktot * 2 * g.N * nws};
   const uint32_t bbox0[5] = {BK, (uint32_t)(p.bn_first / 2), 1, 1, 1};
   const uint32_t bbox1[5] = {BK, (uint32_t)(bn_last / 2), 1, 1, 1};
   const CUtensorMap* ma = get_tmap(g.A, adims, astr, abox);
@@ -1153,6 +1179,7 @@ bool tapgemm_tc3(const TapGemm& g, cudaStream_t st) {
 
 bool tapgemm_tc2(const TapGemm& g, cudaStream_t st) {
   MUDG_REQUIRE(tapgemm_tc_eligible(g), "layer not eligible for the tcgen05 path (Cin=%d N=%d)", g.Cin, g.N);
+  MUDG_REQUIRE(g.wt_samples == 0 || tapgemm_per_sample_ok(g), "per-sample weights need the pair kernel (check tapgemm_per_sample_ok first)");
   {
     int budget = BM;
     const int bw = pick_box(g.W, budget); budget /= bw;

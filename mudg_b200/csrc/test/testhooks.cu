@@ -301,6 +301,7 @@ MUDG_EXPORT int mudg_test_set_knob(const char* name, int value) {
   else if (n == "flash_split") k.flash_split = value;
   else if (n == "tattn_generic") k.tattn_generic = value;
   else if (n == "gn_fuse") k.gn_fuse = value;
+  else if (n == "gn_fold") k.gn_fold = value;
   else if (n == "reset") k = Knobs{};
   else MUDG_REQUIRE(false, "unknown knob %s", n.c_str());
   MUDG_API_END
@@ -314,6 +315,13 @@ static int g_next_gn_div = 1;
 MUDG_EXPORT int mudg_test_next_gemm_gn(void* sums_f64, int gn_div) {
   g_next_gn_sums = static_cast<double*>(sums_f64);
   g_next_gn_div = gn_div;
+  return 0;
+}
+// per-sample weights for the NEXT mudg_test_tapgemm(backend 0) call: Wt is then [samples][N][K], sample = (b*T + t) / div
+static int g_next_ws = 0, g_next_wdiv = 1;
+MUDG_EXPORT int mudg_test_next_gemm_per_sample(int samples, int div) {
+  g_next_ws = samples;
+  g_next_wdiv = div;
   return 0;
 }
 
@@ -341,6 +349,10 @@ MUDG_EXPORT int mudg_test_tapgemm(const void* A, int B, int T, int H, int W, int
     g.gn_sums = g_next_gn_sums;
     g.gn_div = g_next_gn_div;
     g_next_gn_sums = nullptr;
+    g.wt_samples = g_next_ws;
+    g.wt_div = g_next_wdiv;
+    g_next_ws = 0;
+    MUDG_REQUIRE(g.wt_samples == 0 || tapgemm_per_sample_ok(g), "per-sample weights: this shape would not run on the pair kernel");
     tapgemm(g, S(stream));
   } else {
     tapgemm_simt(g, S(stream));

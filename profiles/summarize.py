@@ -65,8 +65,11 @@ def table(paths, out_json=None):
         hbm = 6650.0
     seen, rows_out = set(), []
     for path in paths:
-        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-        rows = list(csv.reader(out.splitlines()))
+        if path.endswith(".csv"):        # already exported on the GPU box: ncu -i x.ncu-rep --page raw --csv > x.csv
+            out = open(path).read()
+        else:
+            out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(l for l in out.splitlines() if not l.startswith("==")))
         if len(rows) < 3:
             continue
         hdr = rows[0]

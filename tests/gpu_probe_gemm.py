@@ -59,6 +59,10 @@ CASES = {
     "lin_ln_small": (1, 1, 1, 2048, 64, 192, 0, 0, 1, 0, 0, 1, 1.0, 2),
     "geglu_ln_small": (1, 1, 1, 2048, 64, 512, 0, 0, 1, 0, 1, 1, 1.0, 2),
 }
+# per-sample weight matrices (GroupNorm folded into proj_in): name -> frames per sample (1 = per frame, T = per batch sample)
+CASES["pair_lin_persample_frame"] = (2, 16, 72, 128, 320, 320, 0, 0, 1, 1, 0, 0, 1.0, 4 | (4 << 8))
+CASES["pair_lin_persample_batch"] = (2, 16, 36, 64, 640, 640, 0, 0, 1, 1, 0, 0, 1.0, 4 | (4 << 8))
+PER_SAMPLE = {"pair_lin_persample_frame": 1, "pair_lin_persample_batch": 16}
 PAIR_CASES = [k for k in CASES if k.startswith("pair_")]
 # cases that also request the fused GroupNorm statistics of their output: name -> frames per GroupNorm sample
 # (1 = per-frame norm, T = TemporalConvBlock norm over (C/32, T, H, W)); the conv modes flatten (B, T) like the model does
@@ -82,11 +86,13 @@ def run_case(name, backends=((1, "simt"), (0, "tc"))):
     if ln:
         A = A * (0.5 + torch.rand(B, T, H, W, 1, device=dev)) + 0.3 * torch.randn(B, T, H, W, 1, device=dev)   # per-row mean / scale
     A = A.half()
+    ws_div = PER_SAMPLE.get(name)
+    n_ws = (B * T) // ws_div if ws_div else 0
     Wraw = torch.randn(N, ntaps, Cin, device=dev) / (ntaps * Cin) ** 0.5
     n_out = N // 2 if geglu else N
     R = torch.randn(B, T, H, W, n_out, device=dev).half() if res else None
     bv = torch.randn(N, device=dev) if bias else None
-    b2 = torch.randn(B, N, device=dev) if bias2 else None
+    b2 = torch.randn(n_ws if ws_div else B, N, device=dev) if bias2 else None
     ln_stats = ln_c1 = None
     if ln:
         # the library's own fold (mudg_finalize_weights): W *= gamma (fp16), c1 = row sums, c2 = W beta + bias
@@ -113,7 +119,12 @@ def run_case(name, backends=((1, "simt"), (0, "tc"))):
         Wt = Wraw.half()
         bias_arg = bv
         # fp32 reference on the fp16-rounded operands, one frame / sample at a time to bound memory
-        if mode == 0:
+        if ws_div:
+            # one weight matrix (and one bias2 row) per sample of ws_div frames
+            Wt = (torch.randn(n_ws, N, Cin, device=dev) / Cin ** 0.5).half()
+            a = A.float().reshape(n_ws, -1, Cin)
+            y = torch.stack([a[i] @ Wt[i].float().t() + b2[i] for i in range(n_ws)]).reshape(B, T, H, W, N)
+        elif mode == 0:
             y = (A.float().reshape(-1, Cin) @ Wt.float().reshape(N, Cin).t()).reshape(B, T, H, W, N)
         elif mode == 1:
             w = Wt.float().reshape(N, 3, 3, Cin).permute(0, 3, 1, 2).contiguous()
@@ -127,7 +138,7 @@ def run_case(name, backends=((1, "simt"), (0, "tc"))):
         y = y * alpha
         if bv is not None:
             y = y + bv
-    if b2 is not None:
+    if b2 is not None and not ws_div:
         y = y + b2[:, None, None, None, :]
     if geglu:
         yy = y.reshape(B, T, H, W, N // 128, 2, 64)
@@ -137,8 +148,12 @@ def run_case(name, backends=((1, "simt"), (0, "tc"))):
     out = {}
     gn_div = GN_CASES.get(name)
     n_samples = (B * T) // gn_div if gn_div else 0
+    if ws_div:
+        backends = ((0, "tc"),)            # the CUDA-core checker has no per-sample weights
     for backend, label in backends:
         D = torch.full((B, T, H, W, n_out), float("nan"), device=dev).half()
+        if ws_div:
+            check(L.mudg_test_next_gemm_per_sample(n_ws, ws_div))
         gn_sums = None
         if gn_div and backend == 0:
             gn_sums = torch.zeros(n_samples, 32, 2, device=dev, dtype=torch.float64)
@@ -147,7 +162,8 @@ def run_case(name, backends=((1, "simt"), (0, "tc"))):
         torch.cuda.synchronize()
         t0 = time.time()
         rc = L.mudg_test_tapgemm(ptr(A), B, T, H, W, Cin, mode, ptr(Wt), N, ptr(D), ptr(R),
-                                 ptr(bias_arg), ptr(b2), ctypes.c_int(T), ctypes.c_int(B if b2 is not None else 0),
+                                 ptr(bias_arg), ptr(b2), ctypes.c_int(ws_div if ws_div else T),
+                                 ctypes.c_int((n_ws if ws_div else B) if b2 is not None else 0),
                                  ctypes.c_float(alpha), int(geglu), ptr(ln_stats), ptr(ln_c1), backend, cur_stream())
         check(rc)
         torch.cuda.synchronize()
@@ -167,7 +183,7 @@ def run_case(name, backends=((1, "simt"), (0, "tc"))):
                 out["_gn"] = (bool(path >> 16), rel)
                 print(f"{name:18s} fused GroupNorm statistics: taken={bool(path >> 16)} max rel err {rel:.2e}", flush=True)
         print(f"{name:18s} {label:5s} max|d|={emax:.5f} mean|d|={float(err.nan_to_num().mean()):.6f} nans={nan} "
-              f"ref_absmax={float(y.abs().max()):.3f} path={path & 255} epi={(path >> 8) - 1} ({(time.time() - t0) * 1e3:.1f} ms)", flush=True)
+              f"ref_absmax={float(y.abs().max()):.3f} path={path & 255} epi={((path >> 8) & 255) - 1} groups={(path >> 20) & 15} ({(time.time() - t0) * 1e3:.1f} ms)", flush=True)
         if label.startswith("tc") and (emax > 0.05 or nan):
             bad = (err > 0.05) | torch.isnan(D.float())
             idx = bad.nonzero()
