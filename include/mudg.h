@@ -26,7 +26,7 @@ extern "C" {
 typedef struct MudgCtx MudgCtx;
 
 enum { MUDG_F32 = 0, MUDG_F16 = 1, MUDG_U8 = 2 /* mudg_postdecode input only */ };
-enum { MUDG_UNET = 0, MUDG_VAE = 1, MUDG_RESAMPLER = 2 };
+enum { MUDG_UNET = 0, MUDG_VAE = 1, MUDG_RESAMPLER = 2, MUDG_CLIP_IMAGE = 3, MUDG_CLIP_TEXT = 4 };
 
 /* unet_config.params of configs/stage{1,2}-*_infer.yaml:26-56 (only the keys that shape the graph) */
 typedef struct {
@@ -112,6 +112,26 @@ MUDG_EXPORT int mudg_postdecode(const void* frames, int dtype, int B, int T, int
  * ("latents" as [num_queries*video_length, dim]); dimensions are derived from the shapes at mudg_finalize_weights.
  * x [B, L, embedding_dim] (MUDG_F32 | MUDG_F16) -> out [B, num_queries*video_length, output_dim] fp32. */
 MUDG_EXPORT int mudg_resampler_forward(MudgCtx* ctx, const void* x, int dtype, int B, int L, void* out, void* stream);
+
+/* "Next" row: the OpenCLIP ViT-H/14 towers, once per clip.  The reference calls open_clip for
+ * them (not vendored); weights are loaded under open_clip's state-dict names relative to `model.visual.` (which =
+ * MUDG_CLIP_IMAGE: conv1.weight, class_embedding, positional_embedding, ln_pre.*, transformer.resblocks.N.{ln_1,ln_2}.*,
+ * .attn.in_proj_{weight,bias}, .attn.out_proj.*, .mlp.{c_fc,c_proj}.*) and to `model.` (which = MUDG_CLIP_TEXT:
+ * token_embedding.weight, positional_embedding, transformer.resblocks.N.*, ln_final.*); widths, depth, patch and grid
+ * are derived from the shapes at mudg_finalize_weights, the head count is an argument (16 for ViT-H/14).
+ *
+ * mudg_clip_image_forward = FrozenOpenCLIPImageEmbedderV2.forward (lvdm/modules/encoders/condition.py:334-372):
+ *   img [B, 3, H, W] (MUDG_F32 | MUDG_F16) -> out [B, 1 + grid^2, width] fp32 token-level transformer output (no
+ *   ln_post / proj).  resize != 0: img is in [-1, 1] at any H x W and first goes through `preprocess` (:318-326: kornia
+ *   bicubic resize to the tower size with align_corners and the anti-alias gaussian, (x + 1) / 2, CLIP mean / std);
+ *   resize == 0: img is the already normalised tower input (H = W = grid * patch).
+ * mudg_clip_text_forward = FrozenOpenCLIPEmbedder.encode_with_transformer (:214-232): tokens [B, L <= 77] int64 (device)
+ *   -> out [B, L, width] fp32 = ln_final(blocks[0 .. layers - skip_last) (token_embedding + positional_embedding)) under
+ *   the causal mask; skip_last is the reference's layer_idx (0 "last", 1 "penultimate").  Tokenisation stays on the host. */
+MUDG_EXPORT int mudg_clip_image_forward(MudgCtx* ctx, const void* img, int dtype, int B, int H, int W, int resize, int heads,
+                                        void* out, void* stream);
+MUDG_EXPORT int mudg_clip_text_forward(MudgCtx* ctx, const int64_t* tokens, int B, int L, int heads, int skip_last, void* out,
+                                       void* stream);
 
 /* colormap(image, cmap="Spectral", bytes=True) of the reference (eval_tools.py:137-250, method_custom): map fp32 [n] in
  * [0,1] (clamped) -> out_u8 [n, 3] (HWC).  Used for the ground-truth depth visualisation (eval_tools.py:82). */

@@ -74,11 +74,10 @@ MUDG_EXPORT int mudg_load_weight(MudgCtx* ctx, int which, const char* key, const
                                  const int64_t* shape, int ndim, void* stream) {
   MUDG_API_BEGIN
   MUDG_REQUIRE(ctx && key && dev_ptr && shape, "null argument");
-  MUDG_REQUIRE(which == MUDG_UNET || which == MUDG_VAE || which == MUDG_RESAMPLER, "unknown weight set %d", which);
+  MUDG_REQUIRE(which >= MUDG_UNET && which <= MUDG_CLIP_TEXT, "unknown weight set %d", which);
   DeviceGuard guard(ctx->model.device());
   ctx->model.begin_load(which);
-  WeightStore& ws = which == MUDG_VAE ? ctx->model.vae_w : (which == MUDG_RESAMPLER ? ctx->model.res_w : ctx->model.unet_w);
-  ws.load(key, dev_ptr, dtype, shape, ndim, S(stream));
+  ctx->model.store(which).load(key, dev_ptr, dtype, shape, ndim, S(stream));
   MUDG_API_END
 }
 
@@ -162,6 +161,25 @@ MUDG_EXPORT int mudg_postdecode(const void* frames, int dtype, int B, int T, int
   ProfScope ps(PF_POST, 0.0, (double)B * T * H * W * 3.0 * ((dtype == MUDG_F32 ? 4.0 : dtype == MUDG_F16 ? 2.0 : 1.0) + 1.0), S(stream), "postdecode");
   postdecode(frames, dtype, static_cast<uint8_t*>(rgb_u8), static_cast<float*>(depth_f32),
              static_cast<uint8_t*>(class_u8), B, T, (int64_t)H * W, modes, S(stream));
+  MUDG_API_END
+}
+
+MUDG_EXPORT int mudg_clip_image_forward(MudgCtx* ctx, const void* img, int dtype, int B, int H, int W, int resize, int heads,
+                                        void* out, void* stream) {
+  MUDG_API_BEGIN
+  MUDG_REQUIRE(ctx && img && out, "null argument");
+  MUDG_REQUIRE(dtype == MUDG_F32 || dtype == MUDG_F16, "clip image: dtype %d", dtype);
+  DeviceGuard guard(ctx->model.device());
+  ctx->model.clip_image_forward(img, dtype, B, H, W, resize, heads, out, S(stream));
+  MUDG_API_END
+}
+
+MUDG_EXPORT int mudg_clip_text_forward(MudgCtx* ctx, const int64_t* tokens, int B, int L, int heads, int skip_last, void* out,
+                                       void* stream) {
+  MUDG_API_BEGIN
+  MUDG_REQUIRE(ctx && tokens && out, "null argument");
+  DeviceGuard guard(ctx->model.device());
+  ctx->model.clip_text_forward(tokens, B, L, heads, skip_last, out, S(stream));
   MUDG_API_END
 }
 

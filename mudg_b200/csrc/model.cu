@@ -262,8 +262,19 @@ void Model::build_plan() {
   n_res_ = res_count;
 }
 
+WeightStore& Model::store(int which) {
+  switch (which) {
+    case MUDG_UNET: return unet_w;
+    case MUDG_VAE: return vae_w;
+    case MUDG_RESAMPLER: return res_w;
+    case MUDG_CLIP_IMAGE: return clipv_w;
+    case MUDG_CLIP_TEXT: return clipt_w;
+  }
+  throw Error(fmt("unknown weight set %d", which));
+}
+
 void Model::begin_load(int which) {
-  WeightStore& ws = which == MUDG_VAE ? vae_w : (which == MUDG_RESAMPLER ? res_w : unet_w);
+  WeightStore& ws = store(which);
   if (!ws.finalized) return;
   MUDG_CUDA(cudaDeviceSynchronize());      // kernels of earlier forwards may still read the old set
   ws.clear();
@@ -275,13 +286,21 @@ void Model::begin_load(int which) {
     ctx_version_++;
   } else if (which == MUDG_VAE) {
     vae_ready_ = vae_enc_ready_ = false;
-  } else {
+  } else if (which == MUDG_RESAMPLER) {
     res_ready_ = false;
+  } else if (which == MUDG_CLIP_IMAGE) {
+    clipv_ready_ = false;
+  } else {
+    clipt_ready_ = false;
   }
 }
 
 void Model::finalize(int which, cudaStream_t st) {
-  (which == MUDG_VAE ? vae_w : (which == MUDG_RESAMPLER ? res_w : unet_w)).finalized = true;
+  store(which).finalized = true;
+  if (which == MUDG_CLIP_IMAGE || which == MUDG_CLIP_TEXT) {
+    finalize_clip(which);
+    return;
+  }
   if (which == MUDG_RESAMPLER) {
     // touch every key Resampler.forward needs and derive the dimensions from the shapes (resampler.py:104-129)
     WeightStore& w = res_w;

@@ -79,6 +79,8 @@ class Model {
   ~Model();
 
   WeightStore unet_w, vae_w, res_w;   // res_w: Resampler (image_proj_model), "next" row f.3
+  WeightStore clipv_w, clipt_w;       // OpenCLIP image / text towers (clip.cu), "next" row f.3
+  WeightStore& store(int which);      // MUDG_UNET / MUDG_VAE / MUDG_RESAMPLER / MUDG_CLIP_IMAGE / MUDG_CLIP_TEXT
   // A load after finalize() replaces the WHOLE weight set: the fused / folded tensors (qkv, kv_text, kv_img, GEGLU
   // interleave, LayerNorm folds, padded rows) are derived from raw tensors that finalize() released, so nothing of the
   // old set may survive.  Also drops the captured CUDA graphs and the cross-attention K/V cache (both hold weight data).
@@ -94,6 +96,13 @@ class Model {
   void vae_encode(const void* x, int F, int H, int W, void* moments, cudaStream_t st);
   // Resampler.forward (resampler.py:131-144): x [B, L, embedding_dim] -> out [B, num_queries*video_length, output_dim] fp32
   void resampler_forward(const void* x, int dtype, int B, int L, void* out, cudaStream_t st);
+  // FrozenOpenCLIPImageEmbedderV2.encode_with_vision_transformer (condition.py:339-372): img [B, 3, H, W] -> out
+  // [B, tokens, width] fp32.  resize != 0: img is in [-1, 1] at any size and goes through the reference's preprocess
+  // (condition.py:318-326); resize == 0: img is already the normalised tower input.
+  void clip_image_forward(const void* img, int dtype, int B, int H, int W, int resize, int heads, void* out, cudaStream_t st);
+  // FrozenOpenCLIPEmbedder.encode_with_transformer (condition.py:214-232): tokens [B, L] int64 -> out [B, L, width] fp32;
+  // skip_last = the reference's layer_idx (1 for layer = "penultimate")
+  void clip_text_forward(const int64_t* tokens, int B, int L, int heads, int skip_last, void* out, cudaStream_t st);
   size_t plan_unet(int N, int dup, int T, int h, int w);
   size_t plan_vae(int h, int w);
   int64_t launches = 0;
@@ -110,6 +119,32 @@ class Model {
   bool unet_ready_ = false, vae_ready_ = false, vae_enc_ready_ = false, res_ready_ = false;
   struct ResamplerDims { int nq = 0, dim = 0, emb = 0, outd = 0, depth = 0, heads = 0, inner = 0, ff = 0; } rs_;
   void resampler_body(const void* x, int dtype, int B, int L, void* out);
+  struct ClipDims { int width = 0, layers = 0, mlp = 0, grid = 0, patch = 0, tokens = 0, vocab = 0; } cv_, ct_;
+  bool clipv_ready_ = false, clipt_ready_ = false;
+  void finalize_clip(int which);
+  Act clip_block(Act x, const std::string& p, int B, int L, int heads, bool causal);
+  void clip_image_body(const void* img, int dtype, int B, int H, int W, int resize, int heads, void* out);
+  void clip_text_body(const int64_t* tokens, int B, int L, int heads, int skip_last, void* out);
+  // body(true) walks the graph allocating nothing (arena high-water mark), then body(false) runs it on `st`
+  template <class F>
+  void run_planned(F&& body, cudaStream_t st) {
+    struct Reset {
+      Model& m;
+      ~Reset() { m.arena_.planning = false; m.planning_ = false; prof_pause(false); }
+    };
+    {
+      Reset guard{*this};
+      arena_.planning = true; planning_ = true;
+      arena_.reset_high();
+      prof_pause(true);
+      body(true);
+    }
+    const size_t need = arena_.high_water();
+    arena_.reset();
+    ensure_arena(need);
+    st_ = st;
+    body(false);
+  }
 
   // ---- per-call state
   Arena arena_;

@@ -14,7 +14,7 @@ import torch
 from ._lib import MudgError, check, cur_stream, lib, ptr
 
 MUDG_F32, MUDG_F16, MUDG_U8 = 0, 1, 2
-MUDG_UNET, MUDG_VAE, MUDG_RESAMPLER = 0, 1, 2
+MUDG_UNET, MUDG_VAE, MUDG_RESAMPLER, MUDG_CLIP_IMAGE, MUDG_CLIP_TEXT = 0, 1, 2, 3, 4
 MUDG_POST_COLOR, MUDG_POST_DEPTH, MUDG_POST_SEMANTIC = 0, 1, 2
 # class labels the driver gives the three modalities (virtual_pose_render.py:247-318)
 LABEL_TO_POST_MODE = {0: MUDG_POST_COLOR, 500: MUDG_POST_DEPTH, 1: MUDG_POST_SEMANTIC}
@@ -136,7 +136,7 @@ class Engine:
                 if not key.startswith(prefix):
                     continue
                 key = key[len(prefix):]
-            if not torch.is_floating_point(t):
+            if not torch.is_floating_point(t) or t.dim() == 0:      # index buffers; scalars (CLIP logit_scale) are not on any path
                 continue
             t = t.detach()
             if t.dtype not in (torch.float32, torch.float16):
@@ -216,6 +216,29 @@ class Engine:
         out = torch.empty((B, n_out, out_dim), device=x.device, dtype=torch.float32)
         check(lib().mudg_resampler_forward(self._h, ptr(x), MUDG_F32 if x.dtype == torch.float32 else MUDG_F16, B, L, ptr(out),
                                            cur_stream()))
+        return out
+
+    def clip_image_forward(self, img: torch.Tensor, tokens: int, width: int, heads: int, resize: bool = True) -> torch.Tensor:
+        """img [B, 3, H, W] -> [B, tokens, width] fp32 (FrozenOpenCLIPImageEmbedderV2.forward; resize=True runs the
+        reference's preprocess on an image in [-1, 1], resize=False takes the normalised tower input)."""
+        img = img.detach()
+        if img.dtype not in (torch.float32, torch.float16):
+            img = img.float()
+        img = img.contiguous()
+        B, C, H, W = img.shape
+        if C != 3:
+            raise MudgError(f"clip_image_forward: {C} channels")
+        out = torch.empty((B, tokens, width), device=img.device, dtype=torch.float32)
+        check(lib().mudg_clip_image_forward(self._h, ptr(img), MUDG_F32 if img.dtype == torch.float32 else MUDG_F16, B, H, W,
+                                            int(bool(resize)), int(heads), ptr(out), cur_stream()))
+        return out
+
+    def clip_text_forward(self, tokens: torch.Tensor, width: int, heads: int, skip_last: int = 1) -> torch.Tensor:
+        """tokens [B, L] int64 (device) -> [B, L, width] fp32 (FrozenOpenCLIPEmbedder.encode_with_transformer)."""
+        tokens = tokens.detach().to(torch.long).contiguous()
+        B, L = tokens.shape
+        out = torch.empty((B, L, width), device=tokens.device, dtype=torch.float32)
+        check(lib().mudg_clip_text_forward(self._h, ptr(tokens), B, L, int(heads), int(skip_last), ptr(out), cur_stream()))
         return out
 
     def ddim_step(self, x, v_cond, v_uncond, noise, *, cfg_scale, guidance_rescale, sqrt_ac, sqrt_1mac, rescale,

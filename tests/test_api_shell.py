@@ -122,6 +122,36 @@ def test_next_rows_fail_loudly_without_gpu():
         E.convert_clip(torch.zeros(1, 3, 2, 4, 8), 0)
 
 
+def test_clip_holders_have_open_clip_layout_and_fail_loudly():
+    """OpenCLIP towers (f.3): the drop-in modules expose the key set of the reference's embedders (an open_clip CLIP under
+    `model.` with `visual` / `transformer` deleted) at ViT-H/14 size, and have no CPU path."""
+    from mudg_b200._lib import MudgError
+    from lvdm.modules.encoders.condition import FrozenOpenCLIPEmbedder, FrozenOpenCLIPImageEmbedderV2
+    from oracle import clip_oracle as C
+    with torch.device("meta"):
+        t, v = FrozenOpenCLIPEmbedder(layer="penultimate"), FrozenOpenCLIPImageEmbedderV2()
+    text_side = {"model." + k: s for k, s in C.clip_text_param_shapes().items()}
+    text_side["model.logit_scale"] = ()
+    assert {k: tuple(x.shape) for k, x in t.state_dict().items()} == text_side and t.layer_idx == 1
+    want_v = {"model.visual." + k: s for k, s in C.clip_vision_param_shapes().items()}
+    want_v.update({k: s for k, s in text_side.items() if "resblocks" not in k})
+    assert {k: tuple(x.shape) for k, x in v.state_dict().items()} == want_v
+    assert "mean" not in v.state_dict() and tuple(v.mean.shape) == (3,)            # non-persistent buffers, as in the reference
+    with pytest.raises(NotImplementedError):
+        FrozenOpenCLIPImageEmbedderV2(layer="penultimate")
+    if torch.cuda.is_available():
+        return
+    small = dict(embed_dim=64, vision=dict(width=128, layers=1, heads=2, mlp=512, image_size=28, patch=14),
+                 text=dict(width=128, layers=2, heads=2, mlp=512, vocab=100, ctx=77))
+    with pytest.raises(MudgError):
+        FrozenOpenCLIPImageEmbedderV2(arch=small)(torch.zeros(1, 3, 32, 32))
+    tm = FrozenOpenCLIPEmbedder(arch=small, layer="penultimate")
+    with pytest.raises(MudgError):
+        tm.encode_with_transformer(torch.zeros(1, 77, dtype=torch.long))
+    with pytest.raises(MudgError):
+        tm(["a prompt"])                                                            # no tokenizer in this image
+
+
 def test_context_tensor_identity_is_kept():
     """DiffusionWrapper hands the UNet the SAME context tensor object every DDIM step (the K/V cache is keyed on it)."""
     from lvdm.models.ddpm3d import DiffusionWrapper

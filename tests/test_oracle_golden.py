@@ -146,3 +146,32 @@ def test_resampler_matches_reference(golden_dir):
     assert float((y - torch.from_numpy(g["y"])).abs().max()) < 1e-5
     full = O.resampler_param_shapes()
     assert len(full) == 51 and full["latents"] == (1, 256, 1024) and full["layers.3.0.to_kv.weight"] == (1536, 1024)
+
+
+def test_clip_oracle_matches_transformers_golden(golden_dir):
+    """OpenCLIP towers (next row f.3): open_clip is not in the image, so the goldens come from the other published
+    implementation of the model, transformers' CLIPVisionModel / CLIPTextModel (oracle/make_golden_clip.py)."""
+    from oracle import clip_oracle as C
+    g = np.load(os.path.join(golden_dir, "clip_small.npz"))
+    v = dict(width=128, layers=3, mlp=512, image_size=56, patch=14, embed_dim=64)
+    sd = C.seeded_clip_state_dict(C.clip_vision_param_shapes(**v), 21)
+    y = C.clip_image_tokens(sd, torch.from_numpy(g["img"]), 2)
+    assert y.shape == (2, 17, 128) and float((y - torch.from_numpy(g["vis"])).abs().max()) < 5e-5
+    v80 = dict(width=320, layers=2, mlp=640, image_size=42, patch=14, embed_dim=64)
+    sd = C.seeded_clip_state_dict(C.clip_vision_param_shapes(**v80), 22)
+    y = C.clip_image_tokens(sd, torch.from_numpy(g["img80"]), 4)
+    assert float((y - torch.from_numpy(g["vis80"])).abs().max()) < 5e-5
+    t = dict(width=128, layers=4, mlp=512, vocab=1000, ctx=77, embed_dim=64)
+    sd = C.seeded_clip_state_dict(C.clip_text_param_shapes(**t), 23)
+    y = C.clip_text_encode(sd, torch.from_numpy(g["tok"]), 2, layer_idx=1)
+    assert y.shape == (2, 77, 128) and float((y - torch.from_numpy(g["txt"])).abs().max()) < 5e-5
+    # ViT-H/14 inventory: 32 x 12 + 8 vision keys, 24 x 12 + 5 text keys
+    assert len(C.clip_vision_param_shapes()) == 392 and len(C.clip_text_param_shapes()) == 293
+    # the resize restatement: identity size -> only (x + 1) / 2 and the CLIP normalisation; down-scaling blurs first
+    x = torch.rand(1, 3, 224, 224) * 2 - 1
+    p = C.clip_preprocess(x)
+    mean = torch.tensor(C.CLIP_MEAN)[None, :, None, None]
+    std = torch.tensor(C.CLIP_STD)[None, :, None, None]
+    assert float((p - ((x + 1) / 2 - mean) / std).abs().max()) < 1e-5
+    big = torch.rand(1, 3, 448, 896) * 2 - 1
+    assert float(C.clip_preprocess(big).std()) < float(C.clip_preprocess(big, antialias=False).std())
