@@ -1,5 +1,6 @@
-"""Seeded stand-ins for the once-per-clip conditioning encoders, which are off the per-step hot path and need
-un-vendored OpenCLIP ViT-H/14 weights.  Point `cond_stage_config.target`,
+"""Seeded stand-ins for the once-per-clip conditioning encoders, for runs WITHOUT weights (bench.py's synthetic conditioning,
+tests of the driver flow).  The real towers are lvdm/modules/encoders/condition.py (csrc/clip.cu) and resampler.py; they need the
+OpenCLIP ViT-H/14 weights a MuDG checkpoint carries.  Point `cond_stage_config.target`,
 `img_cond_stage_config.target` and `image_proj_stage_config.target` at these in a YAML to run the sampler with
 synthetic conditioning of the right shapes: text [B,77,1024], image tokens [B,257,1280] -> [B,16*T,1024]."""
 from __future__ import annotations
