@@ -1083,6 +1083,23 @@ bool tapgemm_tc3(const TapGemm& g, cudaStream_t st) {
   p.n_unit = g.geglu ? 128 : 64;
   const int units = g.N / p.n_unit, max_units = 256 / p.n_unit;
   p.nt = (units + max_units - 1) / max_units;
+  {
+    // Wave balance: the tiles of one launch are equal work, dealt to sm_count / 2 CTA pairs, so the launch takes
+    // ceil(tiles / pairs) waves of one tile width each.  Narrower N tiles (down to half the maximum) are taken when they cut
+    // that product by 10 % or more: 2 560 x 1 280 is one wave of 70 192-wide tiles instead of one of 50 256-wide ones, 4 608 x
+    // 1 280 two waves of 192 instead of two of 256.  The constant stands for the per-tile pipeline fill / epilogue tail and the
+    // lower MMA efficiency of narrow tiles (with 32, 10 240 x 640 went to 128-wide tiles and lost 6 %).
+    const int64_t pairs = std::max(1, sm_count() / 2), m_pairs = (m_tiles + 1) / 2;
+    auto cost = [&](int nt) {
+      const int width = ((units + nt - 1) / nt) * p.n_unit;
+      return ((int64_t)nt * m_pairs + pairs - 1) / pairs * (width + 96);
+    };
+    int best = p.nt;
+    if (knobs().gemm_balance)
+      for (int nt = p.nt + 1; nt <= std::min(units, 2 * p.nt); nt++)
+        if (cost(nt) * 10 <= cost(best) * 9) best = nt;
+    p.nt = best;
+  }
   p.n_q = units / p.nt;
   p.n_rem = units % p.nt;
   p.bn_first = (p.n_q + (p.n_rem > 0 ? 1 : 0)) * p.n_unit;

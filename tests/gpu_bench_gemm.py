@@ -54,6 +54,29 @@ SHAPES_512 = [
 ]
 
 
+# shapes whose 256-wide pair tiles leave the last wave mostly empty (knob gemm_balance: narrower N tiles)
+SHAPES_BALANCE = [
+    ("conv3 L3 1280->1280", 1, 32, 9, 16, 1280, 1280, 1, 1, 0),
+    ("conv3 L3 2560->1280", 1, 32, 9, 16, 2560, 1280, 1, 0, 0),
+    ("tconv L3 1280", 2, 16, 9, 16, 1280, 1280, 2, 1, 0),
+    ("lin L3 1280->1280", 1, 1, 1, 4608, 1280, 1280, 0, 1, 0),
+    ("lin L3 5120->1280 +res", 1, 1, 1, 4608, 5120, 1280, 0, 1, 0),
+    ("lin L3 1280->3840 qkv", 1, 1, 1, 4608, 1280, 3840, 0, 0, 0),
+    ("lin L3 1280->10240 geglu", 1, 1, 1, 4608, 1280, 10240, 0, 0, 1),
+    ("conv3 L2 1280->1280", 1, 32, 18, 32, 1280, 1280, 1, 1, 0),
+    ("lin L2 1280->1280 +res", 1, 1, 1, 18432, 1280, 1280, 0, 1, 0),
+    ("lin L1 640->640 +res", 1, 1, 1, 73728, 640, 640, 0, 1, 0),
+    ("512 conv3 L2 1280->1280", 1, 16, 10, 16, 1280, 1280, 1, 1, 0),
+    ("512 tconv L2 1280", 1, 16, 10, 16, 1280, 1280, 2, 0, 0),
+    ("512 lin L2 1280->1280 +res", 1, 1, 1, 2560, 1280, 1280, 0, 1, 0),
+    ("512 lin L2 5120->1280 +res", 1, 1, 1, 2560, 5120, 1280, 0, 1, 0),
+    ("512 lin L2 1280->3840 qkv", 1, 1, 1, 2560, 1280, 3840, 0, 0, 0),
+    ("512 conv3 L1 640->640", 1, 16, 20, 32, 640, 640, 1, 1, 0),
+    ("512 lin L1 640->640 +res", 1, 1, 1, 10240, 640, 640, 0, 1, 0),
+    ("512 lin L1 2560->640 +res", 1, 1, 1, 10240, 2560, 640, 0, 1, 0),
+]
+
+
 def main():
     dev = "cuda"
     L = test_lib()
@@ -66,6 +89,11 @@ def main():
         SHAPES, knob = SHAPES_512, b"gemm_pair"
         backends = [(0, "single"), (0, "pair"), (0, "auto")]
         vals = {"single": 0, "pair": 1, "auto": -1}
+        sys.argv = sys.argv[:1]
+    if len(sys.argv) > 1 and sys.argv[1] == "balance":
+        SHAPES, knob = SHAPES_BALANCE, b"gemm_balance"
+        backends = [(0, "wide"), (0, "balanced")]
+        vals = {"wide": 0, "balanced": 1}
         sys.argv = sys.argv[:1]
     print(f"{'shape':28s} " + " ".join(f"{n:>8s}us {n:>6s}TF" for _, n in backends))
     only = sys.argv[1] if len(sys.argv) > 1 else None

@@ -62,12 +62,16 @@ CASES = {
 # per-sample weight matrices (GroupNorm folded into proj_in): name -> frames per sample (1 = per frame, T = per batch sample)
 CASES["pair_lin_persample_frame"] = (2, 16, 72, 128, 320, 320, 0, 0, 1, 1, 0, 0, 1.0, 4 | (4 << 8))
 CASES["pair_lin_persample_batch"] = (2, 16, 36, 64, 640, 640, 0, 0, 1, 1, 0, 0, 1.0, 4 | (4 << 8))
+# wave-balanced N tiles (1 280 columns as 6 x 192 + 128 instead of 5 x 256): MDM1024 level 3 and MDM512 level 2
+CASES["pair_conv_l3_balanced"] = (2, 16, 9, 16, 1280, 1280, 1, 1, 1, 0, 0, 0, 1.0, 4 | (6 << 8))
+CASES["pair_lin_l2_balanced"] = (1, 1, 1, 2560, 1280, 1280, 0, 1, 1, 0, 0, 0, 1.0, 4 | (6 << 8))
+CASES["pair_tconv_l3_balanced"] = (2, 16, 9, 16, 1280, 1280, 2, 0, 1, 0, 0, 0, 1.0, 4 | (2 << 8))
 PER_SAMPLE = {"pair_lin_persample_frame": 1, "pair_lin_persample_batch": 16}
 PAIR_CASES = [k for k in CASES if k.startswith("pair_")]
 # cases that also request the fused GroupNorm statistics of their output: name -> frames per GroupNorm sample
 # (1 = per-frame norm, T = TemporalConvBlock norm over (C/32, T, H, W)); the conv modes flatten (B, T) like the model does
 GN_CASES = {"pair_conv_l0_emb": 1, "pair_conv_l0_res": 16, "pair_conv_l0_cat": 1, "pair_tconv_l0_res": 1, "pair_tconv_l0": 16,
-            "pair_conv_l1_cat": 1, "conv3x3_l0": 1}
+            "pair_conv_l1_cat": 1, "conv3x3_l0": 1, "pair_conv_l3_balanced": 16}
 
 
 def run_case(name, backends=((1, "simt"), (0, "tc"))):
@@ -159,6 +163,8 @@ def run_case(name, backends=((1, "simt"), (0, "tc"))):
             gn_sums = torch.zeros(n_samples, 32, 2, device=dev, dtype=torch.float64)
             check(L.mudg_test_set_knob(b"gn_fuse", 2))      # also the 3-tap convs (the product only fuses 9-tap ones: slack)
             check(L.mudg_test_next_gemm_gn(ptr(gn_sums), gn_div))
+        if os.environ.get("PROBE_BALANCE") and backend == 0:
+            check(L.mudg_test_set_knob(b"gemm_balance", int(os.environ["PROBE_BALANCE"])))
         torch.cuda.synchronize()
         t0 = time.time()
         rc = L.mudg_test_tapgemm(ptr(A), B, T, H, W, Cin, mode, ptr(Wt), N, ptr(D), ptr(R),
@@ -180,8 +186,15 @@ def run_case(name, backends=((1, "simt"), (0, "tc"))):
                 d64 = D.double().reshape(n_samples, -1, 32, n_out // 32)
                 want = torch.stack([d64.sum(dim=(1, 3)), (d64 * d64).sum(dim=(1, 3))], dim=-1)
                 rel = float(((gn_sums - want).abs() / (want.abs() + 1e-3 * want.abs().max())).max())
-                out["_gn"] = (bool(path >> 16), rel)
-                print(f"{name:18s} fused GroupNorm statistics: taken={bool(path >> 16)} max rel err {rel:.2e}", flush=True)
+                taken = bool((path >> 16) & 1)          # bit 16 only: the epilogue-group count sits at bit 20
+                out["_gn"] = (taken, rel)
+                if rel > 1e-3:
+                    e = (gn_sums - want).abs() / (want.abs() + 1e-3 * want.abs().max())
+                    bad = (e > 1e-3).nonzero()
+                    print("   bad (sample, group, sum|sumsq):", bad[:12].tolist(), "count", bad.shape[0], "of", e.numel(), flush=True)
+                    for i in bad[:6].tolist():
+                        print("     got", float(gn_sums[tuple(i)]), "want", float(want[tuple(i)]), flush=True)
+                print(f"{name:18s} fused GroupNorm statistics: taken={taken} max rel err {rel:.2e}", flush=True)
         print(f"{name:18s} {label:5s} max|d|={emax:.5f} mean|d|={float(err.nan_to_num().mean()):.6f} nans={nan} "
               f"ref_absmax={float(y.abs().max()):.3f} path={path & 255} epi={((path >> 8) & 255) - 1} groups={(path >> 20) & 15} ({(time.time() - t0) * 1e3:.1f} ms)", flush=True)
         if label.startswith("tc") and (emax > 0.05 or nan):
