@@ -774,6 +774,167 @@ temporal_attn16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out,
   }
 }
 
+// ---------------------------------------------------------------- temporal attention, T == 32 | 64: the same tensor-core scheme
+// One warp per (b, pixel, head) problem; Q / K / V tiles of T tokens x 128 B in a 2-deep cp.async ring.  Per 16-query block:
+// S = Q K^T (T / 8 n-tiles x 4 k-steps), softmax in the accumulator fragments, O = P V (8 n-tiles x T / 16 k-steps), O staged
+// over the block's own Q rows (dead by then) and stored with 128-bit coalesced writes.  Algorithmic traffic is the same
+// 4 x T x 128 B per problem as T == 16, so the kernel is HBM-bound (T = 64: 1 MFLOP and 4 096 exponentials per 32 KB).
+template <int T>
+struct TaCfg {
+  static constexpr int TILE = T * 128;
+  static constexpr int WARPS = 4;
+  static constexpr int SMEM = WARPS * 2 * 3 * TILE;     // T = 64: 192 KB (one CTA per SM), T = 32: 96 KB
+};
+
+template <int T>
+__global__ void __launch_bounds__(TaCfg<T>::WARPS * 32)
+temporal_attn_mma_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int B, int HW, int heads, float scale_log2) {
+  extern __shared__ __align__(128) uint8_t ta_smem[];
+  constexpr int TILE = TaCfg<T>::TILE, NT = T / 8, KT = T / 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int inner = heads * 64;
+  const int64_t pitch = 3 * (int64_t)inner;
+  const int64_t npairs = (int64_t)B * HW * heads;
+  const int64_t wid = (int64_t)blockIdx.x * TaCfg<T>::WARPS + warp;
+  const int64_t wstride = (int64_t)gridDim.x * TaCfg<T>::WARPS;
+  uint8_t* wbase = ta_smem + warp * (2 * 3 * TILE);
+  const uint32_t wbase_u = smem_u32(wbase);
+
+  auto issue_loads = [&](int64_t pr, int buf) {
+    const int head = pr % heads;
+    const int64_t bp = pr / heads;
+    const int px = bp % HW;
+    const int b = bp / HW;
+    const __half* base = qkv + ((int64_t)b * T * HW + px) * pitch + head * 64;
+    const uint32_t sb = wbase_u + buf * (3 * TILE);
+#pragma unroll
+    for (int i = 0; i < T / 4; i++) {                      // T rows x 8 chunks of 16 B, 32 pieces per pass
+      const int piece = lane + 32 * i;
+      const int r = piece >> 3, c = piece & 7;
+      const __half* src = base + (int64_t)r * HW * pitch + c * 8;
+      const uint32_t dst = sb + r * 128 + ((c ^ (r & 7)) << 4);
+      cp_async16(dst, src);                                  // Q
+      cp_async16(dst + TILE, src + inner);                   // K
+      cp_async16(dst + 2 * TILE, src + 2 * inner);           // V
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int buf = 0;
+  if (wid < npairs) issue_loads(wid, 0);
+  for (int64_t pr = wid; pr < npairs; pr += wstride, buf ^= 1) {
+    const int64_t nxt = pr + wstride;
+    if (nxt < npairs) {
+      issue_loads(nxt, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+    const uint32_t sq = wbase_u + buf * (3 * TILE), sk = sq + TILE, sv = sq + 2 * TILE;
+    uint8_t* so = wbase + buf * (3 * TILE);
+#pragma unroll 1
+    for (int mt = 0; mt < KT; mt++) {
+      // ---- S = Q[mt] K^T : 16 queries x T keys
+      float s[NT][4];
+#pragma unroll
+      for (int j = 0; j < NT; j++) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 4; ks++) {
+        uint32_t a0, a1, a2, a3;
+        {
+          const int r = mt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1), c = 2 * ks + (lane >> 4);
+          ldsm_x4(sq + r * 128 + ((c ^ (r & 7)) << 4), a0, a1, a2, a3);
+        }
+#pragma unroll
+        for (int np = 0; np < KT; np++) {                    // 16 keys per ldmatrix.x4
+          uint32_t b0, b1, b2, b3;
+          const int r = np * 16 + (lane & 7) + 8 * (lane >> 4), c = 2 * ks + ((lane >> 3) & 1);
+          ldsm_x4(sk + r * 128 + ((c ^ (r & 7)) << 4), b0, b1, b2, b3);
+          mma16816(s[2 * np], a0, a1, a2, a3, b0, b1);
+          mma16816(s[2 * np + 1], a0, a1, a2, a3, b2, b3);
+        }
+      }
+      // ---- softmax over the T keys of rows g (c0, c1) and g + 8 (c2, c3); a row lives in one quad of lanes
+      float mA = -INFINITY, mB = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < NT; j++) {
+        mA = fmaxf(mA, fmaxf(s[j][0], s[j][1]));
+        mB = fmaxf(mB, fmaxf(s[j][2], s[j][3]));
+      }
+      mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 1)); mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 2));
+      mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 1)); mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 2));
+      const float oA = mA * scale_log2, oB = mB * scale_log2;
+      float lA = 0.f, lB = 0.f;
+      uint32_t pa[KT][4];
+#pragma unroll
+      for (int j = 0; j < NT; j++) {
+        const float p0 = exp2f(fmaf(s[j][0], scale_log2, -oA)), p1 = exp2f(fmaf(s[j][1], scale_log2, -oA));
+        const float p2 = exp2f(fmaf(s[j][2], scale_log2, -oB)), p3 = exp2f(fmaf(s[j][3], scale_log2, -oB));
+        lA += p0 + p1;
+        lB += p2 + p3;
+        pa[j >> 1][(j & 1) * 2] = pack_half2(p0, p1);        // A fragment of the P V k-step j / 2: keys 8 (j & 1) + ...
+        pa[j >> 1][(j & 1) * 2 + 1] = pack_half2(p2, p3);
+      }
+      lA += __shfl_xor_sync(0xffffffffu, lA, 1); lA += __shfl_xor_sync(0xffffffffu, lA, 2);
+      lB += __shfl_xor_sync(0xffffffffu, lB, 1); lB += __shfl_xor_sync(0xffffffffu, lB, 2);
+      // ---- O = P V
+      float o[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; j++) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < KT; kk++) {
+#pragma unroll
+        for (int nj = 0; nj < 8; nj += 2) {
+          uint32_t b0, b1, b2, b3;
+          const int r = kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1), c = nj + (lane >> 4);
+          ldsm_x4_t(sv + r * 128 + ((c ^ (r & 7)) << 4), b0, b1, b2, b3);
+          mma16816(o[nj], pa[kk][0], pa[kk][1], pa[kk][2], pa[kk][3], b0, b1);
+          mma16816(o[nj + 1], pa[kk][0], pa[kk][1], pa[kk][2], pa[kk][3], b2, b3);
+        }
+      }
+      const float iA = 1.f / lA, iB = 1.f / lB;
+      // ---- stage O (fp16) over this block's Q rows: every lane's ldmatrix reads of them are done (warp-synchronous mma)
+      __syncwarp();
+      {
+        const int g = mt * 16 + (lane >> 2), t = lane & 3;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          *reinterpret_cast<uint32_t*>(so + g * 128 + ((j ^ (g & 7)) << 4) + t * 4) = pack_half2(o[j][0] * iA, o[j][1] * iA);
+          *reinterpret_cast<uint32_t*>(so + (g + 8) * 128 + ((j ^ ((g + 8) & 7)) << 4) + t * 4) = pack_half2(o[j][2] * iB, o[j][3] * iB);
+        }
+      }
+    }
+    __syncwarp();
+    {
+      const int head = pr % heads;
+      const int64_t bp = pr / heads;
+      const int px = bp % HW;
+      const int b = bp / HW;
+      __half* ob = out + ((int64_t)b * T * HW + px) * inner + head * 64;
+#pragma unroll
+      for (int i = 0; i < T / 4; i++) {
+        const int piece = lane + 32 * i;
+        const int r = piece >> 3, c = piece & 7;
+        const uint4 val = *reinterpret_cast<const uint4*>(so + r * 128 + ((c ^ (r & 7)) << 4));
+        *reinterpret_cast<uint4*>(ob + (int64_t)r * HW * inner + c * 8) = val;
+      }
+    }
+    __syncwarp();     // the tiles are reused by the prefetch issued two iterations from now
+  }
+}
+
+template <int T>
+static void launch_temporal_mma(const __half* qkv, __half* out, int B, int HW, int heads, float scale, cudaStream_t st) {
+  MUDG_CUDA(cudaFuncSetAttribute(temporal_attn_mma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, TaCfg<T>::SMEM));
+  const int64_t np = (int64_t)B * HW * heads;
+  const int64_t want = (np + TaCfg<T>::WARPS - 1) / TaCfg<T>::WARPS;
+  const int per_sm = TaCfg<T>::SMEM > 100 * 1024 ? 1 : 2;
+  const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count() * per_sm);
+  temporal_attn_mma_kernel<T><<<grid, TaCfg<T>::WARPS * 32, TaCfg<T>::SMEM, st>>>(qkv, out, B, HW, heads, scale * 1.4426950408889634f);
+  MUDG_CUDA(cudaGetLastError());
+}
+
 // ---------------------------------------------------------------- V -> V^T (the P V MMA wants its B operand K-major)
 // V rows [nbatch][len] of pitch elements, head h at columns [h*64, h*64+64)  ->  VT [nbatch][heads*64][len_pad], kv contiguous.
 __global__ void __launch_bounds__(256) transpose_v_kernel(const __half* __restrict__ V, int pitch, int len, int heads,
@@ -903,6 +1064,11 @@ void temporal_attention(const __half* qkv, __half* out, int B, int T, int HW, in
     const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count() * 4);
     temporal_attn16_kernel<<<grid, TA_WARPS * 32, TA_SMEM, st>>>(qkv, out, B, HW, heads, scale * 1.4426950408889634f);
     MUDG_CUDA(cudaGetLastError());
+    return;
+  }
+  if ((T == 32 || T == 64) && !generic_only) {
+    if (T == 32) launch_temporal_mma<32>(qkv, out, B, HW, heads, scale, st);
+    else launch_temporal_mma<64>(qkv, out, B, HW, heads, scale, st);
     return;
   }
   int group = 1;

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 CASES = ["flash_self_small", "flash_self_l1", "flash_self_ragged", "flash_cross", "flash_cross_else", "tattn16", "tattn4",
-         "tattn64", "gn_frame", "gn_time", "ln320", "ln1280", "ln512"]
+         "tattn64", "tattn32", "tattn64g", "tattn48", "gn_frame", "gn_time", "ln320", "ln1280", "ln512"]
 
 
 def ref_attn(q, k, v, heads, scale):
@@ -107,7 +107,10 @@ def run_case(name):
             torch.cuda.synchronize()
             report(name, f"tc{rep}", O, ref)
     elif name.startswith("tattn"):
-        T = int(name[5:])
+        generic = name.endswith("g")               # force the CUDA-core kernel (any T <= 64) where a tensor-core one exists
+        T = int(name[5:].rstrip("g"))
+        if generic:
+            check(L.mudg_test_set_knob(b"tattn_generic", 1))
         B, HW, heads = 2, 37, 5
         C = heads * 64
         qkv = torch.randn(B, T, HW, 3 * C, device=dev).half()
@@ -118,6 +121,7 @@ def run_case(name):
         O = torch.full((B, T, HW, C), float("nan"), device=dev).half()
         check(L.mudg_test_temporal_attn(ptr(qkv), ptr(O), B, T, HW, heads, f32(0.125), cur_stream()))
         torch.cuda.synchronize()
+        check(L.mudg_test_set_knob(b"reset", 0))
         report(name, "cuda", O, ref)
     elif name.startswith("gn_"):
         over_time = name == "gn_time"
