@@ -222,6 +222,25 @@ def main():
                         alphas_prev50=np.asarray(sampler.ddim_alphas_prev, dtype=np.float64),
                         timesteps50=np.asarray(sampler.ddim_timesteps))
     meta["ddim_small"] = dict(S=S, seed=123, cfg=7.5, rescale=0.7, eta=1.0)
+
+    # ---- the mask / x0 branch of ddim_sampling (ddim.py:173-180): known latent kept where mask == 1, noised to the
+    # step's level by q_sample (one extra draw per step) or taken clean (clean_cond=True) ----
+    gm = torch.Generator().manual_seed(77)
+    mask = (torch.rand(B, 1, T, H, W, generator=gm) > 0.5).float()
+    x0 = torch.randn(B, 4, T, H, W, generator=gm)
+    masked = {}
+    for clean in (False, True):
+        torch.manual_seed(321)
+        masked[clean], _ = sampler.sample(S=S, conditioning=cond, batch_size=B, shape=[4, T, H, W], verbose=False,
+                                          unconditional_guidance_scale=7.5, unconditional_conditioning=uc, eta=1.0,
+                                          cfg_img=None, mask=mask, x0=x0, fs=fs, timestep_spacing="uniform_trailing",
+                                          guidance_rescale=0.7, sparse_x=None, class_label=label2,
+                                          unconditional_conditioning_img_nonetext=None, clean_cond=clean)
+    print("ddim mask branch: |noised - clean| max =", float((masked[False] - masked[True]).abs().max()),
+          " |masked - unmasked| max =", float((masked[False] - samples).abs().max()))
+    np.savez_compressed(os.path.join(OUT, "ddim_mask_small.npz"), mask=mask.numpy(), x0=x0.numpy(),
+                        samples=masked[False].numpy(), samples_clean=masked[True].numpy())
+    meta["ddim_mask_small"] = dict(S=S, seed=321, mask_seed=77)
     with open(os.path.join(OUT, "meta.json"), "w") as f:
         json.dump(meta, f, indent=1, sort_keys=True)
     print("wrote", OUT)

@@ -712,10 +712,13 @@ def ddim_sample(unet_sd: SD, ucfg: UNetCfg, tab: DiffusionTables, *, S: int, sha
                 context: Tensor, uc_context: Optional[Tensor], class_label: Tensor, fs: Tensor,
                 cfg_scale: float = 1.0, guidance_rescale: float = 0.0, eta: float = 1.0,
                 spacing: str = "uniform_trailing", generator: Optional[torch.Generator] = None,
-                noises: Optional[List[Tensor]] = None, device="cpu", unet_fn=None) -> Tensor:
+                noises: Optional[List[Tensor]] = None, device="cpu", unet_fn=None, mask: Optional[Tensor] = None,
+                x0: Optional[Tensor] = None, clean_cond: bool = False) -> Tensor:
     """DDIMSampler.sample/ddim_sampling (ddim.py:60-203) with the hybrid DiffusionWrapper
     (ddpm3d.py:1320-1324).  RNG order: x_T first, then one draw per step (App. D #10);
     `noises` (len S+1) overrides the generator so CUDA/CPU runs can share draws.
+    mask / x0 (ddim.py:173-180): before every step the known latent x0 -- noised to the step's level by q_sample
+    (ddpm3d.py:305-308, ONE EXTRA draw per step, taken before the step's own) or clean -- replaces x where mask == 1.
     `unet_fn(xc, ts, class_label, context, fs)` replaces the oracle's own UNet forward (used to put the reference's
     autocast-fp16 UNetModel into the same loop when calibrating tolerances)."""
     if unet_fn is not None:
@@ -729,6 +732,14 @@ def ddim_sample(unet_sd: SD, ucfg: UNetCfg, tab: DiffusionTables, *, S: int, sha
     for i, step in enumerate(np.flip(sch.timesteps)):
         index = S - i - 1
         ts = torch.full((B,), int(step), dtype=torch.long, device=x.device)
+        if mask is not None:
+            assert x0 is not None and noises is None, "mask branch: draws come from the generator in the reference's order"
+            orig = x0
+            if not clean_cond:
+                a = tab.sqrt_alphas_cumprod.to(x.device)[int(step)]
+                b1 = tab.sqrt_one_minus_alphas_cumprod.to(x.device)[int(step)]
+                orig = a * x0 + b1 * torch.randn(shape, generator=generator, device=device)
+            x = orig * mask + (1.0 - mask) * x
         xc = torch.cat([x, c_concat], dim=1)
         v_c = unet_forward(unet_sd, ucfg, xc, ts, class_label, context, fs)
         v_u = None

@@ -120,6 +120,24 @@ def test_ddim_sample_matches_reference(golden_dir):
     assert float((frames - t(d["frames"]).float()).abs().max()) < 5e-3    # fixture stored as fp16
 
 
+def test_ddim_sample_mask_branch_matches_reference(golden_dir):
+    """ddim_sampling's mask / x0 blend (ddim.py:173-180), q_sample-noised and clean_cond, against the reference's samples."""
+    small = O.UNetCfg(model_channels=64, temporal_length=4)
+    sd = O.seeded_state_dict(O.unet_param_shapes(small), seed=1)
+    tab = O.make_tables(base_scale=0.3)
+    g = np.load(os.path.join(golden_dir, "unet_small.npz"))
+    d = np.load(os.path.join(golden_dir, "ddim_small.npz"))
+    m = np.load(os.path.join(golden_dir, "ddim_mask_small.npz"))
+    t = torch.from_numpy
+    for clean, key in ((False, "samples"), (True, "samples_clean")):
+        torch.manual_seed(321)
+        out = O.ddim_sample(sd, small, tab, S=3, shape=(2, 4, 4, 16, 16), c_concat=t(d["c_concat"]), context=t(g["ctx"]),
+                            uc_context=t(d["uc_ctx"]), class_label=t(g["lab"]), fs=t(g["fs"]), cfg_scale=7.5, guidance_rescale=0.7,
+                            eta=1.0, mask=t(m["mask"]), x0=t(m["x0"]), clean_cond=clean)
+        assert float((out - t(m[key])).abs().max()) < 1e-3, (clean, float((out - t(m[key])).abs().max()))
+    assert float((t(m["samples"]) - t(d["samples"])).abs().max()) > 1.0      # the mask changes the result
+
+
 def test_multicond_sample_matches_reference(golden_dir):
     """DDIMSampler_multicond (three UNet evaluations per step) restated in the oracle vs the reference's own output."""
     d = np.load(os.path.join(golden_dir, "ddim_multicond_small.npz"))
