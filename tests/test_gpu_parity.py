@@ -83,7 +83,8 @@ def test_unet_forward_vs_reference_golden(engine, golden_dir):
         y = engine.unet_forward(t("x"), t("ts"), t("lab"), t("fs"))
         torch.cuda.synchronize()
         err = (y.float().cpu() - torch.from_numpy(g[yk])).abs()
-        assert float(err.max()) < 0.03 and float(err.mean()) < 0.004, (ck, float(err.max()), float(err.mean()))
+        print(f"MEASURED unet small {ck}: max {float(err.max()):.5f} mean {float(err.mean()):.6f}")
+        assert float(err.max()) < 0.014 and float(err.mean()) < 0.0025, (ck, float(err.max()), float(err.mean()))     # 2x measured (0.0066 / 0.0012)
 
 
 def test_unet_linearity_in_batch(engine, golden_dir):
@@ -105,7 +106,8 @@ def test_vae_decode_vs_reference_golden(engine, golden_dir):
     dec = engine.vae_decode(torch.from_numpy(g["z"]).cuda())
     torch.cuda.synchronize()
     err = (dec.float().cpu() - torch.from_numpy(g["dec"])).abs()
-    assert float(err.max()) < 0.03, float(err.max())
+    print(f"MEASURED vae decode small: max {float(err.max()):.5f}")
+    assert float(err.max()) < 0.014, float(err.max())          # 2x measured (0.0066)
 
 
 def test_vae_encode_vs_reference_golden(engine, golden_dir):
@@ -113,7 +115,8 @@ def test_vae_encode_vs_reference_golden(engine, golden_dir):
     mom = engine.vae_encode_moments(torch.from_numpy(g["x"]).cuda())
     torch.cuda.synchronize()
     err = (mom.cpu() - torch.from_numpy(g["moments"])).abs()
-    assert float(err.max()) < 0.03, float(err.max())
+    print(f"MEASURED vae encode small: max {float(err.max()):.5f}")
+    assert float(err.max()) < 0.008, float(err.max())          # 2x measured (0.0039)
 
 
 def test_ddim_step_vs_oracle(engine):
@@ -187,7 +190,8 @@ def test_sampler_public_api_vs_reference_golden(golden_dir):
     assert float(err.max()) < 0.11 and float(psnr) > 46.0           # measured 0.054 / 52.4 dB (small config, 3 steps)
     assert set(inter) == {"x_inter", "pred_x0"}
     ferr = (frames.float().cpu() - torch.from_numpy(d["frames"]).float()).abs()
-    assert frames.shape == (2, 3, 4, 128, 128) and float(ferr.max()) < 0.25, float(ferr.max())
+    print(f"MEASURED decoded frames of the 3-step sample: max {float(ferr.max()):.4f} mean {float(ferr.mean()):.5f}")
+    assert frames.shape == (2, 3, 4, 128, 128) and float(ferr.max()) < 0.09 and float(ferr.mean()) < 0.01, float(ferr.max())   # 2x measured (0.041 / 0.0045)
     # the mask / x0 branch (ddim.py:173-180): q_sample-noised (one extra draw per step, before the step's own) and clean_cond
     m = np.load(os.path.join(golden_dir, "ddim_mask_small.npz"))
     for clean, key in ((False, "samples"), (True, "samples_clean")):
@@ -395,7 +399,7 @@ def test_multicond_sampler_vs_reference_golden(golden_dir):
     err = (z.float().cpu() - ref).abs()
     psnr = 10 * torch.log10(ref.abs().max() ** 2 / ((z.float().cpu() - ref) ** 2).mean())
     print(f"2-step multicond sample: max|d|={float(err.max()):.4f} latent PSNR={float(psnr):.1f} dB")
-    assert float(err.max()) < 0.15 and float(psnr) > 40.0
+    assert float(err.max()) < 0.08 and float(psnr) > 46.0           # measured 0.037 / 52.6 dB
 
 
 def test_resampler_vs_reference_golden(golden_dir):
@@ -412,7 +416,8 @@ def test_resampler_vs_reference_golden(golden_dir):
     y = m(torch.from_numpy(g["x"]).cuda())
     torch.cuda.synchronize()
     err = (y.float().cpu() - torch.from_numpy(g["y"])).abs()
-    assert y.shape == (3, 16, 128) and float(err.max()) < 0.03 and float(err.mean()) < 0.004, (float(err.max()), float(err.mean()))
+    print(f"MEASURED resampler small: max {float(err.max()):.5f} mean {float(err.mean()):.6f}")
+    assert y.shape == (3, 16, 128) and float(err.max()) < 0.012 and float(err.mean()) < 0.002, (float(err.max()), float(err.mean()))
     # full size (infer yaml): [2, 257, 1280] -> [2, 256, 1024]
     full = dict(dim=1024, depth=4, dim_head=64, heads=12, num_queries=16, embedding_dim=1280, output_dim=1024, ff_mult=4,
                 video_length=16)
@@ -426,7 +431,8 @@ def test_resampler_vs_reference_golden(golden_dir):
     out = mf(x.cuda())
     torch.cuda.synchronize()
     ferr = (out.float().cpu() - ref).abs()
-    assert out.shape == (2, 256, 1024) and float(ferr.max()) < 0.05 and float(ferr.mean()) < 0.005, (float(ferr.max()), float(ferr.mean()))
+    print(f"MEASURED resampler full: max {float(ferr.max()):.5f} mean {float(ferr.mean()):.6f}")
+    assert out.shape == (2, 256, 1024) and float(ferr.max()) < 0.016 and float(ferr.mean()) < 0.002, (float(ferr.max()), float(ferr.mean()))
     # batch independence (size-independent property): sample 1 alone == sample 1 of the batch
     one = mf(x[1:2].cuda())
     assert float((one[0].float() - out[1].float()).abs().max()) < 2e-2
@@ -456,14 +462,16 @@ def test_unet_full_size_properties():
     torch.cuda.synchronize()
     assert y_eager.shape == (N, 4, T, h, w) and bool(torch.isfinite(y_eager.float()).all())
     assert float(y_eager.float().abs().max()) > 0.1
-    assert float((y_cap.float() - y_eager.float()).abs().max()) < 2e-2      # GroupNorm sums use atomics: not bitwise
-    assert float((y_rep.float() - y_cap.float()).abs().max()) < 2e-2
+    # measured 0.0 for both; the fp64 GroupNorm atomics are the only order-dependent arithmetic, far below fp16 resolution
+    assert float((y_cap.float() - y_eager.float()).abs().max()) < 1e-3
+    assert float((y_rep.float() - y_cap.float()).abs().max()) < 1e-3
     for i in range(N):
         eng.set_context(ctx[i:i + 1].contiguous(), T)
         one = eng.unet_forward(x[i:i + 1].contiguous(), ts[i:i + 1], lab[i:i + 1], fs[i:i + 1])
         torch.cuda.synchronize()
         d = (one[0].float() - y_eager[i].float()).abs()
-        assert float(d.max()) < 5e-2 and float(d.mean()) < 2e-3, (i, float(d.max()), float(d.mean()))
+        print(f"MEASURED full-size N=2 vs N=1 sample {i}: max {float(d.max()):.5f} mean {float(d.mean()):.6f}; eager/capture {float((y_cap.float() - y_eager.float()).abs().max()):.5f} replay {float((y_rep.float() - y_cap.float()).abs().max()):.5f}")
+        assert float(d.max()) < 1.4e-2 and float(d.mean()) < 2.2e-3, (i, float(d.max()), float(d.mean()))     # 2x measured (0.0068 / 0.0011)
     del eng
     torch.cuda.empty_cache()
 
