@@ -367,10 +367,14 @@ __global__ void geglu_interleave_kernel(const __half* __restrict__ w, const floa
 
 // ---------------------------------------------------------------- embeddings
 // [cos | sin] sinusoid of an int64 index (utils_diffusion.py:8-28)
-__global__ void sinusoid_kernel(const int64_t* __restrict__ t, float* __restrict__ out, int B, int dim) {
+// blockIdx.y picks the index vector (timestep / class label / fps): out [3][B][dim]
+__global__ void sinusoid_kernel(const int64_t* __restrict__ t0, const int64_t* __restrict__ t1, const int64_t* __restrict__ t2,
+                                float* __restrict__ out, int B, int dim) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int half = dim / 2;
   if (i >= B * half) return;
+  const int64_t* t = blockIdx.y == 0 ? t0 : (blockIdx.y == 1 ? t1 : t2);
+  out += (size_t)blockIdx.y * B * dim;
   const int b = i / half, k = i % half;
   const float freq = expf(-logf(10000.f) * (float)k / (float)half);
   const float arg = (float)t[b] * freq;
@@ -378,26 +382,43 @@ __global__ void sinusoid_kernel(const int64_t* __restrict__ t, float* __restrict
   out[b * dim + half + k] = sinf(arg);
 }
 
-// y[b][n] (+)= sum_k act(x[b][k]) * W[n][k] + bias[n]; warp per output; fp32 activations, fp16 weights
-__global__ void small_linear_kernel(const float* __restrict__ x, const __half* __restrict__ W,
-                                    const float* __restrict__ bias, float* __restrict__ y, int Bn, int N, int K,
-                                    int silu_in, int accumulate) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= Bn * N) return;
-  const int b = warp / N, n = warp % N;
-  const float* xr = x + (int64_t)b * K;
-  const __half* wr = W + (int64_t)n * K;
+// Up to 24 small Linear layers in ONE launch (the three embedding MLPs, the 22 ResBlock emb_layers): warp per output,
+// fp32 activations, fp16 weights read as 128-bit vectors.  Separate outputs (job j: y_j[b][n], n < n_out_j) or, with
+// `sum`, one output y_0[b][n] = sum_j (x_j[b] . W_j[n] + bias_j[n]); `silu_out` applies SiLU to what is stored.
+__global__ void __launch_bounds__(256) batched_linear_kernel(const LinearBatch lb) {
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int per_row = lb.sum ? lb.off[1] : lb.off[lb.count];
+  if (warp >= (int64_t)lb.Bn * per_row) return;
+  const int b = (int)(warp / per_row), gn = (int)(warp % per_row);
+  int j0 = 0, j1 = lb.count, n = gn;
+  if (!lb.sum) {
+    while (gn >= lb.off[j0 + 1]) j0++;
+    j1 = j0 + 1;
+    n = gn - lb.off[j0];
+  }
   float acc = 0.f;
-  for (int k = lane; k < K; k += 32) {
-    float xv = xr[k];
-    if (silu_in) xv = xv / (1.f + expf(-xv));
-    acc += xv * __half2float(wr[k]);
+  for (int j = j0; j < j1; j++) {
+    const float* xr = lb.x[j] + (int64_t)b * lb.K;
+    const __half* wr = lb.W[j] + (int64_t)n * lb.K;
+    if ((lb.K & 7) == 0) {
+      for (int k = lane * 8; k < lb.K; k += 256) {
+        const uint4 w8 = __ldg(reinterpret_cast<const uint4*>(wr + k));
+        const float4 x0 = *reinterpret_cast<const float4*>(xr + k), x1 = *reinterpret_cast<const float4*>(xr + k + 4);
+        float w[8];
+        unpack8(w8, w);
+        acc = fmaf(x0.x, w[0], acc); acc = fmaf(x0.y, w[1], acc); acc = fmaf(x0.z, w[2], acc); acc = fmaf(x0.w, w[3], acc);
+        acc = fmaf(x1.x, w[4], acc); acc = fmaf(x1.y, w[5], acc); acc = fmaf(x1.z, w[6], acc); acc = fmaf(x1.w, w[7], acc);
+      }
+    } else {
+      for (int k = lane; k < lb.K; k += 32) acc = fmaf(xr[k], __half2float(wr[k]), acc);
+    }
+    if (lane == 0 && lb.bias[j] != nullptr) acc += lb.bias[j][n];
   }
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) {
-    float v = acc + (bias ? bias[n] : 0.f);
-    if (accumulate) v += y[(int64_t)b * N + n];
-    y[(int64_t)b * N + n] = v;
+    if (lb.silu_out) acc = acc / (1.f + expf(-acc));
+    lb.y[lb.sum ? 0 : j0][(int64_t)b * (lb.sum ? lb.off[1] : lb.off[j0 + 1] - lb.off[j0]) + n] = acc;
   }
 }
 
@@ -716,20 +737,17 @@ void geglu_interleave(const __half* w, const float* b, __half* wo, float* bo, in
   MUDG_CUDA(cudaGetLastError());
 }
 
-void sinusoid(const int64_t* t, float* out, int B, int dim, cudaStream_t st) {
+void sinusoid3(const int64_t* t, const int64_t* label, const int64_t* fs, float* out, int B, int dim, cudaStream_t st) {
   const int n = B * (dim / 2);
-  sinusoid_kernel<<<(n + 127) / 128, 128, 0, st>>>(t, out, B, dim);
+  sinusoid_kernel<<<dim3((n + 127) / 128, 3), 128, 0, st>>>(t, label, fs, out, B, dim);
   MUDG_CUDA(cudaGetLastError());
 }
-
-void small_linear(const float* x, const __half* W, const float* bias, float* y, int Bn, int N, int K, bool silu_in,
-                  bool accumulate, cudaStream_t st) {
-  const int64_t threads = (int64_t)Bn * N * 32;
-  small_linear_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, W, bias, y, Bn, N, K, silu_in ? 1 : 0,
-                                                                        accumulate ? 1 : 0);
+void batched_linear(const LinearBatch& lb, cudaStream_t st) {
+  MUDG_REQUIRE(lb.count >= 1 && lb.count <= LinearBatch::MAX_JOBS, "batched_linear: %d jobs", lb.count);
+  const int64_t warps = (int64_t)lb.Bn * (lb.sum ? lb.off[1] : lb.off[lb.count]);
+  batched_linear_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(lb);
   MUDG_CUDA(cudaGetLastError());
 }
-
 void to_channels_last(const void* x, bool x_fp32, __half* y, int B, int C, int64_t R, int Cpad, cudaStream_t st) {
   const int64_t total = (int64_t)B * R * Cpad;
   if (x_fp32)

@@ -880,36 +880,60 @@ Act Model::run_block(Act h, const Block& b, bool owns_input, GnReq* in_gn) {
 // time_embed(t) + class_embed(label) + fps_embedding(fs), then every ResBlock's Linear(SiLU(emb))
 // (openaimodel3d.py:569-576,594-602 and :219).  Computed on N rows, not N*T (emb is repeated over frames).
 void Model::compute_embeddings(const int64_t* t, const int64_t* label, const int64_t* fs, int N) {
+  // emb = time_embed(sin(t)) + class_embed(sin(label)) + fps_embedding(sin(fs)) (openaimodel3d.py:567-579); every ResBlock
+  // then applies emb_layers = SiLU -> Linear (:169-176).  Four launches: the three sinusoids, the three first MLP layers
+  // (+ SiLU), the three second layers summed (+ the emb_layers' SiLU), and all emb_layers Linears of the graph at once.
   const int mc = ucfg_.model_channels, ted = 4 * mc;
-  float* sin_buf = static_cast<float*>(alloc_bytes(sizeof(float) * N * mc));
-  float* hid = static_cast<float*>(alloc_bytes(sizeof(float) * N * ted));
-  float* emb = static_cast<float*>(alloc_bytes(sizeof(float) * N * ted));
+  float* sin_buf = static_cast<float*>(alloc_bytes(sizeof(float) * 3 * N * mc));
+  float* hid = static_cast<float*>(alloc_bytes(sizeof(float) * 3 * N * ted));
+  float* emb = static_cast<float*>(alloc_bytes(sizeof(float) * N * ted));       // SiLU(emb): the only form the graph uses
   const char* names[3] = {"time_embed", "class_embed", "fps_embedding"};
-  const int64_t* idx[3] = {t, label, fs};
   ProfScope ps_embed(PF_EMBED, 0.0, 0.0, st_, "time/class/fps MLPs + emb_layers");
   if (live()) {
+    sinusoid3(t, label, fs, sin_buf, N, mc, st_);
+    LinearBatch l0, l2;
+    l0.count = l2.count = 3;
+    l0.K = mc; l2.K = ted;
+    l0.Bn = l2.Bn = N;
+    l0.silu_out = 1;                      // MLP = Linear -> SiLU -> Linear
+    l2.sum = 1; l2.silu_out = 1;
+    l0.off[0] = l2.off[0] = 0;
     for (int i = 0; i < 3; i++) {
       const std::string n = names[i];
-      sinusoid(idx[i], sin_buf, N, mc, st_);
-      small_linear(sin_buf, ws_->W(n + ".0.weight").w, ws_->V(n + ".0.bias").p, hid, N, ted, mc, false, false, st_);
-      small_linear(hid, ws_->W(n + ".2.weight").w, ws_->V(n + ".2.bias").p, emb, N, ted, ted, true, i > 0, st_);
-      launches += 3;
+      l0.x[i] = sin_buf + (size_t)i * N * mc; l0.W[i] = ws_->W(n + ".0.weight").w; l0.bias[i] = ws_->V(n + ".0.bias").p;
+      l0.y[i] = hid + (size_t)i * N * ted; l0.off[i + 1] = (i + 1) * ted;
+      l2.x[i] = hid + (size_t)i * N * ted; l2.W[i] = ws_->W(n + ".2.weight").w; l2.bias[i] = ws_->V(n + ".2.bias").p;
+      l2.y[i] = emb; l2.off[i + 1] = ted;
     }
+    batched_linear(l0, st_);
+    batched_linear(l2, st_);
+    launches += 3;
   }
   emb_out_.assign(n_res_, nullptr);
+  LinearBatch le;
+  le.K = ted; le.Bn = N; le.off[0] = 0;
+  auto flush = [&]() {
+    if (le.count && live()) {
+      batched_linear(le, st_);
+      launches++;
+    }
+    le.count = 0;
+  };
   auto visit = [&](const Layer& l) {
     if (l.kind != "res") return;
     float* e = static_cast<float*>(alloc_bytes(sizeof(float) * N * l.cout));
     emb_out_[l.res_index] = e;
     if (live()) {
-      small_linear(emb, ws_->W(l.prefix + ".emb_layers.1.weight").w, ws_->V(l.prefix + ".emb_layers.1.bias").p, e, N, l.cout,
-                   ted, true, false, st_);
-      launches++;
+      const int j = le.count++;
+      le.x[j] = emb; le.W[j] = ws_->W(l.prefix + ".emb_layers.1.weight").w; le.bias[j] = ws_->V(l.prefix + ".emb_layers.1.bias").p;
+      le.y[j] = e; le.off[j + 1] = le.off[j] + l.cout;
+      if (le.count == LinearBatch::MAX_JOBS) flush();
     }
   };
   for (auto& b : in_blocks_) for (auto& l : b.layers) visit(l);
   for (auto& l : mid_.layers) visit(l);
   for (auto& b : out_blocks_) for (auto& l : b.layers) visit(l);
+  flush();
   release_bytes(sin_buf);
   release_bytes(hid);
   release_bytes(emb);

@@ -38,9 +38,20 @@ void to_channels_last(const void* x, bool x_fp32, __half* y, int B, int C, int64
 void from_channels_last(const __half* y, __half* out, int B, int C, int64_t R, int Cp, cudaStream_t st);
 void gather_rows_f16(const void* src, bool src_fp32, __half* dst, int B, int src_rows, int r0, int nrows, int cols,
                      cudaStream_t st);
-void sinusoid(const int64_t* t, float* out, int B, int dim, cudaStream_t st);
-void small_linear(const float* x, const __half* W, const float* bias, float* y, int Bn, int N, int K, bool silu_in,
-                  bool accumulate, cudaStream_t st);
+void sinusoid3(const int64_t* t, const int64_t* label, const int64_t* fs, float* out /*[3][B][dim]*/, int B, int dim,
+               cudaStream_t st);
+// Small Linear layers batched into one launch (embedding MLPs, ResBlock emb_layers): y_j[b][:] = x_j[b] W_j^T + bias_j for
+// job j (n_out_j = off[j+1] - off[j]); with `sum` all jobs share n_out = off[1] and y[0] receives their sum.  fp32 in / out.
+struct LinearBatch {
+  static constexpr int MAX_JOBS = 24;
+  const float* x[MAX_JOBS];
+  const __half* W[MAX_JOBS];
+  const float* bias[MAX_JOBS];
+  float* y[MAX_JOBS];
+  int off[MAX_JOBS + 1];
+  int count = 0, K = 0, Bn = 0, sum = 0, silu_out = 0;
+};
+void batched_linear(const LinearBatch& lb, cudaStream_t st);
 
 // ---- attention (attn.cu)
 // Flash attention, head dim 64, fp16 in/out, tcgen05.  Q rows: [F frames][Nq tokens], row pitch q_pitch elements,
