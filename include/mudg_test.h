@@ -51,6 +51,9 @@ MUDG_EXPORT int mudg_test_temporal_attn(const void* qkv, void* out, int B, int T
                                         void* stream);
 MUDG_EXPORT int mudg_test_groupnorm(const void* x, void* y, int S, int64_t rows_per_sample, int C, const float* gamma,
                                     const float* beta, float eps, int silu, void* stream);
+/* the one-kernel GroupNorm (statistics + apply from shared memory); fails when the sample does not fit */
+MUDG_EXPORT int mudg_test_groupnorm_small(const void* x, void* y, int S, int64_t rows_per_sample, int C, const float* gamma,
+                                          const float* beta, float eps, int silu, void* stream);
 MUDG_EXPORT int mudg_test_layernorm(const void* x, void* y, const float* gamma, const float* beta, int64_t rows, int C,
                                     void* stream);
 MUDG_EXPORT int mudg_test_ln_stats(const void* x, void* mean_rstd, int64_t rows, int C, void* stream);

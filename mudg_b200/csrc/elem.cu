@@ -148,6 +148,88 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict
   for (; r < row_end; r += rstep) *reinterpret_cast<uint4*>(yb + r * C) = one(__ldg(reinterpret_cast<const uint4*>(xb + r * C)));
 }
 
+// ---------------------------------------------------------------- GroupNorm in ONE kernel for samples that fit shared memory
+// One CTA per (sample, slab of Cs channels = whole groups, multiple of 8): the [R][Cs] slab is read once into shared
+// memory with its per-channel sums, reduced in a FIXED order (no atomics, no pre-zeroed buffer, no statistics pass), then
+// normalised (+ SiLU) from shared memory.  2 passes over HBM instead of 3 and 1 launch instead of 3 (memset, statistics,
+// apply): the levels 1-3 of MDM512 and 2-3 of MDM1024, where the tensors are a few MB and launches dominate.
+constexpr int GNS_THREADS = 256;
+__global__ void __launch_bounds__(GNS_THREADS) gn_small_kernel(const __half* __restrict__ x, __half* __restrict__ y,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               int R, int C, int cpg, int Cs, float eps, int act) {
+  extern __shared__ __align__(16) unsigned char gns_smem[];
+  const int vpr = Cs >> 3, rstep = GNS_THREADS / vpr;
+  uint4* slab = reinterpret_cast<uint4*>(gns_smem);                        // [R][vpr]
+  float* part = reinterpret_cast<float*>(slab + (size_t)R * vpr);          // [rstep][Cs][2]
+  double* csum = reinterpret_cast<double*>(part + (size_t)rstep * Cs * 2); // [Cs][2]
+  float* stat = reinterpret_cast<float*>(csum + Cs * 2);                   // [groups in slab][2]: mean, rstd
+  const int s = blockIdx.y, c0 = blockIdx.x * Cs;
+  const int v = threadIdx.x % vpr, r0 = threadIdx.x / vpr;
+  const __half* xb = x + ((int64_t)s * R) * C + c0 + v * 8;
+  if (r0 < rstep) {
+    float sm[8], sq[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) sm[i] = sq[i] = 0.f;
+    for (int r = r0; r < R; r += rstep) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(xb + (int64_t)r * C));
+      slab[r * vpr + v] = raw;
+      float f[8];
+      unpack8(raw, f);
+#pragma unroll
+      for (int i = 0; i < 8; i++) { sm[i] += f[i]; sq[i] = fmaf(f[i], f[i], sq[i]); }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      part[((size_t)r0 * Cs + v * 8 + i) * 2] = sm[i];
+      part[((size_t)r0 * Cs + v * 8 + i) * 2 + 1] = sq[i];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < Cs) {                      // per-channel totals, rows partitions summed in order
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < rstep; k++) {
+      a += (double)part[((size_t)k * Cs + threadIdx.x) * 2];
+      b += (double)part[((size_t)k * Cs + threadIdx.x) * 2 + 1];
+    }
+    csum[threadIdx.x * 2] = a;
+    csum[threadIdx.x * 2 + 1] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x < Cs / cpg) {
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < cpg; k++) {
+      a += csum[(threadIdx.x * cpg + k) * 2];
+      b += csum[(threadIdx.x * cpg + k) * 2 + 1];
+    }
+    const double count = (double)R * cpg, mean = a / count;
+    double var = b / count - mean * mean;
+    if (var < 0) var = 0;
+    stat[threadIdx.x * 2] = (float)mean;
+    stat[threadIdx.x * 2 + 1] = rsqrtf((float)var + eps);
+  }
+  __syncthreads();
+  if (r0 >= rstep) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int cl = v * 8 + i, g = cl / cpg;
+    sc[i] = __ldg(gamma + c0 + cl) * stat[g * 2 + 1];
+    sh[i] = __ldg(beta + c0 + cl) - stat[g * 2] * sc[i];
+  }
+  __half* yb = y + ((int64_t)s * R) * C + c0 + v * 8;
+  for (int r = r0; r < R; r += rstep) {
+    float f[8];
+    unpack8(slab[r * vpr + v], f);
+#pragma unroll
+    for (int i = 0; i < 8; i++) f[i] = fmaf(f[i], sc[i], sh[i]);
+    if (act) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) f[i] = silu(f[i]);
+    }
+    *reinterpret_cast<uint4*>(yb + (int64_t)r * C) = pack8(f);
+  }
+}
+
 // ---------------------------------------------------------------- LayerNorm (warp per row, row kept in registers)
 template <int MAXV>
 __global__ void layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ gamma,
@@ -622,6 +704,39 @@ void gn_apply(const __half* x, __half* y, const double* sums, int S, int64_t row
   gn_geometry(S, rows_per_sample, C, threads, rpb, chunks);
   gn_apply_kernel<<<dim3(chunks, S), threads, 0, st>>>(x, y, sums, gamma, beta, rows_per_sample, C, C / 32,
                                                      (double)rows_per_sample * (C / 32), eps, rpb, silu_act ? 1 : 0);
+  MUDG_CUDA(cudaGetLastError());
+}
+
+// slab width for gn_small_kernel: whole groups and whole 128-bit vectors
+static int gn_small_slab(int C) {
+  const int cpg = C / 32;
+  int cs = cpg;
+  while (cs % 8) cs += cpg;
+  return cs;
+}
+static size_t gn_small_smem(int64_t rows_per_sample, int Cs) {
+  const int rstep = GNS_THREADS / (Cs / 8);
+  return (size_t)rows_per_sample * Cs * 2 + (size_t)rstep * Cs * 2 * sizeof(float) + (size_t)Cs * 2 * sizeof(double) + 64 * sizeof(float);
+}
+bool gn_small_ok(int S, int64_t rows_per_sample, int C) {
+  if (C % 32 != 0 || rows_per_sample < 1 || rows_per_sample > 65535) return false;
+  const int Cs = gn_small_slab(C);
+  if (Cs > GNS_THREADS || Cs / 8 > GNS_THREADS || C % Cs != 0) return false;
+  // measured (tests/gpu_ab_knob.py gn_small): -3.1 % on the MDM512 forward; at MDM1024 level 2 (47 MB tensors, bandwidth-bound,
+  // the two-pass form re-reads from L2) the one-kernel form is slightly slower, so it is kept to tensors of a few MB
+  // -- and to at most 4 slabs per SM (MDM1024 level 3: 1 024 slabs of 11 KB, +0.3 % on that forward).
+  if ((int64_t)S * rows_per_sample * C * 2 > (int64_t)16 << 20) return false;
+  const int64_t ctas = (int64_t)S * (C / Cs);
+  return gn_small_smem(rows_per_sample, Cs) <= 160 * 1024 && ctas >= 16 && ctas <= 4 * (int64_t)sm_count();
+}
+void gn_small(const __half* x, __half* y, int S, int64_t rows_per_sample, int C, const float* gamma, const float* beta,
+              float eps, bool silu_act, cudaStream_t st) {
+  MUDG_REQUIRE(gn_small_ok(S, rows_per_sample, C), "gn_small: [%d][%lld][%d] does not fit", S, (long long)rows_per_sample, C);
+  const int Cs = gn_small_slab(C);
+  const size_t smem = gn_small_smem(rows_per_sample, Cs);
+  MUDG_CUDA(cudaFuncSetAttribute(gn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  gn_small_kernel<<<dim3(C / Cs, S), GNS_THREADS, smem, st>>>(x, y, gamma, beta, (int)rows_per_sample, C, C / 32, Cs, eps,
+                                                              silu_act ? 1 : 0);
   MUDG_CUDA(cudaGetLastError());
 }
 

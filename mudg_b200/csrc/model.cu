@@ -465,11 +465,15 @@ Act Model::group_norm(const Act& x, const std::string& p, float eps, bool silu, 
     MUDG_REQUIRE(g.n == x.C, "GroupNorm %s: %d channels vs activation %d", p.c_str(), g.n, x.C);
     // ideal traffic: 1 read + 1 write of the activation
     ProfScope ps(PF_GN, 0.0, 4.0 * (double)x.numel(), st_, fmt("%lldx%d%s", (long long)x.rows(), x.C, pre->fused ? ":fused" : "").c_str());
-    if (!pre->fused) {
-      gn_stats(x.p, S, rps, x.C, pre->sums, st_);
-      launches++;
+    if (!pre->fused && knobs().gn_small != 0 && gn_small_ok(S, rps, x.C)) {
+      gn_small(x.p, y.p, S, rps, x.C, g.p, b.p, eps, silu, st_);          // statistics + apply in one kernel
+    } else {
+      if (!pre->fused) {
+        gn_stats(x.p, S, rps, x.C, pre->sums, st_);
+        launches++;
+      }
+      gn_apply(x.p, y.p, pre->sums, S, rps, x.C, g.p, b.p, eps, silu, st_);
     }
-    gn_apply(x.p, y.p, pre->sums, S, rps, x.C, g.p, b.p, eps, silu, st_);
     launches++;
   }
   release_bytes(pre->sums);

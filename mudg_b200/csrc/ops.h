@@ -10,6 +10,10 @@ namespace mudg {
 void gn_stats(const __half* x, int S, int64_t rows_per_sample, int C, double* sums, cudaStream_t st);
 void gn_apply(const __half* x, __half* y, const double* sums, int S, int64_t rows_per_sample, int C, const float* gamma,
               const float* beta, float eps, bool silu_act, cudaStream_t st);
+// GroupNorm (+ SiLU) in one kernel, statistics included, when a (sample, channel slab) fits shared memory (gn_small_ok)
+bool gn_small_ok(int S, int64_t rows_per_sample, int C);
+void gn_small(const __half* x, __half* y, int S, int64_t rows_per_sample, int C, const float* gamma, const float* beta,
+              float eps, bool silu_act, cudaStream_t st);
 // GroupNorm without activation folded into the Linear W [N][K] that consumes it: per-sample weights Ws [S][N][K] (fp16)
 // and bias rows cs [S][N] (fp32, WITHOUT the layer's own bias); see TapGemm::wt_samples
 void gn_fold_weights(const __half* W, const double* sums, int S, int64_t rows_per_sample, const float* gamma,

@@ -303,6 +303,7 @@ MUDG_EXPORT int mudg_test_set_knob(const char* name, int value) {
   else if (n == "tattn_generic") k.tattn_generic = value;
   else if (n == "gn_fuse") k.gn_fuse = value;
   else if (n == "gn_fold") k.gn_fold = value;
+  else if (n == "gn_small") k.gn_small = value;
   else if (n == "reset") k = Knobs{};
   else MUDG_REQUIRE(false, "unknown knob %s", n.c_str());
   MUDG_API_END
@@ -463,6 +464,13 @@ MUDG_EXPORT int mudg_test_groupnorm(const void* x, void* y, int Sn, int64_t rows
            S(stream));
   MUDG_CUDA(cudaStreamSynchronize(S(stream)));
   cudaFree(sums);
+  MUDG_API_END
+}
+
+MUDG_EXPORT int mudg_test_groupnorm_small(const void* x, void* y, int Sn, int64_t rows_per_sample, int C, const float* gamma,
+                                          const float* beta, float eps, int silu, void* stream) {
+  MUDG_API_BEGIN
+  gn_small(static_cast<const __half*>(x), static_cast<__half*>(y), Sn, rows_per_sample, C, gamma, beta, eps, silu != 0, S(stream));
   MUDG_API_END
 }
 

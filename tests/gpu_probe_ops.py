@@ -8,7 +8,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 CASES = ["flash_self_small", "flash_self_l1", "flash_self_ragged", "flash_cross", "flash_cross_else", "tattn16", "tattn4",
-         "tattn64", "tattn32", "tattn64g", "tattn48", "gn_frame", "gn_time", "ln320", "ln1280", "ln512"]
+         "tattn64", "tattn32", "tattn64g", "tattn48", "gns_frame_c320", "gns_frame_c1280", "gns_time_c640", "gns_frame_c64", "gns_big_c1280",
+         "gn_frame", "gn_time", "ln320", "ln1280", "ln512"]
 
 
 def ref_attn(q, k, v, heads, scale):
@@ -123,6 +124,30 @@ def run_case(name):
         torch.cuda.synchronize()
         check(L.mudg_test_set_knob(b"reset", 0))
         report(name, "cuda", O, ref)
+    elif name.startswith("gns_"):
+        # one-kernel GroupNorm (+ SiLU / no activation) against F.group_norm: per frame / per sample over T, several widths
+        over_time = "time" in name
+        C = int(name.split("_c")[1])
+        B, T, H, W = (2, 4, 9, 16) if "big" not in name else (1, 16, 18, 32)
+        x = (torch.randn(B, T, H, W, C, device=dev) * 2 + 0.5).half()
+        g = torch.randn(C, device=dev); b = torch.randn(C, device=dev)
+        for act in (1, 0):
+            if over_time:
+                ref = Fn.group_norm(x.float().permute(0, 4, 1, 2, 3), 32, g, b, 1e-6).permute(0, 2, 3, 4, 1)
+                S, rps = B, T * H * W
+            else:
+                ref = Fn.group_norm(x.float().reshape(B * T, H, W, C).permute(0, 3, 1, 2), 32, g, b, 1e-6).permute(0, 2, 3, 1).reshape(B, T, H, W, C)
+                S, rps = B * T, H * W
+            if act:
+                ref = Fn.silu(ref)
+            y = torch.full_like(x, float("nan"))
+            check(L.mudg_test_groupnorm_small(ptr(x), ptr(y), S, ctypes.c_int64(rps), C, ptr(g), ptr(b), f32(1e-6), act, cur_stream()))
+            torch.cuda.synchronize()
+            report(name, f"small act={act}", y, ref)
+            y2 = torch.full_like(x, float("nan"))
+            check(L.mudg_test_groupnorm(ptr(x), ptr(y2), S, ctypes.c_int64(rps), C, ptr(g), ptr(b), f32(1e-6), act, cur_stream()))
+            torch.cuda.synchronize()
+            report(name, f"vs two-pass act={act}", y, y2.float())
     elif name.startswith("gn_"):
         over_time = name == "gn_time"
         B, T, H, W, C = 2, 4, 9, 16, 320
