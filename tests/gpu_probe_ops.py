@@ -128,7 +128,7 @@ def run_case(name):
         # one-kernel GroupNorm (+ SiLU / no activation) against F.group_norm: per frame / per sample over T, several widths
         over_time = "time" in name
         C = int(name.split("_c")[1])
-        B, T, H, W = (2, 4, 9, 16) if "big" not in name else (1, 16, 18, 32)
+        B, T, H, W = (2, 4, 9, 16) if "big" not in name else (1, 8, 18, 32)
         x = (torch.randn(B, T, H, W, C, device=dev) * 2 + 0.5).half()
         g = torch.randn(C, device=dev); b = torch.randn(C, device=dev)
         for act in (1, 0):
