@@ -83,17 +83,20 @@ struct TcParams {
 constexpr int G2_BN_MAX = 128;
 constexpr int G2_A_BYTES = BM * BK * 2;                 // 16 KB per sub-tile
 constexpr int G2_B_BYTES = G2_BN_MAX * BK * 2;          // 16 KB
-template <int SUB> struct G2Cfg {
-  static constexpr int STAGES = SUB == 1 ? 3 : 4;
+// DEEP (SUB 1 only): a 6-stage ring and one CTA per SM for launches with at most one tile per SM -- there the k-loop is bound
+// by the bytes in flight (3 stages x 32 KB against ~1 us of L2 / HBM latency is ~100 GB/s per SM: 680 clk per 256-clk k-step).
+template <int SUB, int DEEP = 0> struct G2Cfg {
+  static constexpr int STAGES = DEEP ? 6 : (SUB == 1 ? 3 : 4);
   static constexpr int STAGE_BYTES = SUB * G2_A_BYTES + G2_B_BYTES;
   static constexpr int STG_BYTES = SUB * 16384;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + STG_BYTES + 128;   // no alignment slack: base declared 1024-aligned
+  static constexpr int SMEM = STAGES * STAGE_BYTES + STG_BYTES + 256;   // barriers (2 STAGES + 4) x 8 B + the TMEM slot; base declared 1024-aligned
   static constexpr int THREADS = 64 + SUB * 128;
   static constexpr int TMEM_COLS = SUB * 256;            // 2 accumulator buffers x SUB x 128 columns
-  static constexpr int CTAS_PER_SM = SUB == 1 ? 2 : 1;
+  static constexpr int CTAS_PER_SM = (SUB == 1 && !DEEP) ? 2 : 1;
 };
 static_assert(2 * (G2Cfg<1>::SMEM + 1024) <= 233472, "two CTAs of the SUB=1 persistent GEMM must fit one SM");
 static_assert(G2Cfg<2>::SMEM + 1024 <= 233472, "SUB=2 persistent GEMM must fit one SM");
+static_assert(G2Cfg<1, 1>::SMEM + 1024 <= 233472, "deep SUB=1 persistent GEMM must fit one SM");
 
 struct G2Params {
   TcParams b;            // shared fields (taps, bias, ...)
@@ -152,14 +155,14 @@ __device__ __forceinline__ G2Tile g2_decode(const G2Params& p, int tile, int sub
   return t;
 }
 
-template <int SUB>
-__global__ void __launch_bounds__(G2Cfg<SUB>::THREADS, G2Cfg<SUB>::CTAS_PER_SM)
+template <int SUB, int DEEP = 0>
+__global__ void __launch_bounds__(G2Cfg<SUB, DEEP>::THREADS, G2Cfg<SUB, DEEP>::CTAS_PER_SM)
 tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmD, const G2Params p) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   uint8_t* smem = smem_dyn;
   if ((smem_u32(smem) & 1023u) != 0) __trap();          // SWIZZLE_128B tiles need a 1024 B aligned base
-  using Cfg = G2Cfg<SUB>;
+  using Cfg = G2Cfg<SUB, DEEP>;
   constexpr int G2_STAGES = Cfg::STAGES, G2_STAGE_BYTES = Cfg::STAGE_BYTES;
   uint8_t* stg_all = smem + G2_STAGES * G2_STAGE_BYTES;  // 16 KB per epilogue group
   uint64_t* bars = reinterpret_cast<uint64_t*>(stg_all + Cfg::STG_BYTES);
@@ -1253,9 +1256,13 @@ bool tapgemm_tc2(const TapGemm& g, cudaStream_t st) {
   if (!attr_set) {
     MUDG_CUDA(cudaFuncSetAttribute(tapgemm_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<1>::SMEM));
     MUDG_CUDA(cudaFuncSetAttribute(tapgemm_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<2>::SMEM));
+    MUDG_CUDA(cudaFuncSetAttribute(tapgemm_tc2_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<1, 1>::SMEM));
     attr_set = true;
   }
-  if (sub == 1) {
+  const bool deep = sub == 1 && total <= sm_count() && ktot_steps >= 8 && knobs().gemm_deep != 0;
+  if (deep) {
+    tapgemm_tc2_kernel<1, 1><<<(int)total, G2Cfg<1, 1>::THREADS, G2Cfg<1, 1>::SMEM, st>>>(*ma, *mb, *md, p);
+  } else if (sub == 1) {
     const int grid = (int)std::min<int64_t>(total, 2 * sm_count());
     tapgemm_tc2_kernel<1><<<grid, G2Cfg<1>::THREADS, G2Cfg<1>::SMEM, st>>>(*ma, *mb, *md, p);
   } else {

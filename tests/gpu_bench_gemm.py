@@ -77,6 +77,19 @@ SHAPES_BALANCE = [
 ]
 
 
+# sub-wave launches of the single-CTA kernel (MDM512 level 3: 640 rows): knob gemm_deep = 6-stage ring, one CTA per SM
+SHAPES_DEEP = [
+    ("512 conv3 L3 1280->1280", 1, 16, 5, 8, 1280, 1280, 1, 1, 0),
+    ("512 conv3 L3 2560->1280", 1, 16, 5, 8, 2560, 1280, 1, 0, 0),
+    ("512 tconv L3 1280", 1, 16, 5, 8, 1280, 1280, 2, 1, 0),
+    ("512 lin L3 1280->1280 +res", 1, 1, 1, 640, 1280, 1280, 0, 1, 0),
+    ("512 lin L3 5120->1280 +res", 1, 1, 1, 640, 5120, 1280, 0, 1, 0),
+    ("512 lin L3 1280->3840 qkv", 1, 1, 1, 640, 1280, 3840, 0, 0, 0),
+    ("512 lin L3 1280->10240 geglu", 1, 1, 1, 640, 1280, 10240, 0, 0, 1),
+    ("vae-ish conv3 512->512 16x24", 1, 1, 16, 24, 512, 512, 1, 1, 0),
+]
+
+
 def main():
     dev = "cuda"
     L = test_lib()
@@ -89,6 +102,11 @@ def main():
         SHAPES, knob = SHAPES_512, b"gemm_pair"
         backends = [(0, "single"), (0, "pair"), (0, "auto")]
         vals = {"single": 0, "pair": 1, "auto": -1}
+        sys.argv = sys.argv[:1]
+    if len(sys.argv) > 1 and sys.argv[1] == "deep":
+        SHAPES, knob = SHAPES_DEEP, b"gemm_deep"
+        backends = [(0, "3stage"), (0, "deep")]
+        vals = {"3stage": 0, "deep": 1}
         sys.argv = sys.argv[:1]
     if len(sys.argv) > 1 and sys.argv[1] == "balance":
         SHAPES, knob = SHAPES_BALANCE, b"gemm_balance"
