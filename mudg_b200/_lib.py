@@ -6,7 +6,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MUDG_LIB_PATH") or os.path.join(_HERE, "libmudg_sm100.so")   # override: A/B builds of the same ABI
-TEST_LIB_PATH = os.path.join(_HERE, "libmudg_sm100_test.so")   # tests/ only: product objects + csrc/test/ (include/mudg_test.h)
+TEST_LIB_PATH = os.environ.get("MUDG_TEST_LIB_PATH") or os.path.join(_HERE, "libmudg_sm100_test.so")   # tests/ only: product objects + csrc/test/ (include/mudg_test.h)
 _lib = None
 _test_lib = None
 

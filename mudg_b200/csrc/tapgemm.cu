@@ -813,10 +813,16 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           for (int c = grp; c < (nx.bn >> 6); c += NG) asm volatile("prefetch.global.L2 [%0];" ::"l"(np_ + c * 64));
         }
       }
-      uint4 res_nxt[4];
+      // Residual rows come straight from global memory (L2 after the prefetch above); a slice's 64 B per thread must be in
+      // flight long before it is used.  kResDeep (NG 3, usually ONE chunk per group and tile): the whole 128 B chunk row
+      // is requested before the wait for the accumulator and each half is re-requested for the next chunk as soon as it has
+      // been consumed -- with a one-slice look-ahead the second slice waited 1 500+ clk on L2 (clock64 trace: 4 000-5 800
+      // clk per chunk against 1 300-1 800 for the same chunk without residual).
+      constexpr bool kResDeep = NG == 3;
+      uint4 res_nxt[kResDeep ? 8 : 4];
       if (rp != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) res_nxt[j] = __ldg(rp + first * 8 + j);
+        for (int j = 0; j < (kResDeep ? 8 : 4); j++) res_nxt[j] = __ldg(rp + first * 8 + j);
       }
       if (grp < 2 && q == 2 && lane == 0) G3_TRACE(2 + grp, lt, 0);       // epilogue group ready for the tile
       mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
@@ -837,13 +843,28 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int coff = ch * 64 + hf * 32;
         uint4 res[4];
         if (rp != nullptr) {
+          if (kResDeep) {
 #pragma unroll
-          for (int j = 0; j < 4; j++) res[j] = res_nxt[j];
-          if (sl + 1 < nslices) {
-            const int nch = first + ((sl + 1) >> 1) * NG;
-            const uint4* np4 = rp + nch * 8 + ((sl + 1) & 1) * 4;
+            for (int j = 0; j < 4; j++) res[j] = hf ? res_nxt[4 + j] : res_nxt[j];
+            if (sl + 2 < nslices) {                       // the same half of my next chunk
+              const uint4* np4 = rp + (ch + NG) * 8 + hf * 4;
+              if (hf) {
 #pragma unroll
-            for (int j = 0; j < 4; j++) res_nxt[j] = __ldg(np4 + j);
+                for (int j = 0; j < 4; j++) res_nxt[4 + j] = __ldg(np4 + j);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) res_nxt[j] = __ldg(np4 + j);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) res[j] = res_nxt[j];
+            if (sl + 1 < nslices) {
+              const int nch = first + ((sl + 1) >> 1) * NG;
+              const uint4* np4 = rp + nch * 8 + ((sl + 1) & 1) * 4;
+#pragma unroll
+              for (int j = 0; j < 4; j++) res_nxt[j] = __ldg(np4 + j);
+            }
           }
         }
         uint8_t* stg = stg_grp + (chunk_no & 1) * 16384;
