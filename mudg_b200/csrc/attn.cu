@@ -775,30 +775,39 @@ temporal_attn16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out,
 }
 
 // ---------------------------------------------------------------- temporal attention, T == 32 | 64: the same tensor-core scheme
-// One warp per (b, pixel, head) problem; Q / K / V tiles of T tokens x 128 B in a 2-deep cp.async ring.  Per 16-query block:
+// One warp (T = 32) or two (T = 64) per (b, pixel, head) problem; Q / K / V tiles of T tokens x 128 B in a 2-deep cp.async
+// ring.  Per 16-query block:
 // S = Q K^T (T / 8 n-tiles x 4 k-steps), softmax in the accumulator fragments, O = P V (8 n-tiles x T / 16 k-steps), O staged
 // over the block's own Q rows (dead by then) and stored with 128-bit coalesced writes.  Algorithmic traffic is the same
 // 4 x T x 128 B per problem as T == 16, so the kernel is HBM-bound (T = 64: 1 MFLOP and 4 096 exponentials per 32 KB).
 template <int T>
 struct TaCfg {
   static constexpr int TILE = T * 128;
-  static constexpr int WARPS = 4;
-  static constexpr int SMEM = WARPS * 2 * 3 * TILE;     // T = 64: 192 KB (one CTA per SM), T = 32: 96 KB
+  static constexpr int PROBS = 4;                       // problems in flight per CTA (each with a 2-deep tile ring)
+  static constexpr int WPP = T >= 64 ? 2 : 1;           // warps per problem: T = 64 has 4 query blocks, two per warp (one warp
+                                                        // alone ran its 1 000-instruction dependent stream at IPC 0.11: 4.0 TB/s)
+  static constexpr int WARPS = PROBS * WPP;
+  static constexpr int SMEM = PROBS * 2 * 3 * TILE;     // T = 64: 192 KB (one CTA per SM), T = 32: 96 KB
 };
 
 template <int T>
 __global__ void __launch_bounds__(TaCfg<T>::WARPS * 32)
 temporal_attn_mma_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int B, int HW, int heads, float scale_log2) {
   extern __shared__ __align__(128) uint8_t ta_smem[];
-  constexpr int TILE = TaCfg<T>::TILE, NT = T / 8, KT = T / 16;
+  constexpr int TILE = TaCfg<T>::TILE, NT = T / 8, KT = T / 16, WPP = TaCfg<T>::WPP;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slot = warp / WPP, sub = warp % WPP;          // problem slot of the CTA, my share of its query blocks
   const int inner = heads * 64;
   const int64_t pitch = 3 * (int64_t)inner;
   const int64_t npairs = (int64_t)B * HW * heads;
-  const int64_t wid = (int64_t)blockIdx.x * TaCfg<T>::WARPS + warp;
-  const int64_t wstride = (int64_t)gridDim.x * TaCfg<T>::WARPS;
-  uint8_t* wbase = ta_smem + warp * (2 * 3 * TILE);
+  const int64_t wid = (int64_t)blockIdx.x * TaCfg<T>::PROBS + slot;
+  const int64_t wstride = (int64_t)gridDim.x * TaCfg<T>::PROBS;
+  uint8_t* wbase = ta_smem + slot * (2 * 3 * TILE);
   const uint32_t wbase_u = smem_u32(wbase);
+  auto slot_sync = [&]() {                                // the WPP warps of one problem
+    if (WPP > 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(32 * WPP) : "memory");
+    else __syncwarp();
+  };
 
   auto issue_loads = [&](int64_t pr, int buf) {
     const int head = pr % heads;
@@ -808,8 +817,8 @@ temporal_attn_mma_kernel(const __half* __restrict__ qkv, __half* __restrict__ ou
     const __half* base = qkv + ((int64_t)b * T * HW + px) * pitch + head * 64;
     const uint32_t sb = wbase_u + buf * (3 * TILE);
 #pragma unroll
-    for (int i = 0; i < T / 4; i++) {                      // T rows x 8 chunks of 16 B, 32 pieces per pass
-      const int piece = lane + 32 * i;
+    for (int i = 0; i < T / 4 / WPP; i++) {               // T rows x 8 chunks of 16 B, shared between the problem's warps
+      const int piece = (sub * (T / 4 / WPP) + i) * 32 + lane;
       const int r = piece >> 3, c = piece & 7;
       const __half* src = base + (int64_t)r * HW * pitch + c * 8;
       const uint32_t dst = sb + r * 128 + ((c ^ (r & 7)) << 4);
@@ -823,18 +832,21 @@ temporal_attn_mma_kernel(const __half* __restrict__ qkv, __half* __restrict__ ou
   int buf = 0;
   if (wid < npairs) issue_loads(wid, 0);
   for (int64_t pr = wid; pr < npairs; pr += wstride, buf ^= 1) {
+    // my share of this problem's tiles has landed; after the sync so has my partner's, and both of us are past every read
+    // of the other buffer (previous iteration), which the prefetch below overwrites
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    slot_sync();
     const int64_t nxt = pr + wstride;
-    if (nxt < npairs) {
-      issue_loads(nxt, buf ^ 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncwarp();
+    if (nxt < npairs) issue_loads(nxt, buf ^ 1);
     const uint32_t sq = wbase_u + buf * (3 * TILE), sk = sq + TILE, sv = sq + 2 * TILE;
     uint8_t* so = wbase + buf * (3 * TILE);
+    const int head = pr % heads;
+    const int64_t bp = pr / heads;
+    const int px = bp % HW;
+    const int b = bp / HW;
+    __half* ob = out + ((int64_t)b * T * HW + px) * inner + head * 64;
 #pragma unroll 1
-    for (int mt = 0; mt < KT; mt++) {
+    for (int mt = sub; mt < KT; mt += WPP) {
       // ---- S = Q[mt] K^T : 16 queries x T keys
       float s[NT][4];
 #pragma unroll
@@ -894,7 +906,8 @@ temporal_attn_mma_kernel(const __half* __restrict__ qkv, __half* __restrict__ ou
         }
       }
       const float iA = 1.f / lA, iB = 1.f / lB;
-      // ---- stage O (fp16) over this block's Q rows: every lane's ldmatrix reads of them are done (warp-synchronous mma)
+      // ---- stage O (fp16) over this block's own Q rows (only this warp reads them, and it is done), then store the block's
+      // 16 rows with 128-bit coalesced writes
       __syncwarp();
       {
         const int g = mt * 16 + (lane >> 2), t = lane & 3;
@@ -904,23 +917,15 @@ temporal_attn_mma_kernel(const __half* __restrict__ qkv, __half* __restrict__ ou
           *reinterpret_cast<uint32_t*>(so + (g + 8) * 128 + ((j ^ ((g + 8) & 7)) << 4) + t * 4) = pack_half2(o[j][2] * iB, o[j][3] * iB);
         }
       }
-    }
-    __syncwarp();
-    {
-      const int head = pr % heads;
-      const int64_t bp = pr / heads;
-      const int px = bp % HW;
-      const int b = bp / HW;
-      __half* ob = out + ((int64_t)b * T * HW + px) * inner + head * 64;
+      __syncwarp();
 #pragma unroll
-      for (int i = 0; i < T / 4; i++) {
+      for (int i = 0; i < 4; i++) {
         const int piece = lane + 32 * i;
-        const int r = piece >> 3, c = piece & 7;
+        const int r = mt * 16 + (piece >> 3), c = piece & 7;
         const uint4 val = *reinterpret_cast<const uint4*>(so + r * 128 + ((c ^ (r & 7)) << 4));
         *reinterpret_cast<uint4*>(ob + (int64_t)r * HW * inner + c * 8) = val;
       }
     }
-    __syncwarp();     // the tiles are reused by the prefetch issued two iterations from now
   }
 }
 
@@ -928,7 +933,7 @@ template <int T>
 static void launch_temporal_mma(const __half* qkv, __half* out, int B, int HW, int heads, float scale, cudaStream_t st) {
   MUDG_CUDA(cudaFuncSetAttribute(temporal_attn_mma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, TaCfg<T>::SMEM));
   const int64_t np = (int64_t)B * HW * heads;
-  const int64_t want = (np + TaCfg<T>::WARPS - 1) / TaCfg<T>::WARPS;
+  const int64_t want = (np + TaCfg<T>::PROBS - 1) / TaCfg<T>::PROBS;
   const int per_sm = TaCfg<T>::SMEM > 100 * 1024 ? 1 : 2;
   const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count() * per_sm);
   temporal_attn_mma_kernel<T><<<grid, TaCfg<T>::WARPS * 32, TaCfg<T>::SMEM, st>>>(qkv, out, B, HW, heads, scale * 1.4426950408889634f);
