@@ -226,13 +226,17 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll 1
     for (int it = 0; it < nb1; it++) {
       const int valid = p.len[0] - it * 128 - half * 64;      // my columns >= valid are padding (TMA zero fill)
+      const bool tracer = q == 2 && half == 0 && lane == 0;
+      if (tracer) F2_TRACE(grp, it, 0);                      // ready for S(it)
       mbar_wait(&s_full[grp], it & 1);
       __syncwarp();
       tc_fence_after();
+      if (tracer) F2_TRACE(grp, it, 1);                      // S(it) available
       uint32_t sr[2][32];
       tmem_ld32(tS, sr[0]);
       tmem_ld32(tS + 32, sr[1]);
       tmem_ld_wait();
+      if (tracer) F2_TRACE(grp, it, 2);                      // S(it) in registers
       tc_fence_before();
       mbar_arrive(&s_free[grp]);
       float mx = -INFINITY;
@@ -260,6 +264,7 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         else if (it > 0) mbar_wait(&exp_done[1], (uint32_t)(it - 1) & 1u);
         __syncwarp();
       }
+      if (tracer) F2_TRACE(grp, it, 5);                      // row max agreed, MUFU turn acquired
       mx *= p.scale_log2;
       const bool grow = (it > 0) && (mx > m_used + F2_LAZY);
       const float m_old = m_used;
@@ -292,6 +297,7 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           }
       }
       if (do_stagger && (p.stagger == 1 || p.stagger > 4 || valid < 64)) mbar_arrive(&exp_done[grp]);
+      if (tracer) F2_TRACE(grp, it, 3);                      // exponentials done
       if (it > 0) {                                  // the previous P V of this tile has retired: P and O may be touched
         mbar_wait(&o_done[grp], (it - 1) & 1);
         __syncwarp();
@@ -317,6 +323,7 @@ flash2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_ready[grp]);
+      if (tracer) F2_TRACE(grp, it, 4);                      // P(it) stored
     }
     // ---- O / l: the halves add their partial row sums, each reads out its 32 of the 64 O columns
     mbar_wait(&o_done[grp], (nb1 - 1) & 1);
