@@ -1032,15 +1032,14 @@ void flash_attention(const FlashArgs& a, cudaStream_t st) {
     p.len[i] = s.len;
     p.kv_div[i] = s.kv_div > 0 ? s.kv_div : 1;
   }
-  static bool attr = false;
-  if (!attr) {
+  static OncePerDevice attr;
+  if (attr.first()) {
     MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
     MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
     MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<1, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
     MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<1, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
     MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<1, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
     MUDG_CUDA(cudaFuncSetAttribute(flash2_kernel<2, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
-    attr = true;
   }
   // Polynomial exp2 offload (FA4 trick).  Measured on B200 (tests/gpu_bench_flash.py): 5.49 ms vs 4.99 ms without it at
   // 9216 tokens -- the exponent phase is latency-bound at this occupancy, so it stays off (knob flash_poly).
@@ -1066,11 +1065,8 @@ void temporal_attention(const __half* qkv, __half* out, int B, int T, int HW, in
   MUDG_REQUIRE(T >= 1 && T <= 64, "temporal attention supports T <= 64 (T=%d)", T);
   const bool generic_only = knobs().tattn_generic != 0;
   if (T == 16 && !generic_only) {
-    static bool attr16 = false;
-    if (!attr16) {
-      MUDG_CUDA(cudaFuncSetAttribute(temporal_attn16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
-      attr16 = true;
-    }
+    static OncePerDevice attr16;
+    if (attr16.first()) MUDG_CUDA(cudaFuncSetAttribute(temporal_attn16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
     const int64_t np = (int64_t)B * HW * heads;
     const int64_t want = (np + TA_WARPS - 1) / TA_WARPS;
     const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count() * 4);
@@ -1090,11 +1086,8 @@ void temporal_attention(const __half* qkv, __half* out, int B, int T, int HW, in
   const size_t smem = (size_t)warps * ppw * T * 16 * sizeof(uint4);
   const int64_t npairs = (int64_t)B * HW * heads;
   const int64_t blocks = (npairs + (int64_t)warps * ppw - 1) / ((int64_t)warps * ppw);
-  static size_t attr_smem = 0;
-  if (smem > 48 * 1024 && smem > attr_smem) {
+  if (smem > 48 * 1024)      // per device and growing with T: set every time (host-side only, microseconds)
     MUDG_CUDA(cudaFuncSetAttribute(temporal_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
-  }
   temporal_attn_kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(qkv, out, B, T, HW, heads,
                                                                   scale * 1.4426950408889634f, group, ppw);
   MUDG_CUDA(cudaGetLastError());

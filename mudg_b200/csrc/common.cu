@@ -85,14 +85,15 @@ std::string prof_report() {
 }
 
 int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& v = n[dev & 63];
+  if (!v) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
   }
-  return n;
+  return v;
 }
 
 // ---------------------------------------------------------------- Arena

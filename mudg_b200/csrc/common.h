@@ -78,6 +78,19 @@ struct Stream {
 };
 
 int sm_count();
+// first() is true once per CUDA device: function attributes (dynamic shared memory limits) are per device, a process may hold
+// contexts on several
+struct OncePerDevice {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 63;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
 
 // Tuning / diagnostic knobs.  The product library never reads the environment for these: they hold the shipped defaults
 // and can only be changed through libmudg_sm100_test.so (csrc/test/testhooks.cu, tests/ only), which links its own

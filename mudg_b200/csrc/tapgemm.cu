@@ -1191,11 +1191,9 @@ bool tapgemm_tc3(const TapGemm& g, cudaStream_t st) {
   const dim3 grid(2 * clusters);
 #define MUDG_TC3_LAUNCH(E, G)                                                                                         \
   do {                                                                                                                 \
-    static bool attr_done = false;                                                                                     \
-    if (!attr_done) {                                                                                                  \
+    static OncePerDevice attr_done;                                                                                    \
+    if (attr_done.first())                                                                                             \
       MUDG_CUDA(cudaFuncSetAttribute(tapgemm_tc3_kernel<E, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, G3Cfg<G>::SMEM)); \
-      attr_done = true;                                                                                                \
-    }                                                                                                                  \
     tapgemm_tc3_kernel<E, G><<<grid, G3Cfg<G>::THREADS, G3Cfg<G>::SMEM, st>>>(*ma, *mb0, *mb1, *md, p);                 \
   } while (0)
 #define MUDG_TC3_EPI(E)                 \
@@ -1273,12 +1271,11 @@ bool tapgemm_tc2(const TapGemm& g, cudaStream_t st) {
   const CUtensorMap* ma = get_tmap(g.A, adims, astr, abox);
   const CUtensorMap* mb = get_tmap(g.Wt, bdims, bstr, bbox);
   const CUtensorMap* md = get_tmap(g.D, ddims, dstr, abox);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static OncePerDevice attr_set;
+  if (attr_set.first()) {
     MUDG_CUDA(cudaFuncSetAttribute(tapgemm_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<1>::SMEM));
     MUDG_CUDA(cudaFuncSetAttribute(tapgemm_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<2>::SMEM));
     MUDG_CUDA(cudaFuncSetAttribute(tapgemm_tc2_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<1, 1>::SMEM));
-    attr_set = true;
   }
   const bool deep = sub == 1 && total <= sm_count() && ktot_steps >= 8 && knobs().gemm_deep != 0;
   if (deep) {

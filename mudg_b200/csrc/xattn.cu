@@ -385,11 +385,8 @@ void xattn_per_frame(const XattnArgs& a, cudaStream_t st) {
   MUDG_REQUIRE(units < (int64_t(1) << 30), "xattn: too many units");
   p.units = (int)units;
   p.scale_log2 = a.scale * 1.4426950408889634f;
-  static bool attr = false;
-  if (!attr) {
-    MUDG_CUDA(cudaFuncSetAttribute(xattn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XA_SMEM));
-    attr = true;
-  }
+  static OncePerDevice attr;
+  if (attr.first()) MUDG_CUDA(cudaFuncSetAttribute(xattn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XA_SMEM));
   const int grid = (int)std::min<int64_t>(units, sm_count());
   xattn_kernel<<<grid, XA_THREADS, XA_SMEM, st>>>(*mq, *mo, *mk, *mv, p);
   MUDG_CUDA(cudaGetLastError());

@@ -638,3 +638,36 @@ def test_full_size_parity_sampler():
     g16 = r.get("reference_fp16_latent_vs_truth")
     if g16:
         assert r["ours_latent_vs_truth"]["mean_abs"] < 1.25 * g16["mean_abs"], (r["ours_latent_vs_truth"], g16)
+
+
+def test_engine_on_second_device_matches_first(golden_dir):
+    """A context created on cuda:1 while cuda:0 is the current device (every C entry point switches to the context's
+    device; kernel attributes are set per device): same forward, VAE decode and Resampler results as on cuda:0, bitwise."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
+    from mudg_b200.engine import Engine, MUDG_UNET, MUDG_VAE
+    from oracle import mudg_oracle as O
+    g = np.load(os.path.join(golden_dir, "unet_small.npz"))
+    v = np.load(os.path.join(golden_dir, "vae_small.npz"))
+    sd = O.seeded_state_dict(O.unet_param_shapes(O.UNetCfg(model_channels=64, temporal_length=4)), seed=1)
+    vsd = O.seeded_state_dict(O.vae_param_shapes(O.VaeCfg(ch=64)), seed=2)
+    outs = []
+    torch.cuda.set_device(0)
+    for dev in (0, 1):
+        eng = Engine(SMALL_UNET, SMALL_VAE, device=dev)
+        assert torch.cuda.current_device() == 0
+        eng.load_state_dict(sd, MUDG_UNET)
+        eng.load_state_dict(vsd, MUDG_VAE)
+        t = lambda k: torch.from_numpy(g[k]).to(f"cuda:{dev}")
+        with torch.cuda.device(dev):                      # torch allocations and the stream handed to the library
+            eng.set_context(t("ctx"), T=4)
+            y = eng.unet_forward(t("x"), t("ts"), t("lab"), t("fs"))
+            y2 = eng.unet_forward(t("x"), t("ts"), t("lab"), t("fs"))      # captured graph
+            dec = eng.vae_decode(torch.from_numpy(v["z"]).to(f"cuda:{dev}"))
+            torch.cuda.synchronize(dev)
+        assert torch.cuda.current_device() == 0
+        assert torch.equal(y, y2)
+        outs.append((y.cpu(), dec.cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    err = (outs[1][0].float() - torch.from_numpy(g["y"])).abs()
+    assert float(err.max()) < 0.014
