@@ -100,6 +100,7 @@ struct Knobs {
   int gemm_sub = 0;         // 0 heuristic, 1 | 2: force the M sub-tile count of the single-CTA kernel (tapgemm_tc2)
   int gemm_epi = 1;         // compile-time epilogue variants of tapgemm_tc3 (0 = run-time variant only)
   int gemm_groups = 0;      // epilogue groups of tapgemm_tc3: 0 per-shape rule, 2 | 3 forced
+  int gemm_resmma = 1;      // tapgemm_tc3: residual added by the tensor core (identity k-steps); 0 = by the epilogue threads
   int gemm_deep = 1;        // tapgemm_tc2: 6-stage, one-CTA-per-SM variant for launches of at most one tile per SM
   int gemm_balance = 1;     // tapgemm_tc3: narrower N tiles when they balance the waves over the CTA pairs
   int gemm_dbg = 0;         // bit 0: skip the output TMA stores, bit 1: release (not relaxed) accumulator hand-back

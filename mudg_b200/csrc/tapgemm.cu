@@ -494,6 +494,7 @@ struct G3Params {
   int tiles_b;
   int dimW, dimH, dimB;
   const __half* R;
+  int res_mma;                  // the residual is added by the tensor core (tmR x identity, see the producer): R is null then
   int alpha_is_one;
   double* gn_sums;              // GroupNorm statistics of the output ([S][32][2] fp64, pre-zeroed), or null
   FastDiv fd_cpg, fd_gn;        // channels per group; frames per GroupNorm sample (sample = (b*T + t) / d)
@@ -568,7 +569,7 @@ template <int EPI, int NG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G3Cfg<NG>::THREADS, 1)
 tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
                    const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmD,
-                   const G3Params p) {
+                   const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmJ, const G3Params p) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   uint8_t* smem = smem_dyn;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -634,6 +635,24 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (++s == NST) { s = 0; ph ^= 1u; }
         }
       }
+      if (p.res_mma) {
+        // Residual through the tensor core: per 64-column chunk one more k-step whose A operand is the residual tile
+        // R[rows, n0 + 64 c .. + 64) and whose B operand is a 64 x 64 identity, accumulated into accumulator columns
+        // [64 c, 64 c + 64).  The residual then rides the TMA ring (requested stages ahead) instead of being fetched by the
+        // epilogue threads, whose loads took 2 000-3 000 clk under load (clock64 trace, profiles/r2_experiments.md).
+        const uint32_t rtx = 2u * (uint32_t)(G3_A_BYTES + 32 * (BK * 2));
+        for (int c = 0; c < (tl.bn >> 6); c++) {
+          mbar_wait(&empty[s], ph);
+          if (elect_one()) {
+            if (rank == 0) mbar_expect_tx(&full[s], rtx);
+            uint8_t* a_s = smem + s * G3_STAGE_BYTES;
+            tma_load_5d_pair(a_s, &tmR, full0 + 8u * s, tl.n0 + c * 64, tl.w0, tl.h0, tl.t0, tl.b0);
+            tma_load_5d_pair(a_s + G3_A_BYTES, &tmJ, full0 + 8u * s, 0, (int)rank * 32, 0, 0, 0);
+          }
+          __syncwarp();
+          if (++s == NST) { s = 0; ph ^= 1u; }
+        }
+      }
       if (lane == 0) G3_TRACE(0, plt, 1);                 // all loads of the tile issued
     }
   } else if (warp == 1) {
@@ -649,18 +668,26 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         tc_fence_after();
         if (lane == 0) G3_TRACE(1, lt, 1);                     // accumulator free
         const uint32_t idesc = umma_idesc_f16(256, tl.bn, 0, 0);
+        const uint32_t idesc_res = umma_idesc_f16(256, 64, 0, 0);     // residual k-steps: 64 accumulator columns at a time
         const uint32_t d_tmem = tmem_base + acc * 256;
-        for (int k = 0; k < ktotal; k++) {
+        const int ksteps = ktotal + (p.res_mma ? (tl.bn >> 6) : 0);
+        for (int k = 0; k < ksteps; k++) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
           if (k == 0 && lane == 0) G3_TRACE(1, lt, 2);         // first operands landed
           if (elect_one()) {
             const uint64_t so = (uint64_t)(s * (G3_STAGE_BYTES >> 4));     // descriptor start address: 16 B units
+            if (k < ktotal) {
 #pragma unroll
-            for (int kk = 0; kk < BK / 16; kk++)
-              umma_f16_pair(d_tmem, da0 + so + 2 * kk, db0 + so + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+              for (int kk = 0; kk < BK / 16; kk++)
+                umma_f16_pair(d_tmem, da0 + so + 2 * kk, db0 + so + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+            } else {
+              const uint32_t d_res = d_tmem + 64u * (uint32_t)(k - ktotal);
+#pragma unroll
+              for (int kk = 0; kk < BK / 16; kk++) umma_f16_pair(d_res, da0 + so + 2 * kk, db0 + so + 2 * kk, idesc_res, 1u);
+            }
             umma_commit_pair(&empty[s], 3);
-            if (k == ktotal - 1) umma_commit_pair(&tmem_full[acc], 3);
+            if (k == ksteps - 1) umma_commit_pair(&tmem_full[acc], 3);
           }
           __syncwarp();
           if (++s == NST) { s = 0; ph ^= 1u; }
@@ -1090,6 +1117,21 @@ bool tapgemm_per_sample_ok(const TapGemm& g) {
   return tapgemm_pair_wanted(g, m_tiles, (g.N + G2_BN_MAX - 1) / G2_BN_MAX) && bb == 1 && div % bt == 0;
 }
 
+// 64 x 64 fp16 identity, one per device: the B operand of the residual k-steps
+static const __half* identity64() {
+  static __half* dev_ptr[64] = {};
+  int d = 0;
+  MUDG_CUDA(cudaGetDevice(&d));
+  __half*& ptr = dev_ptr[d & 63];
+  if (ptr == nullptr) {
+    std::vector<__half> h(64 * 64, __float2half(0.f));
+    for (int i = 0; i < 64; i++) h[i * 64 + i] = __float2half(1.f);
+    MUDG_CUDA(cudaMalloc(&ptr, h.size() * sizeof(__half)));
+    MUDG_CUDA(cudaMemcpy(ptr, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  }
+  return ptr;
+}
+
 bool tapgemm_tc3(const TapGemm& g, cudaStream_t st) {
   G3Params p{};
   p.b = make_params(g);
@@ -1174,6 +1216,24 @@ bool tapgemm_tc3(const TapGemm& g, cudaStream_t st) {
   const CUtensorMap* mb0 = get_tmap(g.Wt, bdims, bstr, bbox0);
   const CUtensorMap* mb1 = get_tmap(g.Wt, bdims, bstr, bbox1);
   const CUtensorMap* md = get_tmap(g.D, ddims, dstr, abox);
+  const int ktot_steps = g.ntaps * p.b.kchunks;
+  // Residual through the tensor core (see the producer).  One 64-column MMA step per chunk costs about one extra full-width
+  // k-step per tile; measured (tests/gpu_bench_gemm.py resmma) it wins on every shape: 320->320+res 178 -> 160 us, the
+  // MDM512-sized ones -14..16 %, and even the 9-tap convs and K = 5120 layers by 1-4 % (their epilogue loses its only
+  // global loads).  Knob gemm_resmma = 0 keeps the residual in the epilogue.
+  const bool res_ok = g.R != nullptr && !g.geglu && g.alpha == 1.f;
+  const bool res_mma = res_ok && knobs().gemm_resmma != 0;
+  p.res_mma = res_mma ? 1 : 0;
+  const CUtensorMap* mr = md;
+  const CUtensorMap* mj = md;
+  if (res_mma) {
+    p.R = nullptr;                                   // the epilogue does not see a residual
+    mr = get_tmap(g.R, ddims, dstr, abox);
+    const uint64_t jdims[5] = {64, 64, 1, 1, 1};
+    const uint64_t jstr[4] = {128, 128 * 64, 128 * 64, 128 * 64};
+    const uint32_t jbox[5] = {BK, 32, 1, 1, 1};
+    mj = get_tmap(identity64(), jdims, jstr, jbox);
+  }
   const int clusters = (int)std::min<int64_t>(total, sm_count() / 2);
   p.rot_div = FastDiv{0u, 0u, 0};
   if (p.nt > 1 && clusters % p.nt == 0) p.rot_div = make_fastdiv(clusters);
@@ -1181,11 +1241,10 @@ bool tapgemm_tc3(const TapGemm& g, cudaStream_t st) {
   const bool epi_on = knobs().gemm_epi != 0;
   int epi = -1;
   if (epi_on && !g.geglu && g.alpha == 1.f)
-    epi = (g.bias ? 1 : 0) | (g.bias2 ? 2 : 0) | (g.R ? 4 : 0) | (g.ln_stats ? 8 : 0);
+    epi = (g.bias ? 1 : 0) | (g.bias2 ? 2 : 0) | ((g.R && !res_mma) ? 4 : 0) | (g.ln_stats ? 8 : 0);
   if (epi != 0 && epi != 1 && epi != 3 && epi != 5 && epi != 9) epi = -1;
   // three epilogue groups (see G3Cfg) for the short-K Linear layers: K = 320 always, K = 640 when the epilogue carries a
   // residual or GEGLU (measured per shape inside the clip); knob gemm_groups = 2 | 3 forces
-  const int ktot_steps = g.ntaps * p.b.kchunks;
   int ng = (g.ntaps == 1 && (ktot_steps <= 5 || (ktot_steps <= 10 && (g.geglu || g.R != nullptr)))) ? 3 : 2;
   if (knobs().gemm_groups == 2 || knobs().gemm_groups == 3) ng = knobs().gemm_groups;
   const dim3 grid(2 * clusters);
@@ -1194,7 +1253,7 @@ bool tapgemm_tc3(const TapGemm& g, cudaStream_t st) {
     static OncePerDevice attr_done;                                                                                    \
     if (attr_done.first())                                                                                             \
       MUDG_CUDA(cudaFuncSetAttribute(tapgemm_tc3_kernel<E, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, G3Cfg<G>::SMEM)); \
-    tapgemm_tc3_kernel<E, G><<<grid, G3Cfg<G>::THREADS, G3Cfg<G>::SMEM, st>>>(*ma, *mb0, *mb1, *md, p);                 \
+    tapgemm_tc3_kernel<E, G><<<grid, G3Cfg<G>::THREADS, G3Cfg<G>::SMEM, st>>>(*ma, *mb0, *mb1, *md, *mr, *mj, p);       \
   } while (0)
 #define MUDG_TC3_EPI(E)                 \
   do {                                  \
@@ -1211,7 +1270,7 @@ bool tapgemm_tc3(const TapGemm& g, cudaStream_t st) {
   }
 #undef MUDG_TC3_EPI
 #undef MUDG_TC3_LAUNCH
-  knobs().last_gemm_path = 4 | ((epi + 1) << 8) | (gn_fuse ? 1 << 16 : 0) | (ng << 20);
+  knobs().last_gemm_path = 4 | ((epi + 1) << 8) | (gn_fuse ? 1 << 16 : 0) | (res_mma ? 1 << 17 : 0) | (ng << 20);
   MUDG_CUDA(cudaGetLastError());
   return gn_fuse;
 }

@@ -298,6 +298,7 @@ MUDG_EXPORT int mudg_test_set_knob(const char* name, int value) {
   else if (n == "gemm_groups") k.gemm_groups = value;
   else if (n == "gemm_balance") k.gemm_balance = value;
   else if (n == "gemm_deep") k.gemm_deep = value;
+  else if (n == "gemm_resmma") k.gemm_resmma = value;
   else if (n == "flash_stagger") k.flash_stagger = value;
   else if (n == "flash_poly") k.flash_poly = value;
   else if (n == "flash_split") k.flash_split = value;

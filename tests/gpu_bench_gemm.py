@@ -108,6 +108,13 @@ def main():
         backends = [(0, "3stage"), (0, "deep")]
         vals = {"3stage": 0, "deep": 1}
         sys.argv = sys.argv[:1]
+    if len(sys.argv) > 1 and sys.argv[1] == "resmma":
+        SHAPES = [x for x in SHAPES if x[8]] + [("lin L1 640->640 +res", 1, 1, 1, 73728, 640, 640, 0, 1, 0), ("lin L2 1280->1280 +res", 1, 1, 1, 18432, 1280, 1280, 0, 1, 0),
+                                                 ("512 lin L0 320->320 +res", 1, 1, 1, 40960, 320, 320, 0, 1, 0), ("512 lin L1 640->640 +res", 1, 1, 1, 10240, 640, 640, 0, 1, 0)]
+        knob = b"gemm_resmma"
+        backends = [(0, "epilogue"), (0, "mma"), (0, "rule")]
+        vals = {"epilogue": 0, "mma": 1, "rule": -1}
+        sys.argv = sys.argv[:1]
     if len(sys.argv) > 1 and sys.argv[1] == "balance":
         SHAPES, knob = SHAPES_BALANCE, b"gemm_balance"
         backends = [(0, "wide"), (0, "balanced")]

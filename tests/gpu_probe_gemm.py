@@ -34,25 +34,25 @@ CASES = {
     # EPI 3: bias + per-sample bias (ResBlock in_layers conv + emb), 9 taps
     "pair_conv_l0_emb": (2, 16, 72, 128, 320, 320, 1, 0, 1, 1, 0, 0, 1.0, 4 | (4 << 8)),
     # EPI 5: bias + residual (ResBlock out_layers conv + skip), 9 taps
-    "pair_conv_l0_res": (2, 16, 72, 128, 320, 320, 1, 1, 1, 0, 0, 0, 1.0, 4 | (6 << 8)),
+    "pair_conv_l0_res": (2, 16, 72, 128, 320, 320, 1, 1, 1, 0, 0, 0, 1.0, 4 | (2 << 8)),
     # concat input (output blocks): 640 -> 320, bias + per-sample bias
     "pair_conv_l0_cat": (2, 16, 72, 128, 640, 320, 1, 0, 1, 1, 0, 0, 1.0, 4 | (4 << 8)),
     # temporal conv (3,1,1) with the TemporalConvBlock identity, 3 taps shifted along T across sample borders
-    "pair_tconv_l0_res": (2, 16, 72, 128, 320, 320, 2, 1, 1, 0, 0, 0, 1.0, 4 | (6 << 8)),
+    "pair_tconv_l0_res": (2, 16, 72, 128, 320, 320, 2, 1, 1, 0, 0, 0, 1.0, 4 | (2 << 8)),
     "pair_tconv_l0": (2, 16, 72, 128, 320, 320, 2, 0, 1, 0, 0, 0, 1.0, 4 | (2 << 8)),
     # Linear 320 -> 320 + residual over all M = 294 912 rows (attention to_out / proj_out)
-    "pair_lin_k320_res": (1, 1, 1, 294912, 320, 320, 0, 1, 1, 0, 0, 0, 1.0, 4 | (6 << 8)),
+    "pair_lin_k320_res": (1, 1, 1, 294912, 320, 320, 0, 1, 1, 0, 0, 0, 1.0, 4 | (2 << 8)),     # residual through the MMA: bias-only epilogue
     # folded LayerNorm (EPI 9 takes bias = c2): QKV 320 -> 960 and to_q 320 -> 320
     "pair_lin_ln_qkv": (1, 1, 1, 294912, 320, 960, 0, 0, 1, 0, 0, 1, 1.0, 4 | (10 << 8)),
     "pair_lin_ln_q": (1, 1, 1, 147456, 320, 320, 0, 0, 1, 0, 0, 1, 1.0, 4 | (10 << 8)),
     # GEGLU with the folded LayerNorm (run-time epilogue variant), 320 -> 2560 -> 1280 columns
     "pair_geglu_ln": (1, 1, 1, 147456, 320, 2560, 0, 0, 1, 0, 1, 1, 1.0, 4),
     # N not a multiple of 256 / odd tile splits: 640 -> 192+192+256 units, 1280, 1920-wide K, N = 448
-    "pair_lin_n640": (1, 1, 1, 73728, 640, 640, 0, 1, 1, 0, 0, 0, 1.0, 4 | (6 << 8)),
+    "pair_lin_n640": (1, 1, 1, 73728, 640, 640, 0, 1, 1, 0, 0, 0, 1.0, 4 | (2 << 8)),
     "pair_lin_n448": (1, 1, 1, 73728, 320, 448, 0, 0, 1, 0, 0, 0, 1.0, 4 | (2 << 8)),
     "pair_conv_l1_cat": (2, 16, 36, 64, 1920, 640, 1, 0, 1, 1, 0, 0, 1.0, 4 | (4 << 8)),
     # rows not a multiple of the 256-row pair tile (odd M-tile count): the second CTA of the last pair runs past the end
-    "pair_lin_ragged": (1, 1, 1, 200000 + 77, 320, 320, 0, 1, 1, 0, 0, 0, 1.0, 4 | (6 << 8)),
+    "pair_lin_ragged": (1, 1, 1, 200000 + 77, 320, 320, 0, 1, 1, 0, 0, 0, 1.0, 4 | (2 << 8)),
     # plain alpha != 1 goes through the run-time variant of the pair kernel
     "pair_lin_alpha": (1, 1, 1, 147456, 512, 512, 0, 0, 0, 0, 0, 0, 0.125, 4),
     # single-CTA kernel with the folded LayerNorm (small M: the small-config UNet's path)
@@ -63,9 +63,18 @@ CASES = {
 CASES["pair_lin_persample_frame"] = (2, 16, 72, 128, 320, 320, 0, 0, 1, 1, 0, 0, 1.0, 4 | (4 << 8))
 CASES["pair_lin_persample_batch"] = (2, 16, 36, 64, 640, 640, 0, 0, 1, 1, 0, 0, 1.0, 4 | (4 << 8))
 # wave-balanced N tiles (1 280 columns as 6 x 192 + 128 instead of 5 x 256): MDM1024 level 3 and MDM512 level 2
-CASES["pair_conv_l3_balanced"] = (2, 16, 9, 16, 1280, 1280, 1, 1, 1, 0, 0, 0, 1.0, 4 | (6 << 8))
-CASES["pair_lin_l2_balanced"] = (1, 1, 1, 2560, 1280, 1280, 0, 1, 1, 0, 0, 0, 1.0, 4 | (6 << 8))
+CASES["pair_conv_l3_balanced"] = (2, 16, 9, 16, 1280, 1280, 1, 1, 1, 0, 0, 0, 1.0, 4 | (2 << 8))
+CASES["pair_lin_l2_balanced"] = (1, 1, 1, 2560, 1280, 1280, 0, 1, 1, 0, 0, 0, 1.0, 4 | (2 << 8))
 CASES["pair_tconv_l3_balanced"] = (2, 16, 9, 16, 1280, 1280, 2, 0, 1, 0, 0, 0, 1.0, 4 | (2 << 8))
+# the residual added by the tensor core (identity k-steps) with the epilogue-side residual forced off / on: same results
+CASES["pair_lin_k320_res_epi"] = (1, 1, 1, 294912, 320, 320, 0, 1, 1, 0, 0, 0, 1.0, 4 | (6 << 8))
+CASES["pair_conv_l0_res_epi"] = (2, 16, 72, 128, 320, 320, 1, 1, 1, 0, 0, 0, 1.0, 4 | (6 << 8))
+CASES["pair_lin_k1280_res_mma"] = (1, 1, 1, 147456, 1280, 320, 0, 1, 1, 0, 0, 0, 1.0, 4 | (2 << 8))
+CASES["pair_conv_l1_res_mma"] = (2, 16, 36, 64, 640, 640, 1, 1, 1, 0, 0, 0, 1.0, 4 | (2 << 8))
+RESMMA_KNOB = {"pair_lin_k320_res_epi": 0, "pair_conv_l0_res_epi": 0}
+RESMMA_EXPECT = {"pair_lin_k320_res": 1, "pair_lin_n640": 1, "pair_lin_ragged": 1, "pair_lin_k320_res_epi": 0, "pair_conv_l0_res_epi": 0,
+                 "pair_lin_k1280_res_mma": 1, "pair_conv_l1_res_mma": 1, "pair_conv_l0_res": 1, "pair_tconv_l0_res": 1,
+                 "pair_lin_l2_balanced": 1, "pair_conv_l3_balanced": 1}
 PER_SAMPLE = {"pair_lin_persample_frame": 1, "pair_lin_persample_batch": 16}
 PAIR_CASES = [k for k in CASES if k.startswith("pair_")]
 # cases that also request the fused GroupNorm statistics of their output: name -> frames per GroupNorm sample
@@ -163,6 +172,8 @@ def run_case(name, backends=((1, "simt"), (0, "tc"))):
             gn_sums = torch.zeros(n_samples, 32, 2, device=dev, dtype=torch.float64)
             check(L.mudg_test_set_knob(b"gn_fuse", 2))      # also the 3-tap convs (the product only fuses 9-tap ones: slack)
             check(L.mudg_test_next_gemm_gn(ptr(gn_sums), gn_div))
+        if name in RESMMA_KNOB and backend == 0:
+            check(L.mudg_test_set_knob(b"gemm_resmma", RESMMA_KNOB[name]))
         if os.environ.get("PROBE_BALANCE") and backend == 0:
             check(L.mudg_test_set_knob(b"gemm_balance", int(os.environ["PROBE_BALANCE"])))
         torch.cuda.synchronize()
@@ -181,6 +192,8 @@ def run_case(name, backends=((1, "simt"), (0, "tc"))):
         out[label] = (emax, nan)
         if backend == 0:
             out["_path"] = (path & 0xffff, want_path)
+            if name in RESMMA_EXPECT:
+                out["_resmma"] = ((path >> 17) & 1, RESMMA_EXPECT[name])
             if gn_sums is not None:
                 # fused GroupNorm statistics against fp64 sums of the fp16 output the kernel stored
                 d64 = D.double().reshape(n_samples, -1, 32, n_out // 32)

@@ -48,6 +48,9 @@ def test_tapgemm(case):
     out = P.run_case(case)
     path, want = out.pop("_path")
     gn = out.pop("_gn", None)
+    rm = out.pop("_resmma", None)
+    if rm is not None:          # residual added by the tensor core (identity k-steps) or by the epilogue, as the dispatch rule says
+        assert rm[0] == rm[1], (case, "residual through the MMA", rm)
     if gn is not None:          # GroupNorm statistics of the output, accumulated by the pair kernel's epilogue
         taken, rel = gn
         assert taken == ((path & 255) == 4), (case, taken, path)      # the pair kernel fuses them (knob gn_fuse = 2: any tap count)
