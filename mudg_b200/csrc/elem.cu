@@ -26,6 +26,16 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return v;
 }
 __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+// The same with the reciprocal on the FMA pipe (magic-number seed + 3 Newton steps, ~1e-7 relative): ONE MUFU op per element
+// instead of two.  gn_apply is co-limited by the MUFU unit (ncu: XU 66 %) -- see knob gn_silu.
+__device__ __forceinline__ float silu_fma(float x) {
+  const float d = 1.f + __expf(-fmaxf(x, -80.f));             // <= 5.6e34: the seed below needs d < 2^126
+  float r = __int_as_float(0x7EF311C7 - __float_as_int(d));
+  r = r * fmaf(-d, r, 2.f);
+  r = r * fmaf(-d, r, 2.f);
+  r = r * fmaf(-d, r, 2.f);
+  return x * r;
+}
 
 // ---------------------------------------------------------------- GroupNorm statistics
 // x: [S samples][R rows][C]; sums: [S][32][2] doubles (sum, sum of squares), pre-zeroed.
@@ -131,9 +141,12 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict
     unpack8(raw, f);
 #pragma unroll
     for (int i = 0; i < 8; i++) f[i] = fmaf(f[i], sc[i], sh[i]);
-    if (act) {
+    if (act == 1) {
 #pragma unroll
       for (int i = 0; i < 8; i++) f[i] = silu(f[i]);
+    } else if (act == 2) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) f[i] = silu_fma(f[i]);
     }
     return pack8(f);
   };
@@ -222,9 +235,12 @@ __global__ void __launch_bounds__(GNS_THREADS) gn_small_kernel(const __half* __r
     unpack8(slab[r * vpr + v], f);
 #pragma unroll
     for (int i = 0; i < 8; i++) f[i] = fmaf(f[i], sc[i], sh[i]);
-    if (act) {
+    if (act == 1) {
 #pragma unroll
       for (int i = 0; i < 8; i++) f[i] = silu(f[i]);
+    } else if (act == 2) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) f[i] = silu_fma(f[i]);
     }
     *reinterpret_cast<uint4*>(yb + (int64_t)r * C) = pack8(f);
   }
@@ -703,7 +719,7 @@ void gn_apply(const __half* x, __half* y, const double* sums, int S, int64_t row
   int threads, rpb, chunks;
   gn_geometry(S, rows_per_sample, C, threads, rpb, chunks);
   gn_apply_kernel<<<dim3(chunks, S), threads, 0, st>>>(x, y, sums, gamma, beta, rows_per_sample, C, C / 32,
-                                                     (double)rows_per_sample * (C / 32), eps, rpb, silu_act ? 1 : 0);
+                                                     (double)rows_per_sample * (C / 32), eps, rpb, silu_act ? (knobs().gn_silu == 2 ? 2 : 1) : 0);
   MUDG_CUDA(cudaGetLastError());
 }
 
@@ -736,7 +752,7 @@ void gn_small(const __half* x, __half* y, int S, int64_t rows_per_sample, int C,
   const size_t smem = gn_small_smem(rows_per_sample, Cs);
   MUDG_CUDA(cudaFuncSetAttribute(gn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   gn_small_kernel<<<dim3(C / Cs, S), GNS_THREADS, smem, st>>>(x, y, gamma, beta, (int)rows_per_sample, C, C / 32, Cs, eps,
-                                                              silu_act ? 1 : 0);
+                                                              silu_act ? (knobs().gn_silu == 2 ? 2 : 1) : 0);
   MUDG_CUDA(cudaGetLastError());
 }
 

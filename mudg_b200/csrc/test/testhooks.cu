@@ -306,6 +306,7 @@ MUDG_EXPORT int mudg_test_set_knob(const char* name, int value) {
   else if (n == "gn_fuse") k.gn_fuse = value;
   else if (n == "gn_fold") k.gn_fold = value;
   else if (n == "gn_small") k.gn_small = value;
+  else if (n == "gn_silu") k.gn_silu = value;
   else if (n == "reset") k = Knobs{};
   else MUDG_REQUIRE(false, "unknown knob %s", n.c_str());
   MUDG_API_END

@@ -9,7 +9,7 @@ sys.path.insert(0, ROOT)
 
 CASES = ["flash_self_small", "flash_self_l1", "flash_self_ragged", "flash_cross", "flash_cross_else", "tattn16", "tattn4",
          "tattn64", "tattn32", "tattn64g", "tattn48", "gns_frame_c320", "gns_frame_c1280", "gns_time_c640", "gns_frame_c64", "gns_big_c1280",
-         "gn_frame", "gn_time", "ln320", "ln1280", "ln512"]
+         "gns_frame_c320_fma", "gn_frame_fma", "gn_time_fma", "gn_frame", "gn_time", "ln320", "ln1280", "ln512"]
 
 
 def ref_attn(q, k, v, heads, scale):
@@ -124,6 +124,16 @@ def run_case(name):
         torch.cuda.synchronize()
         check(L.mudg_test_set_knob(b"reset", 0))
         report(name, "cuda", O, ref)
+    elif name.endswith("_fma"):
+        # the same cases with the SiLU reciprocal on the FMA pipe (knob gn_silu = 2)
+        check(L.mudg_test_set_knob(b"gn_silu", 2))
+        try:
+            run_case(name[:-4])
+        finally:
+            check(L.mudg_test_set_knob(b"reset", 0))
+        for k in list(RESULTS):
+            if k[0] == name[:-4]:
+                RESULTS[(name,) + tuple(k[1:])] = RESULTS.pop(k)
     elif name.startswith("gns_"):
         # one-kernel GroupNorm (+ SiLU / no activation) against F.group_norm: per frame / per sample over T, several widths
         over_time = "time" in name

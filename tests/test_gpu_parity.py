@@ -69,7 +69,7 @@ def test_tapgemm(case):
                                   "flash_self_l1_s1", "flash_self_l0",
                                   "xattn_small", "xattn_ragged", "xattn_l0", "xattn_l3", "xattn_one_tile",
                                   "tattn16", "tattn4", "tattn64", "tattn32", "tattn64g", "tattn48", "gns_frame_c320", "gns_frame_c1280",
-                                  "gns_time_c640", "gns_frame_c64", "gns_big_c1280", "gn_frame", "gn_time", "ln320", "ln1280", "ln512"])
+                                  "gns_time_c640", "gns_frame_c64", "gns_big_c1280", "gns_frame_c320_fma", "gn_frame_fma", "gn_time_fma", "gn_frame", "gn_time", "ln320", "ln1280", "ln512"])
 def test_ops(case):
     import gpu_probe_ops as P
     P.RESULTS.clear()
