@@ -25,6 +25,12 @@ MUDG_EXPORT int mudg_test_next_gemm_gn(void* sums_f64, int gn_div);
  * (b*T + t) / div use matrix number that (TapGemm::wt_samples; the GroupNorm-into-proj_in fold) */
 MUDG_EXPORT int mudg_test_next_gemm_per_sample(int samples, int div);
 
+/* LayerNorm partial sums of the output of the NEXT mudg_test_tapgemm(backend 0) call: ln_out = [n_out / 64][rows] float2 the
+ * epilogue fills with each row's (sum, sum of squares) per 64-column chunk (TapGemm::ln_out; pair kernel only);
+ * mudg_test_ln_finalize reduces such planes to the [rows] (mean, rstd) a folded-LayerNorm consumer takes (eps 1e-5) */
+MUDG_EXPORT int mudg_test_next_gemm_ln(void* ln_out);
+MUDG_EXPORT int mudg_test_ln_finalize(const void* parts, int nparts, void* mean_rstd, int64_t rows, int C, void* stream);
+
 /* backend 0 = product dispatch (tcgen05), 1 = CUDA-core checker.  mode 0 linear, 1 conv 3x3, 2 temporal conv (3,1,1).
  * ln_stats ([rows] float2 mean,rstd) / ln_c1 ([N]): folded-LayerNorm epilogue (bias then carries W beta + bias), or NULL */
 MUDG_EXPORT int mudg_test_tapgemm(const void* A, int B, int T, int H, int W, int Cin, int mode, const void* Wt, int N,

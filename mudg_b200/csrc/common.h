@@ -111,8 +111,9 @@ struct Knobs {
   int gn_fuse = 1;          // GroupNorm statistics from the producing GEMM's epilogue
   int gn_silu = 1;          // SiLU of the GroupNorm apply: 1 = ex2 + rcp on the MUFU unit, 2 = ex2 + Newton reciprocal on the FMA pipe
   int gn_small = 1;         // one-kernel GroupNorm (statistics + apply from shared memory) for samples that fit
+  int ln_fuse = 1;          // LayerNorm statistics as per-chunk partial sums from the producing GEMM's epilogue (pair kernel)
   int gn_fold = 1;          // GroupNorm (no activation) folded into per-sample weights of the consuming Linear
-  int last_gemm_path = 0;   // written by tapgemm(): 2 = tc2<1>, 3 = tc2<2>, 4 = tc3; | (epi + 1) << 8 | gn fused << 16 | groups << 20
+  int last_gemm_path = 0;   // written by tapgemm(): 2 = tc2<1>, 3 = tc2<2>, 4 = tc3; | (epi + 1) << 8 | gn fused << 16 | residual by MMA << 17 | ln partials << 18 | groups << 20
 };
 Knobs& knobs();
 

@@ -621,6 +621,27 @@ __global__ void __launch_bounds__(256) ln_stats_kernel(const __half* __restrict_
   }
 }
 
+// (mean, rstd) per row from the per-64-column partial (sum, sum of squares) planes a producing GEMM's epilogue stored
+// (TapGemm::ln_out): thread per row, the planes are read coalesced (consecutive rows are consecutive float2), all loads of a
+// row issued before the first add.  Same single-sweep variance as ln_stats_kernel.
+template <int PARTS>
+__global__ void __launch_bounds__(256) ln_finalize_kernel(const float2* __restrict__ parts, float2* __restrict__ out, int64_t rows,
+                                                          int nparts, float inv_c, float eps) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float s = 0.f, q = 0.f;
+  for (int c0 = 0; c0 < nparts; c0 += PARTS) {
+    float2 v[PARTS];
+#pragma unroll
+    for (int j = 0; j < PARTS; j++) v[j] = c0 + j < nparts ? __ldg(parts + (int64_t)(c0 + j) * rows + r) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < PARTS; j++) { s += v[j].x; q += v[j].y; }
+  }
+  const float mean = s * inv_c;
+  const float var = fmaxf(q - mean * s, 0.f) * inv_c;
+  out[r] = make_float2(mean, rsqrtf(var + eps));
+}
+
 // Fold a LayerNorm's affine part into the Linear that consumes it: W[n][k] *= gamma[k] (re-rounded to fp16, in place),
 // c1[n] = sum_k fp16(W gamma), c2[n] = sum_k W[n][k] beta[k] + bias[n].  Warp per output row.
 __global__ void ln_fold_kernel(__half* __restrict__ W, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -912,6 +933,14 @@ void ln_stats(const __half* x, float2* out, int64_t rows, int C, float eps, cuda
   if (vecs <= 64) ln_stats_kernel<2, 4><<<blocks(4), wpb * 32, 0, st>>>(x, out, rows, C, eps);
   else if (vecs <= 160) ln_stats_kernel<5, 2><<<blocks(2), wpb * 32, 0, st>>>(x, out, rows, C, eps);
   else ln_stats_kernel<10, 1><<<blocks(1), wpb * 32, 0, st>>>(x, out, rows, C, eps);
+  MUDG_CUDA(cudaGetLastError());
+}
+
+void ln_finalize(const float2* parts, int nparts, float2* out, int64_t rows, int C, float eps, cudaStream_t st) {
+  MUDG_REQUIRE(nparts > 0 && nparts * 64 == C, "ln_finalize: %d partial planes for width %d", nparts, C);
+  const unsigned blocks = (unsigned)((rows + 255) / 256);
+  if (nparts % 5 == 0) ln_finalize_kernel<5><<<blocks, 256, 0, st>>>(parts, out, rows, nparts, 1.f / (float)C, eps);
+  else ln_finalize_kernel<4><<<blocks, 256, 0, st>>>(parts, out, rows, nparts, 1.f / (float)C, eps);
   MUDG_CUDA(cudaGetLastError());
 }
 

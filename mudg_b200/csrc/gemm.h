@@ -31,6 +31,12 @@ struct TapGemm {
   //   D = rstd[m] * (acc - mean[m] * ln_c1[n]) + bias[n]      with bias = W beta (+ the layer's own bias)
   const float2* ln_stats = nullptr;   // [rows] (mean, rstd)
   const float* ln_c1 = nullptr;       // [N] row sums of the gamma-scaled fp16 weight
+  // LayerNorm statistics of the OUTPUT for the LayerNorm that consumes it: REQUEST to store, per row and 64-column chunk of
+  // the output, (sum, sum of squares) of the fp32 epilogue values into ln_out [n_out / 64][rows] float2 (plain stores, every
+  // element written exactly once: deterministic, no zeroing); ln_finalize (ops.h) turns the planes into the (mean, rstd)
+  // rows a consumer takes as ln_stats -- an 8 % pass over the partials instead of ln_stats_kernel's full read of the
+  // activation.  Only the CTA-pair kernel does this: ask tapgemm_ln_out_ok() first.
+  float2* ln_out = nullptr;
   // GroupNorm statistics of the OUTPUT for the norm that consumes it (32 groups over the n_out channels): REQUEST to
   // accumulate (sum, sum of squares) per (sample, group) into gn_sums [S][32][2] fp64 (pre-zeroed) from the epilogue;
   // sample = (b*T + t) / gn_div.  tapgemm() returns whether it did (only the CTA-pair kernel does, and only when a
@@ -64,6 +70,7 @@ struct TapGemmGeneric {
 };
 
 bool tapgemm_tc_eligible(const TapGemm& g);
+bool tapgemm_ln_out_ok(const TapGemm& g);       // would tapgemm() honour g.ln_out (CTA-pair kernel, plain epilogue)?
 bool tapgemm_per_sample_ok(const TapGemm& g);   // would tapgemm() run g (with wt_samples / wt_div set) on the pair kernel, tiles inside one sample?
 bool tapgemm_tc2(const TapGemm& g, cudaStream_t st);       // persistent single-CTA kernel, or the CTA-pair kernel for large problems
 void tapgemm_generic(const TapGemmGeneric& g, cudaStream_t st);

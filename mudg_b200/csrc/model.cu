@@ -487,7 +487,7 @@ Act Model::group_norm(const Act& x, const std::string& p, float eps, bool silu, 
 // on the pair kernel with tiles inside one sample and the per-sample weights are small next to the activation; otherwise
 // the norm runs as its own pass.
 Act Model::linear_gn(const Act& x, const std::string& norm, float eps, bool over_time, const std::string& wkey,
-                     const std::string& bkey, GnReq* pre) {
+                     const std::string& bkey, GnReq* pre, LnReq* ln_out) {
   const Weight& w = ws_->W(wkey);
   const int S = over_time ? x.B : x.B * x.T;
   const int64_t rps = over_time ? (int64_t)x.T * x.H * x.W : (int64_t)x.H * x.W;
@@ -502,7 +502,7 @@ Act Model::linear_gn(const Act& x, const std::string& norm, float eps, bool over
                     (planning_ ? fold_plan_ok(g) : tapgemm_per_sample_ok(g));
   if (!fold) {
     Act n = group_norm(x, norm, eps, false, over_time, pre);
-    Act y = linear(n, wkey, bkey, nullptr);
+    Act y = linear(n, wkey, bkey, nullptr, false, 1.f, nullptr, ln_out);
     release(n);
     return y;
   }
@@ -512,6 +512,11 @@ Act Model::linear_gn(const Act& x, const std::string& norm, float eps, bool over
     pre = &own;
   }
   Act y = alloc(x.B, x.T, x.H, x.W, w.O);
+  if (ln_out && ln_plan_ok(g)) {             // LayerNorm partials of the output for the transformer block's norm1
+    ln_out->nparts = w.O / 64;
+    ln_out->parts = static_cast<float2*>(alloc_bytes(sizeof(float2) * (size_t)ln_out->nparts * x.rows()));
+    g.ln_out = ln_out->parts;
+  }
   __half* Ws = static_cast<__half*>(alloc_bytes(sizeof(__half) * (size_t)S * w.O * w.K()));
   float* cs = static_cast<float*>(alloc_bytes(sizeof(float) * (size_t)S * w.O));
   if (live()) {
@@ -549,8 +554,19 @@ Act Model::layer_norm(const Act& x, const std::string& p) {
 }
 
 // (mean, rstd) per row for a LayerNorm that has been folded into its consumer GEMM
-float2* Model::layer_norm_stats(const Act& x) {
+float2* Model::layer_norm_stats(const Act& x, LnReq* pre) {
   float2* st = static_cast<float2*>(alloc_bytes(sizeof(float2) * (size_t)x.rows()));
+  if (pre && pre->parts) {                   // the producer's epilogue has stored per-chunk partial sums: reduce those
+    MUDG_REQUIRE(pre->nparts * 64 == x.C, "LayerNorm partials: %d chunks for width %d", pre->nparts, x.C);
+    if (live()) {
+      ProfScope ps(PF_LN_STATS, 0.0, 8.0 * (double)x.rows() * (pre->nparts + 1), st_, fmt("%lldx%d:fused", (long long)x.rows(), x.C).c_str());
+      ln_finalize(pre->parts, pre->nparts, st, x.rows(), x.C, 1e-5f, st_);
+      launches++;
+    }
+    release_bytes(pre->parts);
+    pre->parts = nullptr;
+    return st;
+  }
   if (live()) {
     ProfScope ps(PF_LN_STATS, 0.0, 2.0 * (double)x.numel() + 8.0 * (double)x.rows(), st_, fmt("%lldx%d", (long long)x.rows(), x.C).c_str());
     ln_stats(x.p, st, x.rows(), x.C, 1e-5f, st_);
@@ -560,22 +576,29 @@ float2* Model::layer_norm_stats(const Act& x) {
 }
 
 Act Model::linear(const Act& x, const std::string& wkey, const std::string& bkey, const Act* residual, bool geglu,
-                  float alpha, const float2* ln) {
+                  float alpha, const float2* ln, LnReq* ln_out) {
   const Weight& w0 = ws_->W(wkey);
   MUDG_REQUIRE(w0.K() == x.C, "linear %s: K %d vs activation width %d", wkey.c_str(), w0.K(), x.C);
   const int n_out = geglu ? w0.O / 2 : w0.O;
   Act y = alloc(x.B, x.T, x.H, x.W, n_out);
+  MUDG_REQUIRE(x.rows() < (int64_t(1) << 31), "too many rows");
+  TapGemm g;
+  g.B = 1; g.T = 1; g.H = 1; g.W = (int)x.rows(); g.Cin = x.C;
+  g.ntaps = 1;
+  g.N = w0.O;
+  g.alpha = alpha; g.geglu = geglu;
+  if (ln_out && !geglu && n_out % 64 == 0 && ln_plan_ok(g)) {   // same decision in the planning walk and the live one
+    ln_out->nparts = n_out / 64;
+    ln_out->parts = static_cast<float2*>(alloc_bytes(sizeof(float2) * (size_t)ln_out->nparts * x.rows()));
+    g.ln_out = ln_out->parts;
+  }
   if (live()) {
     const Weight& w = ws_->W(wkey);
-    MUDG_REQUIRE(x.rows() < (int64_t(1) << 31), "too many rows");
-    TapGemm g;
-    g.A = x.p; g.B = 1; g.T = 1; g.H = 1; g.W = (int)x.rows(); g.Cin = x.C;
-    g.ntaps = 1;
-    g.Wt = w.w; g.N = w.O;
+    g.A = x.p;
+    g.Wt = w.w;
     g.D = y.p;
     g.R = residual ? residual->p : nullptr;
     g.bias = bkey.empty() ? nullptr : ws_->V(bkey).p;
-    g.alpha = alpha; g.geglu = geglu;
     if (ln) {                                  // folded LayerNorm: the weight already carries gamma
       g.ln_stats = ln;
       g.ln_c1 = ws_->V(wkey + ".ln_c1").p;
@@ -723,8 +746,8 @@ Act Model::res_block(const Act& x, const Layer& l, GnReq* out_gn, GnReq* in_gn) 
 }
 
 // LN3 -> GEGLU FF -> +x   (BasicTransformerBlock._forward last line, attention.py:399); consumes x
-Act Model::transformer_block_tail(Act x, const std::string& tb) {
-  float2* s3 = layer_norm_stats(x);
+Act Model::transformer_block_tail(Act x, const std::string& tb, LnReq* pre) {
+  float2* s3 = layer_norm_stats(x, pre);
   Act hid = linear(x, tb + ".ff.net.0.proj.geglu.weight", tb + ".ff.net.0.proj.geglu.bias", nullptr, true, 1.f, s3);
   release_bytes(s3);
   Act y = linear(hid, tb + ".ff.net.2.weight", tb + ".ff.net.2.bias", &x);
@@ -737,9 +760,12 @@ Act Model::spatial_transformer(const Act& xin, const Layer& l, GnReq* in_gn) {  
   const std::string& p = l.prefix;
   const std::string tb = p + ".transformer_blocks.0";
   const int C = l.ch, HW = xin.H * xin.W;
-  Act x = linear_gn(xin, p + ".norm", 1e-6f, false, p + ".proj_in.weight", p + ".proj_in.bias", in_gn);
+  // Each LayerNorm's statistics come out of the epilogue of the GEMM that produces its input (LnReq) where that GEMM runs on
+  // the pair kernel (layer_norm_stats then only reduces the partial sums); it reads the activation otherwise.
+  LnReq r1, r2, r3;
+  Act x = linear_gn(xin, p + ".norm", 1e-6f, false, p + ".proj_in.weight", p + ".proj_in.bias", in_gn, &r1);
   // attn1: self-attention over the H*W tokens of each frame
-  float2* s1 = layer_norm_stats(x);
+  float2* s1 = layer_norm_stats(x, &r1);
   Act qkv = linear(x, tb + ".attn1.qkv.weight", "", nullptr, false, 1.f, s1);
   release_bytes(s1);
   Act a1 = alloc(xin.B, xin.T, xin.H, xin.W, C);
@@ -766,13 +792,13 @@ Act Model::spatial_transformer(const Act& xin, const Layer& l, GnReq* in_gn) {  
   }
   release_bytes(vt);
   release(qkv);
-  Act x1 = linear(a1, tb + ".attn1.to_out.0.weight", tb + ".attn1.to_out.0.bias", &x);
+  const bool split = xin.B < N_;          // (the partials of a tensor that is tiled over the CFG copies below are not)
+  Act x1 = linear(a1, tb + ".attn1.to_out.0.weight", tb + ".attn1.to_out.0.bias", &x, false, 1.f, nullptr, split ? nullptr : &r2);
   release(a1);
   release(x);
   // Shared CFG prefix ends here: up to this point the `dup` copies of a sample (same latent, same t / label / fs) are
   // identical, from the first cross-attention on they differ.  Tile x1 and the block input (residual of proj_out).
   Act xin_full = xin;
-  const bool split = xin.B < N_;
   if (split) {
     Act t1 = tile_batch(x1, N_);
     release(x1);
@@ -781,7 +807,7 @@ Act Model::spatial_transformer(const Act& xin, const Layer& l, GnReq* in_gn) {  
   }
   const int F = xin_full.B * xin_full.T;
   // attn2: text (77 tokens, shared by the frames of a sample) + image tokens, separate softmaxes summed
-  float2* s2 = layer_norm_stats(x1);
+  float2* s2 = layer_norm_stats(x1, &r2);
   Act q = linear(x1, tb + ".attn2.to_q.weight", "", nullptr, false, 1.f, s2);
   release_bytes(s2);
   Act a2 = alloc(xin_full.B, xin.T, xin.H, xin.W, C);
@@ -816,10 +842,10 @@ Act Model::spatial_transformer(const Act& xin, const Layer& l, GnReq* in_gn) {  
     }
   }
   release(q);
-  Act x2 = linear(a2, tb + ".attn2.to_out.0.weight", tb + ".attn2.to_out.0.bias", &x1);
+  Act x2 = linear(a2, tb + ".attn2.to_out.0.weight", tb + ".attn2.to_out.0.bias", &x1, false, 1.f, nullptr, &r3);
   release(a2);
   release(x1);
-  Act x3 = transformer_block_tail(x2, tb);
+  Act x3 = transformer_block_tail(x2, tb, &r3);
   Act y = linear(x3, p + ".proj_out.weight", p + ".proj_out.bias", &xin_full);
   release(x3);
   if (split) release(xin_full);
@@ -830,12 +856,14 @@ Act Model::temporal_transformer(const Act& xin, const Layer& l) {   // attention
   const std::string& p = l.prefix;
   const std::string tb = p + ".transformer_blocks.0";
   const int HW = xin.H * xin.W;
-  Act x = linear_gn(xin, p + ".norm", 1e-6f, true, p + ".proj_in.weight", p + ".proj_in.bias", nullptr);
+  LnReq rq;                        // statistics of the next LayerNorm's input, from the GEMM that produces it
+  Act x = linear_gn(xin, p + ".norm", 1e-6f, true, p + ".proj_in.weight", p + ".proj_in.bias", nullptr, &rq);
   for (int k = 1; k <= 2; k++) {   // attn1 and attn2 are both self-attention over T (only_self_att)
     const std::string an = tb + ".attn" + std::to_string(k);
-    float2* sk = layer_norm_stats(x);
+    float2* sk = layer_norm_stats(x, &rq);
     Act qkv = linear(x, an + ".qkv.weight", "", nullptr, false, 1.f, sk);
     release_bytes(sk);
+    rq = LnReq{};
     Act a = alloc(xin.B, xin.T, xin.H, xin.W, l.inner);
     if (live()) {
       ProfScope ps(PF_TATTN, 4.0 * (double)xin.T * xin.T * 64.0 * l.heads * xin.B * HW, 8.0 * (double)a.numel(), st_,
@@ -844,12 +872,12 @@ Act Model::temporal_transformer(const Act& xin, const Layer& l) {   // attention
       launches++;
     }
     release(qkv);
-    Act xn = linear(a, an + ".to_out.0.weight", an + ".to_out.0.bias", &x);
+    Act xn = linear(a, an + ".to_out.0.weight", an + ".to_out.0.bias", &x, false, 1.f, nullptr, &rq);
     release(a);
     release(x);
     x = xn;
   }
-  Act x3 = transformer_block_tail(x, tb);
+  Act x3 = transformer_block_tail(x, tb, &rq);
   Act y = linear(x3, p + ".proj_out.weight", p + ".proj_out.bias", &xin);
   release(x3);
   return y;

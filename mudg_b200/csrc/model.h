@@ -191,6 +191,13 @@ class Model {
 
   // ---- ops (all no-ops apart from allocation when planning)
   // GroupNorm statistics handed from a producing conv to the norm that consumes its output
+  // LayerNorm folded into its consumer GEMM: the consumer takes (mean, rstd) per row.  They come from ln_stats (a full read
+  // of the activation), or -- where the GEMM that PRODUCES the activation runs on the pair kernel -- from per-64-column
+  // partial sums its epilogue stored (LnReq; TapGemm::ln_out), reduced by ln_finalize.
+  struct LnReq {               // handed to the linear() that PRODUCES the LayerNorm's input
+    float2* parts = nullptr;   // [nparts][rows], allocated by linear() when its GEMM will store them (pair kernel), else null
+    int nparts = 0;
+  };
   struct GnReq {
     bool over_time = false;   // statistics per sample over (C/32, T, H, W) instead of per frame
     double* sums = nullptr;   // [S][32][2] fp64 in the arena (allocated + zeroed by gn_request, released by group_norm)
@@ -199,13 +206,14 @@ class Model {
   void gn_request(GnReq& r, int S);
   Act group_norm(const Act& x, const std::string& p, float eps, bool silu, bool over_time, GnReq* pre = nullptr);
   Act linear_gn(const Act& x, const std::string& norm, float eps, bool over_time, const std::string& wkey,
-                const std::string& bkey, GnReq* pre);
+                const std::string& bkey, GnReq* pre, LnReq* ln_out = nullptr);
   // planning walks use fake pointers: the fold decision must not depend on pointer alignment
   bool fold_plan_ok(TapGemm g) { g.A = g.D = nullptr; g.Wt = nullptr; return tapgemm_per_sample_ok(g); }
   Act layer_norm(const Act& x, const std::string& p);
+  bool ln_plan_ok(TapGemm g) { g.A = g.R = nullptr; g.D = nullptr; g.Wt = nullptr; return tapgemm_ln_out_ok(g); }
   Act linear(const Act& x, const std::string& wkey, const std::string& bkey, const Act* residual, bool geglu = false,
-             float alpha = 1.f, const float2* ln = nullptr);
-  float2* layer_norm_stats(const Act& x);
+             float alpha = 1.f, const float2* ln = nullptr, LnReq* ln_out = nullptr);
+  float2* layer_norm_stats(const Act& x, LnReq* pre = nullptr);
   Act conv3x3(const Act& x, const std::string& p, const Act* residual, const float* bias2, GnReq* gn = nullptr);
   Act conv_t3(const Act& x, const std::string& p, const Act* residual, GnReq* gn = nullptr);
   Act gemm_raw(const __half* A, int M, int K, const __half* Wt, int N, const float* bias, const Act* residual, float alpha);
@@ -215,7 +223,7 @@ class Model {
   Act downsample(const Act& x, const std::string& p, int pad);
 
   Act res_block(const Act& x, const Layer& l, GnReq* out_gn = nullptr, GnReq* in_gn = nullptr);
-  Act transformer_block_tail(Act x, const std::string& p);   // LN3 + GEGLU FF + residual (consumes x)
+  Act transformer_block_tail(Act x, const std::string& p, LnReq* pre = nullptr);   // LN3 + GEGLU FF + residual (consumes x)
   Act spatial_transformer(const Act& x, const Layer& l, GnReq* in_gn = nullptr);
   Act temporal_transformer(const Act& x, const Layer& l);
   Act run_block(Act h, const Block& b, bool owns_input, GnReq* in_gn = nullptr);

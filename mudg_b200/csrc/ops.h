@@ -21,6 +21,8 @@ void gn_fold_weights(const __half* W, const double* sums, int S, int64_t rows_pe
 void layernorm(const __half* x, __half* y, const float* gamma, const float* beta, int64_t rows, int C, float eps,
                cudaStream_t st);
 void ln_stats(const __half* x, float2* out, int64_t rows, int C, float eps, cudaStream_t st);
+// the same (mean, rstd) rows from the [nparts = C / 64][rows] partial (sum, sum of squares) planes of TapGemm::ln_out
+void ln_finalize(const float2* parts, int nparts, float2* out, int64_t rows, int C, float eps, cudaStream_t st);
 void ln_fold(__half* W, const float* gamma, const float* beta, const float* bias, float* c1, float* c2, int N, int K,
              cudaStream_t st);
 // out[r] = [a[r] | b[r % rows_b]] (rows_b divides rows: a skip tensor shared by the copies of a CFG batch)

@@ -65,6 +65,8 @@ struct TcParams {
   int bias2_div, nb2, dimT;
   const float2* ln_stats;   // folded LayerNorm: per-row (mean, rstd), or null
   const float* ln_c1;       // [N]
+  float2* ln_out;           // per-row, per-64-column-chunk (sum, sum of squares) of the output [n_out / 64][ln_rows], or null
+  int64_t ln_rows;
   int8_t taps[9][4];
 };
 
@@ -134,6 +136,27 @@ __device__ __forceinline__ float gelu_as25(float g) {
   const float e = ex2_approx(g * g * -0.72134752044448170f);     // exp(-g^2 / 2)
   return fmaf(-ag * poly, e, fmaxf(g, 0.f));
 }
+
+// The same GELU with ONE MUFU op: erfc(a / sqrt 2) = 2^(-a Q(a)) for a = |g|, Q a degree-4 polynomial fitted (weighted by
+// a erfc, a in [0, 5.5], increasing beyond) to -log2(erfc(a / sqrt 2)) / a, so
+//   gelu(g) = max(g, 0) - 0.5 |g| 2^(-|g| Q(|g|)):  1 MUFU + 9 FMA-pipe instructions, max |err| 1.3e-6 over all g
+// (tests/test_oracle_golden.py::test_gelu_q4_polynomial holds the fit against erf in float64).  The GEGLU epilogues are
+// co-limited by the MUFU unit and the issue slots; the reciprocal of the 7.1.25 form was the second MUFU op per element.
+__device__ __forceinline__ float gelu_q4(float g) {
+  const float a = fabsf(g);
+  float q = fmaf(0.0005244618f, a, -0.0074173124f);
+  q = fmaf(q, a, 0.052593093f);
+  q = fmaf(q, a, 0.45923585f);
+  q = fmaf(q, a, 1.1510944f);
+  const float e = ex2_approx(-a * q);
+  return fmaf(-0.5f * a, e, fmaxf(g, 0.f));
+}
+
+#ifdef MUDG_GELU_AS25
+#define GELU gelu_as25
+#else
+#define GELU gelu_q4
+#endif
 
 struct G2Tile {
   int n0, bn, w0, h0, t0, b0;
@@ -787,8 +810,8 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 const float g1 = fmaf(__uint_as_float(g[4 * i4 + 1]), al, fmaf(k, c_g.y, b_g.y));
                 const float g2 = fmaf(__uint_as_float(g[4 * i4 + 2]), al, fmaf(k, c_g.z, b_g.z));
                 const float g3 = fmaf(__uint_as_float(g[4 * i4 + 3]), al, fmaf(k, c_g.w, b_g.w));
-                o[2 * i4] = pack_half2(v0 * gelu_as25(g0), v1 * gelu_as25(g1));
-                o[2 * i4 + 1] = pack_half2(v2 * gelu_as25(g2), v3 * gelu_as25(g3));
+                o[2 * i4] = pack_half2(v0 * GELU(g0), v1 * GELU(g1));
+                o[2 * i4 + 1] = pack_half2(v2 * GELU(g2), v3 * GELU(g3));
               }
             } else {
               const float al = p.b.alpha;
@@ -800,8 +823,8 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 const float v2 = fmaf(__uint_as_float(v[4 * i4 + 2]), al, b_v.z), v3 = fmaf(__uint_as_float(v[4 * i4 + 3]), al, b_v.w);
                 const float g0 = fmaf(__uint_as_float(g[4 * i4]), al, b_g.x), g1 = fmaf(__uint_as_float(g[4 * i4 + 1]), al, b_g.y);
                 const float g2 = fmaf(__uint_as_float(g[4 * i4 + 2]), al, b_g.z), g3 = fmaf(__uint_as_float(g[4 * i4 + 3]), al, b_g.w);
-                o[2 * i4] = pack_half2(v0 * gelu_as25(g0), v1 * gelu_as25(g1));
-                o[2 * i4 + 1] = pack_half2(v2 * gelu_as25(g2), v3 * gelu_as25(g3));
+                o[2 * i4] = pack_half2(v0 * GELU(g0), v1 * GELU(g1));
+                o[2 * i4 + 1] = pack_half2(v2 * GELU(g2), v3 * GELU(g3));
               }
             }
 #pragma unroll
@@ -864,6 +887,7 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       constexpr bool kPrefetchLd = NG == 2 && EPI >= 0 && (EPI & 4) == 0;      // (NG 3 runs at 152 registers: no room)
       uint32_t va[32], vb[32];
       if (kPrefetchLd) tmem_ld32(t_row + first * 64, va);
+      float ln_s = 0.f, ln_q = 0.f;          // LayerNorm partials of my row over the first half of the current chunk
       auto do_slice = [&](int sl, uint32_t (&v)[32], uint32_t (&vn)[32]) {
         const int hf = sl & 1;
         const int ch = first + (sl >> 1) * NG;                 // chunk: accumulator / output columns [64 ch, 64 ch + 64)
@@ -947,6 +971,19 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             f[8 * j + 0] += r0.x; f[8 * j + 1] += r0.y; f[8 * j + 2] += r1.x; f[8 * j + 3] += r1.y;
             f[8 * j + 4] += r2.x; f[8 * j + 5] += r2.y; f[8 * j + 6] += r3.x; f[8 * j + 7] += r3.y;
           }
+        }
+        if (p.b.ln_out != nullptr) {
+          // LayerNorm statistics for the consumer of this output (TapGemm::ln_out): thread == row, so a row's (sum, sum of
+          // squares) over the chunk's 64 columns are two private registers -- no shuffles, one 8-byte store per chunk
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            s0 += f[i]; q0 = fmaf(f[i], f[i], q0);
+            s1 += f[i + 1]; q1 = fmaf(f[i + 1], f[i + 1], q1);
+          }
+          if (!hf) { ln_s = s0 + s1; ln_q = q0 + q1; }
+          else if (row_ok)
+            p.b.ln_out[(int64_t)((tl.n0 >> 6) + ch) * p.b.ln_rows + pix] = make_float2(ln_s + (s0 + s1), ln_q + (q0 + q1));
         }
 #pragma unroll
         for (int j = 0; j < 4; j++)
@@ -1054,6 +1091,8 @@ TcParams make_params(const TapGemm& g) {
   p.dimT = g.T;
   p.ln_stats = g.ln_stats;
   p.ln_c1 = g.ln_c1;
+  p.ln_rows = (int64_t)g.B * g.T * g.H * g.W;
+  p.ln_out = nullptr;       // only the pair kernel produces them (tapgemm_tc3)
   for (int i = 0; i < g.ntaps; i++)
     for (int j = 0; j < 3; j++) p.taps[i][j] = g.taps[i][j];
   return p;
@@ -1107,6 +1146,13 @@ static int64_t tapgemm_boxes(const TapGemm& g, int& bw, int& bh, int& bt, int& b
   bt = pick_box(g.T, budget); budget /= bt;
   bb = budget;
   return (int64_t)((g.W + bw - 1) / bw) * ((g.H + bh - 1) / bh) * ((g.T + bt - 1) / bt) * ((g.B + bb - 1) / bb);
+}
+
+bool tapgemm_ln_out_ok(const TapGemm& g) {
+  if (!tapgemm_tc_eligible(g) || g.geglu || knobs().ln_fuse == 0) return false;
+  int bw, bh, bt, bb;
+  const int64_t m_tiles = tapgemm_boxes(g, bw, bh, bt, bb);
+  return tapgemm_pair_wanted(g, m_tiles, (g.N + G2_BN_MAX - 1) / G2_BN_MAX);
 }
 
 bool tapgemm_per_sample_ok(const TapGemm& g) {
@@ -1194,6 +1240,8 @@ bool tapgemm_tc3(const TapGemm& g, cudaStream_t st) {
   p.fd_gn = make_fastdiv(gn_div);
   p.trace = g_gemm_trace;
   p.dbg = knobs().gemm_dbg;
+  MUDG_REQUIRE(g.ln_out == nullptr || !g.geglu, "LayerNorm partials of a GEGLU output are not implemented");
+  p.b.ln_out = g.ln_out;
 
   const uint64_t C = g.Cin, No = p.b.n_out, Ktot = (uint64_t)g.ntaps * g.Cin;
   const uint64_t adims[5] = {C, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.T, (uint64_t)g.B};
@@ -1270,7 +1318,7 @@ bool tapgemm_tc3(const TapGemm& g, cudaStream_t st) {
   }
 #undef MUDG_TC3_EPI
 #undef MUDG_TC3_LAUNCH
-  knobs().last_gemm_path = 4 | ((epi + 1) << 8) | (gn_fuse ? 1 << 16 : 0) | (res_mma ? 1 << 17 : 0) | (ng << 20);
+  knobs().last_gemm_path = 4 | ((epi + 1) << 8) | (gn_fuse ? 1 << 16 : 0) | (res_mma ? 1 << 17 : 0) | (g.ln_out ? 1 << 18 : 0) | (ng << 20);
   MUDG_CUDA(cudaGetLastError());
   return gn_fuse;
 }
@@ -1287,6 +1335,7 @@ bool tapgemm_tc2(const TapGemm& g, cudaStream_t st) {
                             ((g.B + budget - 1) / budget);
     if (tapgemm_pair_wanted(g, m_tiles, (g.N + G2_BN_MAX - 1) / G2_BN_MAX)) return tapgemm_tc3(g, st);
   }
+  MUDG_REQUIRE(g.ln_out == nullptr, "LayerNorm partials need the pair kernel (check tapgemm_ln_out_ok first)");
   G2Params p{};
   p.b = make_params(g);
   int budget = BM;

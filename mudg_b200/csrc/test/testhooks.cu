@@ -307,6 +307,7 @@ MUDG_EXPORT int mudg_test_set_knob(const char* name, int value) {
   else if (n == "gn_fold") k.gn_fold = value;
   else if (n == "gn_small") k.gn_small = value;
   else if (n == "gn_silu") k.gn_silu = value;
+  else if (n == "ln_fuse") k.ln_fuse = value;
   else if (n == "reset") k = Knobs{};
   else MUDG_REQUIRE(false, "unknown knob %s", n.c_str());
   MUDG_API_END
@@ -328,6 +329,19 @@ MUDG_EXPORT int mudg_test_next_gemm_per_sample(int samples, int div) {
   g_next_ws = samples;
   g_next_wdiv = div;
   return 0;
+}
+
+// LayerNorm partials of the output of the NEXT mudg_test_tapgemm(backend 0) call: where its epilogue stores them
+// ([n_out / 64][rows] float2, TapGemm::ln_out)
+static float2* g_next_ln_out = nullptr;
+MUDG_EXPORT int mudg_test_next_gemm_ln(void* ln_out) {
+  g_next_ln_out = static_cast<float2*>(ln_out);
+  return 0;
+}
+MUDG_EXPORT int mudg_test_ln_finalize(const void* parts, int nparts, void* mean_rstd, int64_t rows, int C, void* stream) {
+  MUDG_API_BEGIN
+  ln_finalize(static_cast<const float2*>(parts), nparts, static_cast<float2*>(mean_rstd), rows, C, 1e-5f, S(stream));
+  MUDG_API_END
 }
 
 MUDG_EXPORT int mudg_test_tapgemm(const void* A, int B, int T, int H, int W, int Cin, int mode, const void* Wt, int N,
@@ -357,6 +371,9 @@ MUDG_EXPORT int mudg_test_tapgemm(const void* A, int B, int T, int H, int W, int
     g.wt_samples = g_next_ws;
     g.wt_div = g_next_wdiv;
     g_next_ws = 0;
+    g.ln_out = g_next_ln_out;
+    g_next_ln_out = nullptr;
+    MUDG_REQUIRE(g.ln_out == nullptr || tapgemm_ln_out_ok(g), "LayerNorm partials: this shape would not run on the pair kernel");
     MUDG_REQUIRE(g.wt_samples == 0 || tapgemm_per_sample_ok(g), "per-sample weights: this shape would not run on the pair kernel");
     tapgemm(g, S(stream));
   } else {

@@ -6,7 +6,8 @@ import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-os.environ["MUDG_LIB_PATH"] = os.path.join(ROOT, "mudg_b200", "libmudg_sm100_test.so")
+# (MUDG_TEST_LIB_PATH = an alternative build of the test library: A/B of two BUILDS, one process each)
+os.environ["MUDG_LIB_PATH"] = os.environ.get("MUDG_TEST_LIB_PATH") or os.path.join(ROOT, "mudg_b200", "libmudg_sm100_test.so")
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch                                                     # noqa: E402

@@ -90,7 +90,49 @@ SHAPES_DEEP = [
 ]
 
 
+def bench_lnfuse():
+    """LayerNorm statistics from the producing GEMM's epilogue (TapGemm::ln_out + ln_finalize) against the separate ln_stats
+    pass over the activation: producer without / with the partial sums, ln_stats, ln_finalize."""
+    dev = "cuda"
+    L = test_lib()
+
+    def timed(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e3
+
+    print(f"{'rows x C':16s} {'prod':>8s} {'prod+ln':>8s} {'ln_stats':>8s} {'finalize':>8s}   (us)")
+    for rows, C in ((294912, 320), (73728, 640), (18432, 1280), (4608, 1280), (40960, 320), (10240, 640)):
+        A = torch.randn(rows, C, device=dev).half()
+        R = torch.randn(rows, C, device=dev).half()
+        D = torch.empty(rows, C, device=dev).half()
+        Wp = (torch.randn(C, C, device=dev) / C ** 0.5).half()
+        bias = torch.randn(C, device=dev)
+        parts = torch.empty(C // 64, rows, 2, device=dev)
+        stats = torch.empty(rows, 2, device=dev)
+
+        def gemm(ln_out=None):
+            if ln_out is not None:
+                check(L.mudg_test_next_gemm_ln(ptr(ln_out)))
+            check(L.mudg_test_tapgemm(ptr(A), 1, 1, 1, rows, C, 0, ptr(Wp), C, ptr(D), ptr(R), ptr(bias), None,
+                                      ctypes.c_int(1), ctypes.c_int(0), ctypes.c_float(1.0), 0, None, None, 0, cur_stream()))
+        t_p = timed(lambda: gemm())
+        t_pl = timed(lambda: gemm(parts))
+        t_ln = timed(lambda: check(L.mudg_test_ln_stats(ptr(A), ptr(stats), ctypes.c_int64(rows), C, cur_stream())))
+        t_f = timed(lambda: check(L.mudg_test_ln_finalize(ptr(parts), C // 64, ptr(stats), ctypes.c_int64(rows), C, cur_stream())))
+        print(f"{rows:7d} x {C:5d} {t_p:8.1f} {t_pl:8.1f} {t_ln:8.1f} {t_f:8.1f}", flush=True)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "lnfuse":
+        return bench_lnfuse()
     dev = "cuda"
     L = test_lib()
     global SHAPES

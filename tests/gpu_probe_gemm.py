@@ -76,6 +76,10 @@ RESMMA_EXPECT = {"pair_lin_k320_res": 1, "pair_lin_n640": 1, "pair_lin_ragged": 
                  "pair_lin_k1280_res_mma": 1, "pair_conv_l1_res_mma": 1, "pair_conv_l0_res": 1, "pair_tconv_l0_res": 1,
                  "pair_lin_l2_balanced": 1, "pair_conv_l3_balanced": 1}
 PER_SAMPLE = {"pair_lin_persample_frame": 1, "pair_lin_persample_batch": 16}
+# producers whose epilogue also stores the LayerNorm partial sums of their output rows (TapGemm::ln_out), checked against
+# torch sums of the fp32 reference output, and reduced by ln_finalize to the (mean, rstd) rows a consumer GEMM takes
+LN_OUT_CASES = {"pair_lin_k320_res", "pair_lin_k320_res_epi", "pair_lin_n640", "pair_lin_ragged", "pair_lin_persample_frame",
+                "pair_lin_persample_batch", "pair_lin_l2_balanced", "pair_lin_k1280_res_mma", "pair_lin_n448"}
 PAIR_CASES = [k for k in CASES if k.startswith("pair_")]
 # cases that also request the fused GroupNorm statistics of their output: name -> frames per GroupNorm sample
 # (1 = per-frame norm, T = TemporalConvBlock norm over (C/32, T, H, W)); the conv modes flatten (B, T) like the model does
@@ -172,6 +176,10 @@ def run_case(name, backends=((1, "simt"), (0, "tc"))):
             gn_sums = torch.zeros(n_samples, 32, 2, device=dev, dtype=torch.float64)
             check(L.mudg_test_set_knob(b"gn_fuse", 2))      # also the 3-tap convs (the product only fuses 9-tap ones: slack)
             check(L.mudg_test_next_gemm_gn(ptr(gn_sums), gn_div))
+        ln_parts_out = None
+        if backend == 0 and name in LN_OUT_CASES:
+            ln_parts_out = torch.full((n_out // 64, rows, 2), float("nan"), device=dev)
+            check(L.mudg_test_next_gemm_ln(ptr(ln_parts_out)))
         if name in RESMMA_KNOB and backend == 0:
             check(L.mudg_test_set_knob(b"gemm_resmma", RESMMA_KNOB[name]))
         if os.environ.get("PROBE_BALANCE") and backend == 0:
@@ -194,6 +202,22 @@ def run_case(name, backends=((1, "simt"), (0, "tc"))):
             out["_path"] = (path & 0xffff, want_path)
             if name in RESMMA_EXPECT:
                 out["_resmma"] = ((path >> 17) & 1, RESMMA_EXPECT[name])
+            if ln_parts_out is not None:
+                # partial LayerNorm sums of the output rows against torch sums of the fp32 reference output
+                y64 = y.reshape(rows, n_out // 64, 64)
+                want = torch.stack([y64.sum(-1), (y64 * y64).sum(-1)], dim=-1).permute(1, 0, 2)
+                e = (ln_parts_out - want).abs() / (want.abs() + 1e-2 * want.abs().max())
+                nan_p = int(torch.isnan(ln_parts_out).sum())
+                rel = float(e.nan_to_num().max())
+                fin = torch.full((rows, 2), float("nan"), device=dev)
+                check(L.mudg_test_ln_finalize(ptr(ln_parts_out), n_out // 64, ptr(fin), ctypes.c_int64(rows), n_out, cur_stream()))
+                torch.cuda.synchronize()
+                y2 = y.reshape(rows, n_out)
+                mean, rstd = y2.mean(1), (y2.var(1, unbiased=False) + 1e-5).rsqrt()
+                dfin = max(float((fin[:, 0] - mean).abs().max()), float(((fin[:, 1] - rstd) / rstd).abs().max()))
+                out["_ln_out"] = (bool((path >> 18) & 1), rel, nan_p, dfin)
+                print(f"{name:18s} LayerNorm partials of the output: taken={bool((path >> 18) & 1)} max rel err {rel:.2e} nans={nan_p}; "
+                      f"ln_finalize vs torch (mean abs, rstd rel) {dfin:.2e}", flush=True)
             if gn_sums is not None:
                 # fused GroupNorm statistics against fp64 sums of the fp16 output the kernel stored
                 d64 = D.double().reshape(n_samples, -1, 32, n_out // 32)

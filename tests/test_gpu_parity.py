@@ -49,6 +49,10 @@ def test_tapgemm(case):
     path, want = out.pop("_path")
     gn = out.pop("_gn", None)
     rm = out.pop("_resmma", None)
+    lo = out.pop("_ln_out", None)
+    if lo is not None:          # per-chunk LayerNorm partial sums of the output rows, stored by the pair kernel's epilogue
+        taken, rel, nan_p, dfin = lo
+        assert taken and nan_p == 0 and rel < 2e-3 and dfin < 1e-3, (case, "LayerNorm partials of the output", lo)
     if rm is not None:          # residual added by the tensor core (identity k-steps) or by the epilogue, as the dispatch rule says
         assert rm[0] == rm[1], (case, "residual through the MMA", rm)
     if gn is not None:          # GroupNorm statistics of the output, accumulated by the pair kernel's epilogue

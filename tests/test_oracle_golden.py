@@ -193,3 +193,27 @@ def test_clip_oracle_matches_transformers_golden(golden_dir):
     assert float((p - ((x + 1) / 2 - mean) / std).abs().max()) < 1e-5
     big = torch.rand(1, 3, 448, 896) * 2 - 1
     assert float(C.clip_preprocess(big).std()) < float(C.clip_preprocess(big, antialias=False).std())
+
+
+def test_gelu_q4_polynomial():
+    """The GEGLU epilogue's one-MUFU GELU (csrc/tapgemm.cu: gelu_q4): erfc(a / sqrt 2) = 2^(-a Q(a)) with the degree-4 Q whose
+    coefficients are read from the kernel source, evaluated here in float32 in the kernel's order, against the erf GELU of
+    the reference (attention.py:31-40, F.gelu) in float64 -- far inside the fp16 resolution of the layer's output."""
+    import os
+    import re
+    import numpy as np
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "mudg_b200", "csrc", "tapgemm.cu")).read()
+    body = src[src.index("float gelu_q4(float g)"):]
+    body = body[:body.index("}")]
+    c = [np.float32(x) for x in re.findall(r"(-?\d+\.\d+(?:e-?\d+)?)f", body)][:5]
+    assert len(c) == 5 and abs(c[4] - 1.1510944) < 1e-6, c
+    g = np.concatenate([np.linspace(-12, 12, 400001), np.linspace(-300, 300, 6001)]).astype(np.float32)
+    a = np.abs(g)
+    q = (c[0] * a + c[1]).astype(np.float32)
+    for k in (2, 3, 4):
+        q = (q * a + c[k]).astype(np.float32)
+    e = np.exp2((-a * q).astype(np.float32)).astype(np.float32)
+    out = (np.float32(-0.5) * a * e + np.maximum(g, np.float32(0))).astype(np.float64)
+    want = torch.nn.functional.gelu(torch.from_numpy(g.astype(np.float64))).numpy()
+    assert np.isfinite(out).all()
+    assert np.abs(out - want).max() < 3e-6, np.abs(out - want).max()
