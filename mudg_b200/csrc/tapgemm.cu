@@ -111,37 +111,12 @@ struct G2Params {
   int alpha_is_one;
 };
 
-__device__ __forceinline__ float erf_fast(float x) {   // Abramowitz-Stegun 7.1.26, |err| <= 1.5e-7
-  const float ax = fabsf(x);
-  const float t = __fdividef(1.f, fmaf(0.3275911f, ax, 1.f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float y = 1.f - poly * t * __expf(-ax * ax);
-  return copysignf(y, x);
-}
-__device__ __forceinline__ float gelu_fast(float x) { return 0.5f * x * (1.f + erf_fast(x * 0.70710678118654752f)); }
-
-// gelu(g) = 0.5 g (1 + erf(g / sqrt 2)) with erf from Abramowitz-Stegun 7.1.25 (|err| <= 2.5e-5, far below the fp16
-// resolution of the output):  erf(x) = 1 - (a1 t + a2 t^2 + a3 t^3) exp(-x^2),  t = 1 / (1 + 0.47047 x),  x >= 0, so
-// gelu(g) = max(g, 0) - |g| * (0.5 P(t)) * exp(-g^2 / 2):  2 MUFU + 9 FMA-pipe instructions per element.
-__device__ __forceinline__ float gelu_as25(float g) {
-  const float ag = fabsf(g);
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(ag, 0.47047f * 0.70710678118654752f, 1.f)));
-  float poly = fmaf(0.5f * 0.7478556f, t, 0.5f * -0.0958798f);
-  poly = fmaf(poly, t, 0.5f * 0.3480242f);
-  poly *= t;
-  const float e = ex2_approx(g * g * -0.72134752044448170f);     // exp(-g^2 / 2)
-  return fmaf(-ag * poly, e, fmaxf(g, 0.f));
-}
-
-// The same GELU with ONE MUFU op: erfc(a / sqrt 2) = 2^(-a Q(a)) for a = |g|, Q a degree-4 polynomial fitted (weighted by
-// a erfc, a in [0, 5.5], increasing beyond) to -log2(erfc(a / sqrt 2)) / a, so
+// gelu(g) = 0.5 g (1 + erf(g / sqrt 2)) with ONE MUFU op: erfc(a / sqrt 2) = 2^(-a Q(a)) for a = |g|, Q a degree-4 polynomial
+// fitted (weighted by a erfc, a in [0, 5.5], increasing beyond) to -log2(erfc(a / sqrt 2)) / a, so
 //   gelu(g) = max(g, 0) - 0.5 |g| 2^(-|g| Q(|g|)):  1 MUFU + 9 FMA-pipe instructions, max |err| 1.3e-6 over all g
 // (tests/test_oracle_golden.py::test_gelu_q4_polynomial holds the fit against erf in float64).  The GEGLU epilogues are
-// co-limited by the MUFU unit and the issue slots; the reciprocal of the 7.1.25 form was the second MUFU op per element.
+// co-limited by the MUFU unit and the issue slots: the Abramowitz-Stegun 7.1.25 form used before (t = 1 / (1 + p a), cubic in
+// t, times exp(-a^2 / 2): 2 MUFU ops, |err| 2.5e-5) made the level-0 GEGLU GEMM 6 % slower (profiles/r2_gelu_q4_ab.log).
 __device__ __forceinline__ float gelu_q4(float g) {
   const float a = fabsf(g);
   float q = fmaf(0.0005244618f, a, -0.0074173124f);
@@ -151,12 +126,6 @@ __device__ __forceinline__ float gelu_q4(float g) {
   const float e = ex2_approx(-a * q);
   return fmaf(-0.5f * a, e, fmaxf(g, 0.f));
 }
-
-#ifdef MUDG_GELU_AS25
-#define GELU gelu_as25
-#else
-#define GELU gelu_q4
-#endif
 
 struct G2Tile {
   int n0, bn, w0, h0, t0, b0;
@@ -340,8 +309,8 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const float v2 = fmaf(__uint_as_float(v[4 * i4 + 2]), al, b_v.z + s_v.z), v3 = fmaf(__uint_as_float(v[4 * i4 + 3]), al, b_v.w + s_v.w);
             const float g0 = fmaf(__uint_as_float(g[4 * i4]), al, b_g.x + s_g.x), g1 = fmaf(__uint_as_float(g[4 * i4 + 1]), al, b_g.y + s_g.y);
             const float g2 = fmaf(__uint_as_float(g[4 * i4 + 2]), al, b_g.z + s_g.z), g3 = fmaf(__uint_as_float(g[4 * i4 + 3]), al, b_g.w + s_g.w);
-            o[2 * i4] = pack_half2(v0 * gelu_fast(g0), v1 * gelu_fast(g1));
-            o[2 * i4 + 1] = pack_half2(v2 * gelu_fast(g2), v3 * gelu_fast(g3));
+            o[2 * i4] = pack_half2(v0 * gelu_q4(g0), v1 * gelu_q4(g1));
+            o[2 * i4 + 1] = pack_half2(v2 * gelu_q4(g2), v3 * gelu_q4(g3));
           }
 #pragma unroll
           for (int j = 0; j < 4; j++)
@@ -810,8 +779,8 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 const float g1 = fmaf(__uint_as_float(g[4 * i4 + 1]), al, fmaf(k, c_g.y, b_g.y));
                 const float g2 = fmaf(__uint_as_float(g[4 * i4 + 2]), al, fmaf(k, c_g.z, b_g.z));
                 const float g3 = fmaf(__uint_as_float(g[4 * i4 + 3]), al, fmaf(k, c_g.w, b_g.w));
-                o[2 * i4] = pack_half2(v0 * GELU(g0), v1 * GELU(g1));
-                o[2 * i4 + 1] = pack_half2(v2 * GELU(g2), v3 * GELU(g3));
+                o[2 * i4] = pack_half2(v0 * gelu_q4(g0), v1 * gelu_q4(g1));
+                o[2 * i4 + 1] = pack_half2(v2 * gelu_q4(g2), v3 * gelu_q4(g3));
               }
             } else {
               const float al = p.b.alpha;
@@ -823,8 +792,8 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 const float v2 = fmaf(__uint_as_float(v[4 * i4 + 2]), al, b_v.z), v3 = fmaf(__uint_as_float(v[4 * i4 + 3]), al, b_v.w);
                 const float g0 = fmaf(__uint_as_float(g[4 * i4]), al, b_g.x), g1 = fmaf(__uint_as_float(g[4 * i4 + 1]), al, b_g.y);
                 const float g2 = fmaf(__uint_as_float(g[4 * i4 + 2]), al, b_g.z), g3 = fmaf(__uint_as_float(g[4 * i4 + 3]), al, b_g.w);
-                o[2 * i4] = pack_half2(v0 * GELU(g0), v1 * GELU(g1));
-                o[2 * i4 + 1] = pack_half2(v2 * GELU(g2), v3 * GELU(g3));
+                o[2 * i4] = pack_half2(v0 * gelu_q4(g0), v1 * gelu_q4(g1));
+                o[2 * i4 + 1] = pack_half2(v2 * gelu_q4(g2), v3 * gelu_q4(g3));
               }
             }
 #pragma unroll
@@ -937,7 +906,18 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 32; i++) f[i] *= p.b.alpha;
         }
-        if (f_ln) {
+        if (f_ln && f_bias) {
+          // folded LayerNorm + its bias (c2) as two FMAs per element: rstd * acc + (k * c1[n] + c2[n]),  k = -mean * rstd
+          const float4* cp = reinterpret_cast<const float4*>(p.b.ln_c1 + col0);
+          const float4* bp = reinterpret_cast<const float4*>(p.b.bias + col0);
+          const float k = -ln_ms.x * ln_ms.y;
+#pragma unroll
+          for (int i4 = 0; i4 < 8; i4++) {
+            const float4 c4 = __ldg(cp + i4), b4 = __ldg(bp + i4);
+            f[4 * i4] = fmaf(f[4 * i4], ln_ms.y, fmaf(k, c4.x, b4.x)); f[4 * i4 + 1] = fmaf(f[4 * i4 + 1], ln_ms.y, fmaf(k, c4.y, b4.y));
+            f[4 * i4 + 2] = fmaf(f[4 * i4 + 2], ln_ms.y, fmaf(k, c4.z, b4.z)); f[4 * i4 + 3] = fmaf(f[4 * i4 + 3], ln_ms.y, fmaf(k, c4.w, b4.w));
+          }
+        } else if (f_ln) {
           const float4* cp = reinterpret_cast<const float4*>(p.b.ln_c1 + col0);
           const float k = -ln_ms.x * ln_ms.y;
 #pragma unroll
@@ -947,7 +927,7 @@ tapgemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             f[4 * i4 + 2] = fmaf(f[4 * i4 + 2], ln_ms.y, k * c4.z); f[4 * i4 + 3] = fmaf(f[4 * i4 + 3], ln_ms.y, k * c4.w);
           }
         }
-        if (f_bias) {
+        if (f_bias && !f_ln) {
           const float4* bp = reinterpret_cast<const float4*>(p.b.bias + col0);
 #pragma unroll
           for (int i4 = 0; i4 < 8; i4++) {
