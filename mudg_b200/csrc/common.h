@@ -109,7 +109,7 @@ struct Knobs {
   int flash_split = 0;      // softmax warps per TMEM lane quarter: 0 heuristic (2 for self-attention over >= 512 keys), 1 | 2 forced
   int tattn_generic = 0;    // force the generic-T temporal attention kernel for T == 16
   int gn_fuse = 1;          // GroupNorm statistics from the producing GEMM's epilogue
-  int gn_silu = 1;          // SiLU of the GroupNorm apply: 1 = ex2 + rcp on the MUFU unit, 2 = ex2 + Newton reciprocal on the FMA pipe
+  int gn_silu = 3;          // SiLU of the GroupNorm apply: 3 = h + h tanh(h) through MUFU.TANH (one MUFU op), 1 = ex2 + rcp (two), 2 = ex2 + Newton reciprocal on the FMA pipe
   int gn_small = 1;         // one-kernel GroupNorm (statistics + apply from shared memory) for samples that fit
   int ln_fuse = 1;          // LayerNorm statistics as per-chunk partial sums from the producing GEMM's epilogue (pair kernel)
   int gn_fold = 1;          // GroupNorm (no activation) folded into per-sample weights of the consuming Linear

@@ -37,6 +37,19 @@ __device__ __forceinline__ float silu_fma(float x) {
   return x * r;
 }
 
+// The default: one MUFU op and three instructions, silu(x) = h + h tanh(h), h = x / 2 (MUFU.TANH).  PTX only promises
+// 2^-11 relative for tanh.approx, which the cancellation in 1 + tanh(h) could turn into 5e-4 |h| absolute for negative
+// inputs; MEASURED against float64 on a level-0 tensor (tests/gpu_probe_silu.py, profiles/r2_silu_tanh.log) the fp16 output
+// differs from the exact SiLU by 7.372e-5 on average against 7.371e-5 for fp16 rounding alone, and by at most 7.1e-5 for
+// inputs below -2: the unit is far better than its bound near saturation.  gn_apply was co-limited by the MUFU unit (XU 66 %
+// with ex2 + rcp); forward -0.9 %.
+__device__ __forceinline__ float silu_tanh(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
 // ---------------------------------------------------------------- GroupNorm statistics
 // x: [S samples][R rows][C]; sums: [S][32][2] doubles (sum, sum of squares), pre-zeroed.
 // block = (C/8) x rows_per_iter threads; a thread owns one 8-channel vector column and strides over rows,
@@ -147,6 +160,9 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict
     } else if (act == 2) {
 #pragma unroll
       for (int i = 0; i < 8; i++) f[i] = silu_fma(f[i]);
+    } else if (act == 3) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) f[i] = silu_tanh(f[i]);
     }
     return pack8(f);
   };
@@ -241,6 +257,9 @@ __global__ void __launch_bounds__(GNS_THREADS) gn_small_kernel(const __half* __r
     } else if (act == 2) {
 #pragma unroll
       for (int i = 0; i < 8; i++) f[i] = silu_fma(f[i]);
+    } else if (act == 3) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) f[i] = silu_tanh(f[i]);
     }
     *reinterpret_cast<uint4*>(yb + (int64_t)r * C) = pack8(f);
   }
@@ -740,7 +759,7 @@ void gn_apply(const __half* x, __half* y, const double* sums, int S, int64_t row
   int threads, rpb, chunks;
   gn_geometry(S, rows_per_sample, C, threads, rpb, chunks);
   gn_apply_kernel<<<dim3(chunks, S), threads, 0, st>>>(x, y, sums, gamma, beta, rows_per_sample, C, C / 32,
-                                                     (double)rows_per_sample * (C / 32), eps, rpb, silu_act ? (knobs().gn_silu == 2 ? 2 : 1) : 0);
+                                                     (double)rows_per_sample * (C / 32), eps, rpb, silu_act ? knobs().gn_silu : 0);
   MUDG_CUDA(cudaGetLastError());
 }
 
@@ -773,7 +792,7 @@ void gn_small(const __half* x, __half* y, int S, int64_t rows_per_sample, int C,
   const size_t smem = gn_small_smem(rows_per_sample, Cs);
   MUDG_CUDA(cudaFuncSetAttribute(gn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   gn_small_kernel<<<dim3(C / Cs, S), GNS_THREADS, smem, st>>>(x, y, gamma, beta, (int)rows_per_sample, C, C / 32, Cs, eps,
-                                                              silu_act ? (knobs().gn_silu == 2 ? 2 : 1) : 0);
+                                                              silu_act ? knobs().gn_silu : 0);
   MUDG_CUDA(cudaGetLastError());
 }
 
